@@ -1,0 +1,166 @@
+"""The CPU oracle (oracle/) against fixtures produced by the UNMODIFIED reference.
+
+Fixtures come from oracle/make_golden.py (reference run under oracle/refshim.py) and include the
+reference's own golden vector (reference tests/test_drt_fit.py:55-141).  No GPU needed.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+from oracle import drt_oracle as orc
+from oracle.coneqp import coneqp_orthant
+
+
+@pytest.fixture(scope='module')
+def tables(lookup_golden):
+    return lookup_golden
+
+
+def test_lookup_tables_match_reference(lookup_golden):
+    tab = orc.lookup_tables(float(lookup_golden['eps']))
+    for key in ('re_x', 're_v', 'im_x', 'im_v', 'resp_x', 'resp_v'):
+        assert rel_err(tab[key], lookup_golden[key]) < 1e-13, key
+
+
+def test_matrix_builders_match_reference(tables):
+    m = load_golden('matrices.npz')
+    eps = float(m['eps'])
+    for part in ('real', 'imag'):
+        got = orc.impedance_matrix(m['f_irreg'], m['tau_irreg'], eps, part, 'interp', tables)
+        assert rel_err(got, m[f'irreg_interp_{part}']) < 1e-13
+        got = orc.impedance_matrix(m['f_irreg'], m['tau_irreg'], eps, part, 'trapz')
+        assert rel_err(got, m[f'irreg_trapz_{part}']) < 1e-13
+    args = (m['tau_resp'], m['t_resp'], m['step_times'], m['step_sizes'], eps)
+    assert rel_err(orc.response_matrix(*args, 'interp', tables), m['resp_interp']) < 1e-13
+    assert rel_err(orc.response_matrix(*args, 'trapz'), m['resp_trapz']) < 1e-13
+    for k in range(3):
+        assert rel_err(orc.penalty_matrix(np.log(m['tau_irreg']), k, eps), m[f'pen_irreg_{k}']) < 1e-13
+        assert rel_err(orc.penalty_matrix(np.log(m['tau_c2']), k, eps), m[f'pen_c2_{k}']) < 1e-13
+    assert rel_err(orc.eis_vmm(m['f_irreg']), m['vmm_irreg']) < 1e-13
+    assert rel_err(orc.eis_vmm(m['f_irreg'], structure='uniform'), m['vmm_uniform']) < 1e-13
+
+
+def test_reference_golden_vector(tables):
+    """The hard-coded expectations of the reference's tests/test_drt_fit.py, same tolerance."""
+    c1 = load_golden('c1_golden.npz')
+    prep = orc.EisPrep(c1['freq'], tables=tables)
+    assert rel_err(prep.zm, c1['zm']) < 1e-13
+    assert rel_err(prep.rm, c1['rm']) < 1e-13
+    assert rel_err(prep.vmm, c1['vmm']) < 1e-13
+    for k in range(3):
+        assert rel_err(prep.pen[k], c1[f'm{k}']) < 1e-13
+    res = prep.fit(c1['z'])
+    p = res['params']
+    assert np.allclose(c1['expected_x'], p['x'])                      # np.allclose as in the reference test
+    assert np.allclose(c1['expected_R_inf'], p['R_inf'])
+    assert np.allclose(c1['expected_inductance'], p['inductance'])
+    assert np.allclose(c1['expected_z_sigma_tot'], p['z_sigma_tot'])
+    assert np.allclose(c1['expected_q_vector'], res['q_vector'])
+    # and against the reference run here, to far tighter tolerance
+    assert res['n_outer'] == int(c1['n_outer'])
+    assert list(res['ipm_iters']) == list(c1['qp_log'])
+    assert rel_err(res['x'], c1['cvx_x']) < 1e-9
+    assert rel_err(res['weights'], c1['weights']) < 1e-9
+    assert rel_err(res['p_matrix'], c1['p_matrix']) < 1e-9
+    assert rel_err(prep.predict_z(p), c1['z_pred']) < 1e-9
+
+
+def test_c2_spectra_match_reference(tables):
+    c2 = load_golden('c2_eis.npz')
+    prep = orc.EisPrep(c2['freq'], tables=tables)
+    for b in range(c2['z'].shape[0]):
+        res = prep.fit(c2['z'][b])
+        assert res['n_outer'] == int(c2['n_outer'][b])
+        assert int(res['ipm_iters'].sum()) == int(c2['qp_log_total'][b])
+        assert rel_err(res['x'], c2['cvx_x'][b]) < 1e-9
+        assert rel_err(res['weights'], c2['weights'][b]) < 1e-9
+        assert abs(res['fun'] - c2['hist_fun_last'][b]) <= 1e-9 * abs(c2['hist_fun_last'][b])
+
+
+def test_free_sign_fit_matches_reference(tables):
+    g = load_golden('c2_free.npz')
+    prep = orc.EisPrep(g['freq'], tables=tables, nonneg=False)
+    res = prep.fit(g['z'])
+    assert res['n_outer'] == int(g['n_outer'])
+    assert rel_err(res['x'], g['cvx_x']) < 1e-9
+
+
+def test_trapz_mode_fit_matches_reference():
+    g = load_golden('c2_trapz_fit.npz')
+    prep = orc.EisPrep(g['freq'], mode='trapz')
+    res = prep.fit(g['z'])
+    assert res['n_outer'] == int(g['n_outer'])
+    assert rel_err(res['x'], g['cvx_x']) < 1e-9
+
+
+def test_dop_matches_reference():
+    d = load_golden('dop.npz')
+    nu_eps = float(d['nu_epsilon'])
+    assert rel_err(orc.dop_z_matrix(d['freq'], d['basis_nu'], nu_eps), d['zm_dop']) < 1e-13
+    scale = orc.dop_scale_vector(d['basis_nu'], d['basis_tau']) / (np.sqrt(np.pi) / nu_eps)
+    assert rel_err(scale, d['dop_scale_vector']) < 1e-13
+    n = d['rm'].shape[1]
+    b = 1
+    prob = dict(rm=d['rm'], rv=d['rv'][b], vmm=orc.eis_vmm(d['freq']), pen=[d['m0'], d['m1'], d['m2']],
+                h=np.zeros(n), l1=np.zeros(n), n_special=52, dop_range=(2, 52))
+    res = orc.qphb_fit(prob)
+    assert res['n_outer'] == int(d['n_outer'][b])
+    assert int(res['ipm_iters'].sum()) == int(d['qp_log_total'][b])
+    assert rel_err(res['x'], d['cvx_x'][b]) < 1e-8
+    assert rel_err(res['dop_rho'], d['dop_rho_vector'][b]) < 1e-8
+
+
+def _layout_pen(tau, eps, diag):
+    ns = len(diag)
+    n = ns + tau.size
+    pen = []
+    for k in range(3):
+        mk = np.zeros((n, n))
+        mk[np.arange(ns), np.arange(ns)] = diag
+        mk[ns:, ns:] = orc.penalty_matrix(np.log(tau), k, eps)
+        pen.append(mk)
+    return pen
+
+
+def test_hybrid_matches_reference(tables):
+    hs = load_golden('hybrid_small.npz')
+    eps = float(tables['eps'])
+    rm0 = hs['rm'].copy()
+    rm0[:, 1] = 0                                   # vz_offset column starts at zero (drt1d.py:5809)
+    n = rm0.shape[1]
+    nc = hs['times'].size
+    pen = _layout_pen(hs['basis_tau'], eps, [1e-6, 1.0, 1e-6, 1e-6])
+    h = np.zeros(n)
+    h[:2] = 1000                                    # v_baseline, vz_offset unbounded (qphb.py:530-533)
+    prob = dict(rm=rm0, rv=hs['rv'], vmm=dict(n_chrono=nc, chrono=None, eis=orc.eis_vmm(hs['freq'])),
+                pen=pen, h=h, l1=np.zeros(n), n_special=4, vz_index=1, vb_range=(0, 1),
+                vz_strength=hs['vz_strength_vec'], n_chrono=nc)
+    res = orc.qphb_fit(prob)
+    assert res['n_outer'] == int(hs['n_outer'])
+    assert list(res['ipm_iters']) == list(hs['qp_log'])
+    assert rel_err(res['x'], hs['cvx_x']) < 1e-8
+    assert rel_err(res['weights'], hs['weights']) < 1e-8
+    assert rel_err(res['rm_final'], hs['rm']) < 1e-10
+
+
+def test_chrono_matches_reference(tables):
+    cs = load_golden('chrono_small.npz')
+    eps = float(tables['eps'])
+    rm = cs['rm']
+    n_rows, n = rm.shape
+    pen = _layout_pen(cs['basis_tau'], eps, [1e-6, 1e-6, 1e-6])
+    h = np.zeros(n)
+    h[0] = 1000
+    prob = dict(rm=rm, rv=cs['rv'], vmm=dict(n_chrono=n_rows, chrono=None, eis=None), pen=pen, h=h,
+                l1=np.zeros(n), n_special=3, n_chrono=n_rows)
+    res = orc.qphb_fit(prob)
+    assert res['n_outer'] == int(cs['n_outer'])
+    assert rel_err(res['x'], cs['cvx_x']) < 1e-8
+
+
+def test_coneqp_small_kat():
+    """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
+    c = np.array([1.0, -2.0, 0.5, -0.1])
+    res = coneqp_orthant(np.eye(4), -c, np.zeros(4))
+    assert res['status'] == 'optimal'
+    assert np.allclose(res['x'], np.maximum(c, 0), atol=1e-6)
