@@ -1,0 +1,433 @@
+// Response-matrix builders (reference: hybdrt/matrices/{basis,mat1d,phasance}.py).
+//
+// All outputs are written with coalesced stores, one CTA per (grid, row-tile); the frequency / time
+// and tau vectors of the grid are staged in shared memory once per CTA.  Interp-mode kernels are
+// HBM-write bound (2 table loads + ~10 flops per 16 bytes stored); trapz-mode kernels are
+// exp-throughput bound (1000 integrand evaluations per entry, one warp per entry).
+#include "common.cuh"
+
+namespace hdrt {
+
+constexpr int kMThreads = 256;
+
+// numpy.linspace(start, stop, num)[i]
+__device__ __forceinline__ double linspace_at(double start, double stop, int num, int i) {
+    if (i == num - 1) return stop;
+    const double step = (stop - start) / (double)(num - 1);
+    return __dadd_rn(__dmul_rn((double)i, step), start);
+}
+
+// Gaussian RBF, basis.py:93-95
+__device__ __forceinline__ double rbf(double y, double eps) {
+    const double t = eps * y;
+    return exp(-(t * t));
+}
+
+// integrands, basis.py:562-570 and :616-618.  kind 0 = Re z, 1 = Im z, 2 = step response
+__device__ __forceinline__ double integrand(int kind, double y, double arg, double eps) {
+    if (kind == 0) return rbf(y, eps) / (1.0 + exp(2.0 * (y + arg)));
+    if (kind == 1) return -rbf(y, eps) * exp(y) * exp(arg) / (1.0 + exp(2.0 * (y + arg)));
+    return rbf(y, eps) * (1.0 - exp(-arg / exp(y)));
+}
+
+// np.trapezoid(f(y), x=y) over y = linspace(-20, 20, quad_points); one warp cooperates.
+// For kind 0/1 `arg` is ln(omega tau); for kind 2 it is dt/tau.
+__device__ double warp_trapz(int kind, double arg, double eps, int quad_points) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i = lane; i < quad_points - 1; i += 32) {
+        const double y0 = linspace_at(-20.0, 20.0, quad_points, i);
+        const double y1 = linspace_at(-20.0, 20.0, quad_points, i + 1);
+        const double f0 = integrand(kind, y0, arg, eps);
+        const double f1 = integrand(kind, y1, arg, eps);
+        acc += (y1 - y0) * (f1 + f0) / 2.0;
+    }
+    return warp_sum(acc);
+}
+
+// numpy.interp(x, gx, gv) with edge clamping (numpy/_core/src/multiarray/compiled_base.c)
+__device__ __forceinline__ double interp_clamped(double x, const double* __restrict__ gx,
+                                                 const double* __restrict__ gv, int npts) {
+    if (isnan(x)) return x;
+    const double x0 = __ldg(gx), xn = __ldg(gx + npts - 1);
+    if (x > xn) return __ldg(gv + npts - 1);
+    if (x < x0) return __ldg(gv);
+    int j = (int)((x - x0) / (xn - x0) * (double)(npts - 1));
+    j = max(0, min(npts - 1, j));
+    while (j > 0 && __ldg(gx + j) > x) --j;
+    while (j < npts - 1 && __ldg(gx + j + 1) <= x) ++j;
+    if (j == npts - 1) return __ldg(gv + j);
+    const double xj = __ldg(gx + j), vj = __ldg(gv + j);
+    if (xj == x) return vj;
+    const double slope = (__ldg(gv + j + 1) - vj) / (__ldg(gx + j + 1) - xj);
+    return __dadd_rn(__dmul_rn(slope, x - xj), vj);
+}
+
+// ---- lookup tables (basis.py:648-689): one warp per table entry ---------------------------------
+__global__ void lookup_kernel(double eps, int grid_points, int quad_points, double* re_x, double* re_v,
+                              double* im_x, double* im_v, double* td_x, double* td_v) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= 3 * grid_points) return;
+    const int table = warp / grid_points, i = warp - table * grid_points;
+    double lo, hi;
+    if (table == 0) { lo = -2.7; hi = 2.7; }
+    else if (table == 1) { lo = -5.4; hi = 5.4; }   // im_lim = re_lim * 2
+    else { lo = -6.0; hi = 2.0; }
+    const double g = pow(10.0, linspace_at(lo, hi, grid_points, i));  // np.logspace
+    const double lg = log(g);
+    const double val = warp_trapz(table, table == 2 ? g : lg, eps, quad_points);
+    if (lane == 0) {
+        double* gx = table == 0 ? re_x : (table == 1 ? im_x : td_x);
+        double* gv = table == 0 ? re_v : (table == 1 ? im_v : td_v);
+        gx[i] = lg;
+        gv[i] = val;
+    }
+}
+
+// ---- impedance matrix (mat1d.py:212-374) ---------------------------------------------------------
+// grid.x = n_grids, grid.y = row tiles.  freq/tau staged in shared memory.
+__global__ void impedance_interp_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int nf,
+                                        int nb, const double* __restrict__ re_x, const double* __restrict__ re_v,
+                                        const double* __restrict__ im_x, const double* __restrict__ im_v,
+                                        int npts, double* __restrict__ a_re, double* __restrict__ a_im,
+                                        int rows_per_cta) {
+    extern __shared__ double sm[];
+    double* s_tau = sm;
+    double* s_om = sm + nb;
+    const int g = blockIdx.x;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int rows = min(rows_per_cta, nf - r0);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_tau[i] = tau[(size_t)g * nb + i];
+    for (int i = threadIdx.x; i < rows; i += blockDim.x)
+        s_om[i] = freq[(size_t)g * nf + r0 + i] * 2.0 * 3.141592653589793;  // frequencies * 2 * np.pi
+    __syncthreads();
+    const size_t base = ((size_t)g * nf + r0) * nb;
+    for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
+        const int rr = idx / nb, m = idx - rr * nb;
+        const double x = log(s_om[rr] * s_tau[m]);
+        a_re[base + idx] = interp_clamped(x, re_x, re_v, npts);
+        a_im[base + idx] = interp_clamped(x, im_x, im_v, npts);
+    }
+}
+
+// trapz mode: one warp per entry, both parts
+__global__ void impedance_trapz_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int n_grids,
+                                       int nf, int nb, double eps, int quad_points, double* __restrict__ a_re,
+                                       double* __restrict__ a_im) {
+    const long long total = (long long)n_grids * nf * nb;
+    const int lane = threadIdx.x & 31;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total;
+         e += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int m = (int)(e % nb);
+        const long long gf = e / nb;
+        const int g = (int)(gf / nf);
+        const double om = freq[gf] * 2.0 * 3.141592653589793;
+        const double x = log(om * tau[(size_t)g * nb + m]);
+        const double vr = warp_trapz(0, x, eps, quad_points);
+        const double vi = warp_trapz(1, x, eps, quad_points);
+        if (lane == 0) { a_re[e] = vr; a_im[e] = vi; }
+    }
+}
+
+// ---- step-response matrix (mat1d.py:16-122) ------------------------------------------------------
+__global__ void response_interp_kernel(const double* __restrict__ times, const double* __restrict__ tau,
+                                       const double* __restrict__ step_times, const double* __restrict__ step_sizes,
+                                       int nt, int nb, int n_steps, const double* __restrict__ td_x,
+                                       const double* __restrict__ td_v, int npts, double* __restrict__ rm,
+                                       int rows_per_cta) {
+    extern __shared__ double sm[];
+    double* s_tau = sm;
+    double* s_t = sm + nb;
+    double* s_st = s_t + rows_per_cta;
+    double* s_sa = s_st + n_steps;
+    const int g = blockIdx.x;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int rows = min(rows_per_cta, nt - r0);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_tau[i] = tau[(size_t)g * nb + i];
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_t[i] = times[(size_t)g * nt + r0 + i];
+    for (int i = threadIdx.x; i < n_steps; i += blockDim.x) {
+        s_st[i] = step_times[(size_t)g * n_steps + i];
+        s_sa[i] = step_sizes[(size_t)g * n_steps + i];
+    }
+    __syncthreads();
+    const size_t base = ((size_t)g * nt + r0) * nb;
+    for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
+        const int rr = idx / nb, m = idx - rr * nb;
+        const double t = s_t[rr];
+        double acc = 0.0;
+        for (int k = 0; k < n_steps; ++k) {
+            if (t > s_st[k]) {
+                const double x = log((t - s_st[k]) / s_tau[m]);
+                acc += __dmul_rn(interp_clamped(x, td_x, td_v, npts), s_sa[k]);
+            }
+        }
+        rm[base + idx] = acc;
+    }
+}
+
+__global__ void response_trapz_kernel(const double* __restrict__ times, const double* __restrict__ tau,
+                                      const double* __restrict__ step_times, const double* __restrict__ step_sizes,
+                                      int n_grids, int nt, int nb, int n_steps, double eps, int quad_points,
+                                      double* __restrict__ rm) {
+    const long long total = (long long)n_grids * nt * nb;
+    const int lane = threadIdx.x & 31;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total;
+         e += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int m = (int)(e % nb);
+        const long long gt = e / nb;
+        const int g = (int)(gt / nt);
+        const double t = times[gt];
+        const double tm = tau[(size_t)g * nb + m];
+        double acc = 0.0;
+        for (int k = 0; k < n_steps; ++k) {
+            const double st = step_times[(size_t)g * n_steps + k];
+            if (t > st) acc += __dmul_rn(warp_trapz(2, (t - st) / tm, eps, quad_points), step_sizes[(size_t)g * n_steps + k]);
+        }
+        if (lane == 0) rm[e] = acc;
+    }
+}
+
+// ---- derivative penalty matrices (mat1d.py:125-209, basis.py:382-395) ----------------------------
+__global__ void penalty_kernel(const double* __restrict__ grid, int n_grids, int nb, double eps, int toeplitz,
+                               double* __restrict__ m) {
+    const long long per = (long long)nb * nb;
+    const long long total = (long long)n_grids * 3 * per;
+    const double c = sqrt(3.141592653589793 / 2.0);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e % nb);
+        const int i = (int)((e / nb) % nb);
+        const int k = (int)((e / per) % 3);
+        const int g = (int)(e / (3 * per));
+        const double* x = grid + (size_t)g * nb;
+        double a;
+        if (toeplitz) {
+            const int d = i > j ? i - j : j - i;
+            a = eps * (x[0] - x[d]);
+        } else {
+            a = eps * (x[j] - x[i]);
+        }
+        const double a2 = a * a;
+        const double ex = exp(-(a2 / 2.0));
+        double v;
+        if (k == 0) v = c * (1.0 / eps) * ex;
+        else if (k == 1) v = -c * eps * (-1.0 + a2) * ex;
+        else v = c * (eps * eps * eps) * (3.0 - 6.0 * a2 + a2 * a2) * ex;
+        m[e] = v;
+    }
+}
+
+// ---- EIS variance-estimation matrix (mat1d.py:493-515): one warp per row --------------------------
+__global__ void eis_vmm_kernel(const double* __restrict__ freq, int n_grids, int nf, double vmm_eps, double reim_cor,
+                               int uniform, double* __restrict__ vmm) {
+    const int n2 = 2 * nf;
+    const long long rows = (long long)n_grids * n2;
+    const int lane = threadIdx.x & 31;
+    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows;
+         row += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int g = (int)(row / n2), i = (int)(row % n2);
+        const double* f = freq + (size_t)g * nf;
+        const double lfi = log(f[i % nf]);
+        double sum = 0.0;
+        for (int j = lane; j < n2; j += 32) {
+            double v = uniform ? 1.0 : rbf(lfi - log(f[j % nf]), vmm_eps);
+            if ((i < nf) != (j < nf)) v *= reim_cor;
+            sum += v;
+        }
+        sum = warp_sum(sum);
+        for (int j = lane; j < n2; j += 32) {
+            double v = uniform ? 1.0 : rbf(lfi - log(f[j % nf]), vmm_eps);
+            if ((i < nf) != (j < nf)) v *= reim_cor;
+            vmm[row * n2 + j] = v / sum;
+        }
+    }
+}
+
+// ---- DOP impedance columns (phasance.py:19-37,61-80,108-118) --------------------------------------
+struct cplx { double re, im; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cexp_(cplx a) { const double e = exp(a.re); double s, c; sincos(a.im, &s, &c); return {e * c, e * s}; }
+
+// erf(x + i y) = erf(x) + (2 i / sqrt(pi)) exp(-x^2) int_0^y exp(t^2 - 2 i x t) dt, 24-point Gauss-Legendre.
+// Valid for the small |y| = pi / (4 nu_eps) this path produces (host rejects |y| > 0.25).
+__constant__ double kGL24x[12] = {0.06405689286260563, 0.19111886747361631, 0.3150426796961634, 0.43379350762604513, 0.54542147138883956, 0.64809365193697555, 0.74012419157855436, 0.82000198597390295, 0.88641552700440107, 0.9382745520027328, 0.97472855597130947, 0.99518721999702131};
+__constant__ double kGL24w[12] = {0.12793819534675202, 0.12583745634682825, 0.12167047292780329, 0.11550566805372552, 0.10744427011596556, 0.097618652104113926, 0.086190161531953205, 0.073346481411080161, 0.05929858491543636, 0.044277438817419412, 0.028531388628933559, 0.01234122979998869};
+
+__device__ cplx cerf_small_imag(double x, double y) {
+    const double base = erf(x);
+    const double ex2 = exp(-x * x);
+    if (ex2 == 0.0 || y == 0.0) return {base, 0.0};
+    // I = int_0^y exp(t^2) (cos(2xt) - i sin(2xt)) dt
+    const double h = 0.5 * y;
+    double ir = 0.0, ii = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 12; ++q) {
+#pragma unroll 1
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const double t = h + sgn * h * kGL24x[q];
+            const double e = exp(t * t) * kGL24w[q];
+            double s, c;
+            sincos(2.0 * x * t, &s, &c);
+            ir += e * c;
+            ii -= e * s;
+        }
+    }
+    ir *= h; ii *= h;
+    const double k = 1.1283791670955125738961589031215451716881 * ex2;  // 2/sqrt(pi)
+    // erf(z) = base + i*k*(ir + i ii) = base - k*ii + i*k*ir
+    return {base - k * ii, k * ir};
+}
+
+__global__ void dop_z_kernel(const double* __restrict__ freq, const double* __restrict__ nu, int n_grids, int nf,
+                             int n_nu, double nu_eps, double* __restrict__ zm) {
+    const long long total = (long long)n_grids * nf * n_nu;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e % n_nu);
+        const long long gf = e / n_nu;
+        const double om = 2.0 * 3.141592653589793 * freq[gf];
+        const double num = nu[m];
+        const cplx lj = {log(om), 1.5707963267948966};  // ln(j omega)
+        // prefactor: 0.5 sqrt(pi) (jw)^nu_m / eps * (jw)^(ln(jw) / (4 eps^2))
+        const double q4 = 4.0 * nu_eps * nu_eps;
+        const cplx ex1 = {num * lj.re, num * lj.im};
+        const cplx l2 = cmul(lj, {lj.re / q4, lj.im / q4});
+        cplx pre = cmul(cexp_(ex1), cexp_(l2));
+        const double s = 0.5 * sqrt(3.141592653589793) / nu_eps;
+        pre.re *= s; pre.im *= s;
+        const double sg = (num > 0.0) ? 1.0 : ((num < 0.0) ? -1.0 : 0.0);
+        const double la = fmin(0.0, sg), lb = fmax(0.0, sg);
+        const double sh_re = lj.re / (2.0 * nu_eps), sh_im = lj.im / (2.0 * nu_eps);
+        const cplx eb = cerf_small_imag(nu_eps * (lb - num) - sh_re, -sh_im);
+        const cplx ea = cerf_small_imag(nu_eps * (la - num) - sh_re, -sh_im);
+        const cplx fb = cmul(pre, eb), fa = cmul(pre, ea);
+        zm[2 * e] = fb.re - fa.re;
+        zm[2 * e + 1] = fb.im - fa.im;
+    }
+}
+
+}  // namespace hdrt
+
+using namespace hdrt;
+
+static int grid_for(long long work_items, int per_block) {
+    long long g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > 148LL * 64) g = 148LL * 64;
+    return (int)g;
+}
+
+extern "C" int hdrt_build_lookup(double eps, int grid_points, int quad_points, double* re_x, double* re_v,
+                                 double* im_x, double* im_v, double* td_x, double* td_v, void* stream) {
+    if (grid_points < 2 || quad_points < 2 || !re_x || !re_v || !im_x || !im_v || !td_x || !td_v) {
+        set_error("hdrt_build_lookup: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    const long long warps = 3LL * grid_points;
+    const int blocks = (int)((warps * 32 + kMThreads - 1) / kMThreads);
+    lookup_kernel<<<blocks, kMThreads, 0, (cudaStream_t)stream>>>(eps, grid_points, quad_points, re_x, re_v, im_x,
+                                                                  im_v, td_x, td_v);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_impedance(int mode, const double* freq, const double* tau, int n_grids, int nf, int nb,
+                                    double eps, const double* re_x, const double* re_v, const double* im_x,
+                                    const double* im_v, int grid_points, int quad_points, double* a_re, double* a_im,
+                                    void* stream) {
+    if (!freq || !tau || !a_re || !a_im || n_grids < 0 || nf <= 0 || nb <= 0) {
+        set_error("hdrt_build_impedance: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    if (n_grids == 0) return HDRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == HDRT_MODE_INTERP) {
+        if (!re_x || !re_v || !im_x || !im_v || grid_points < 2) { set_error("interp mode needs lookup tables"); return HDRT_ERR_ARG; }
+        // aim for >= 4 waves of 148 SMs; each CTA writes rows_per_cta * nb * 16 bytes
+        int rows_per_cta = nf;
+        while (rows_per_cta > 8 && (long long)n_grids * ((nf + rows_per_cta - 1) / rows_per_cta) < 148 * 8) rows_per_cta = (rows_per_cta + 1) / 2;
+        dim3 grid(n_grids, (nf + rows_per_cta - 1) / rows_per_cta);
+        const size_t smem = sizeof(double) * (nb + rows_per_cta);
+        impedance_interp_kernel<<<grid, kMThreads, smem, st>>>(freq, tau, nf, nb, re_x, re_v, im_x, im_v, grid_points,
+                                                               a_re, a_im, rows_per_cta);
+    } else if (mode == HDRT_MODE_TRAPZ) {
+        if (quad_points < 2) { set_error("quad_points < 2"); return HDRT_ERR_ARG; }
+        const long long total = (long long)n_grids * nf * nb;
+        impedance_trapz_kernel<<<grid_for(total * 32, kMThreads), kMThreads, 0, st>>>(freq, tau, n_grids, nf, nb, eps,
+                                                                                     quad_points, a_re, a_im);
+    } else {
+        set_error("unknown mode %d", mode);
+        return HDRT_ERR_UNSUPPORTED;
+    }
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_response(int mode, const double* times, const double* tau, const double* step_times,
+                                   const double* step_sizes, int n_grids, int nt, int nb, int n_steps, double eps,
+                                   const double* td_x, const double* td_v, int grid_points, int quad_points,
+                                   double* rm, void* stream) {
+    if (!times || !tau || !step_times || !step_sizes || !rm || n_grids < 0 || nt <= 0 || nb <= 0 || n_steps <= 0) {
+        set_error("hdrt_build_response: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    if (n_grids == 0) return HDRT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == HDRT_MODE_INTERP) {
+        if (!td_x || !td_v || grid_points < 2) { set_error("interp mode needs the response lookup"); return HDRT_ERR_ARG; }
+        int rows_per_cta = 64;
+        while (rows_per_cta > 8 && (long long)n_grids * ((nt + rows_per_cta - 1) / rows_per_cta) < 148 * 8) rows_per_cta /= 2;
+        dim3 grid(n_grids, (nt + rows_per_cta - 1) / rows_per_cta);
+        const size_t smem = sizeof(double) * (nb + rows_per_cta + 2 * n_steps);
+        if (smem > 48 * 1024) { set_error("too many steps / basis points for the staging buffer"); return HDRT_ERR_UNSUPPORTED; }
+        response_interp_kernel<<<grid, kMThreads, smem, st>>>(times, tau, step_times, step_sizes, nt, nb, n_steps, td_x,
+                                                              td_v, grid_points, rm, rows_per_cta);
+    } else if (mode == HDRT_MODE_TRAPZ) {
+        const long long total = (long long)n_grids * nt * nb;
+        response_trapz_kernel<<<grid_for(total * 32, kMThreads), kMThreads, 0, st>>>(times, tau, step_times, step_sizes,
+                                                                                   n_grids, nt, nb, n_steps, eps,
+                                                                                   quad_points, rm);
+    } else {
+        set_error("unknown mode %d", mode);
+        return HDRT_ERR_UNSUPPORTED;
+    }
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_penalty(const double* grid, int n_grids, int nb, double eps, int toeplitz, double* m,
+                                  void* stream) {
+    if (!grid || !m || n_grids < 0 || nb <= 0) { set_error("hdrt_build_penalty: invalid argument"); return HDRT_ERR_ARG; }
+    if (n_grids == 0) return HDRT_OK;
+    const long long total = (long long)n_grids * 3 * nb * nb;
+    penalty_kernel<<<grid_for(total, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(grid, n_grids, nb, eps, toeplitz, m);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_eis_vmm(const double* freq, int n_grids, int nf, double vmm_eps, double reim_cor, int uniform,
+                                  double* vmm, void* stream) {
+    if (!freq || !vmm || n_grids < 0 || nf <= 0) { set_error("hdrt_build_eis_vmm: invalid argument"); return HDRT_ERR_ARG; }
+    if (n_grids == 0) return HDRT_OK;
+    const long long rows = (long long)n_grids * 2 * nf;
+    eis_vmm_kernel<<<grid_for(rows * 32, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(freq, n_grids, nf, vmm_eps,
+                                                                                         reim_cor, uniform, vmm);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_dop_z(const double* freq, const double* nu, int n_grids, int nf, int n_nu, double nu_eps,
+                                double* zm, void* stream) {
+    if (!freq || !nu || !zm || n_grids < 0 || nf <= 0 || n_nu <= 0 || !(nu_eps > 0.0)) {
+        set_error("hdrt_build_dop_z: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    if (3.141592653589793 / (4.0 * nu_eps) > 0.25) {
+        set_error("nu_epsilon %.3g too small for the small-imaginary-part complex erf (need >= pi)", nu_eps);
+        return HDRT_ERR_UNSUPPORTED;
+    }
+    if (n_grids == 0) return HDRT_OK;
+    const long long total = (long long)n_grids * nf * n_nu;
+    dop_z_kernel<<<grid_for(total, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(freq, nu, n_grids, nf, n_nu, nu_eps, zm);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}

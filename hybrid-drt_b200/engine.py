@@ -1,0 +1,327 @@
+"""ctypes binding of libhybdrt_b200.so (include/hybdrt_b200.h) with torch as the device allocator.
+
+torch is plumbing here: it owns device memory and the CUDA stream.  Every number is produced by the
+CUDA kernels behind the C ABI; if the library is missing or no GPU is present this module raises --
+there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libhybdrt_b200.so')
+
+MODE_INTERP, MODE_TRAPZ = 0, 1
+ST_CONVERGED, ST_MAXITER, ST_QP_MAXITERS, ST_KKT_FAIL, ST_NAN = 1, 2, 4, 8, 16
+
+_D3 = C.c_double * 3
+
+
+class Hypers(C.Structure):
+    """struct hdrt_hypers"""
+    _fields_ = [
+        ('derivative_weights', _D3), ('sigma_ds', _D3), ('s_alpha', _D3), ('s_0', _D3),
+        ('rho_alpha', _D3), ('rho_0', _D3), ('l2_lambda_0', C.c_double),
+        ('dop_derivative_weights', _D3), ('dop_sigma_ds', _D3), ('dop_s_alpha', _D3), ('dop_s_0', _D3),
+        ('dop_rho_alpha', _D3), ('dop_rho_0', _D3), ('dop_l2_lambda_0', C.c_double),
+        ('iw_l1_lambda_0', C.c_double), ('iw_l2_lambda_0', C.c_double),
+        ('iw_alpha', C.c_double), ('iw_beta', C.c_double),
+        ('xtol', C.c_double), ('weight_factor', C.c_double),
+        ('chrono_weight_factor', C.c_double), ('eis_weight_factor', C.c_double),
+        ('has_iw_prior', C.c_int), ('max_iter', C.c_int),
+    ]
+
+
+_P = C.c_void_p
+
+
+class Problem(C.Structure):
+    """struct hdrt_qphb_problem"""
+    _fields_ = [
+        ('batch', C.c_int), ('n_rows', C.c_int), ('n_cols', C.c_int), ('n_special', C.c_int),
+        ('n_chrono', C.c_int), ('dop_start', C.c_int), ('dop_end', C.c_int), ('vz_index', C.c_int),
+        ('vb_start', C.c_int), ('vb_end', C.c_int), ('hybrid', C.c_int),
+        ('rm', _P), ('rm_stride', C.c_longlong), ('rv', _P),
+        ('vmm_eis', _P), ('vmm_eis_stride', C.c_longlong),
+        ('vmm_chrono', _P), ('vmm_chrono_stride', C.c_longlong),
+        ('pen', _P), ('pen_stride', C.c_longlong),
+        ('h', _P), ('l1', _P), ('vz_strength', _P),
+        ('hyp', Hypers),
+        ('x', _P), ('weights', _P), ('est_weights', _P), ('init_weights', _P), ('x_overfit', _P),
+        ('s_vectors', _P), ('rho', _P), ('dop_rho', _P), ('xmx_norms', _P), ('dop_xmx_norms', _P),
+        ('fun', _P), ('vz_col', _P), ('p_matrix', _P), ('q_vector', _P),
+        ('n_outer', _P), ('n_ipm', _P), ('status', _P),
+    ]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f'{LIB_PATH} not found: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          f'(or python hybrid-drt_b200/build.py). hybdrt_b200 has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.hdrt_version.restype = C.c_int
+    lib.hdrt_last_error.restype = C.c_char_p
+    lib.hdrt_create.argtypes = [C.POINTER(_P), C.c_int]
+    lib.hdrt_destroy.argtypes = [_P]
+    lib.hdrt_sm_count.argtypes = [_P]
+    lib.hdrt_build_lookup.argtypes = [C.c_double, C.c_int, C.c_int] + [_P] * 6 + [_P]
+    lib.hdrt_build_impedance.argtypes = [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P, _P, _P,
+                                         C.c_int, C.c_int, _P, _P, _P]
+    lib.hdrt_build_response.argtypes = [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        _P, _P, C.c_int, C.c_int, _P, _P]
+    lib.hdrt_build_penalty.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P]
+    lib.hdrt_build_eis_vmm.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]
+    lib.hdrt_build_dop_z.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
+    lib.hdrt_default_hypers.argtypes = [C.POINTER(Hypers)]
+    lib.hdrt_default_hypers.restype = None
+    lib.hdrt_qphb_smem_bytes.argtypes = [C.c_int, C.c_int]
+    lib.hdrt_qphb_smem_bytes.restype = C.c_longlong
+    lib.hdrt_qphb_fit_batch.argtypes = [_P, C.POINTER(Problem), _P]
+    lib.hdrt_probe_fp64.argtypes = [_P, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    'hdrt_version', 'hdrt_last_error', 'hdrt_create', 'hdrt_destroy', 'hdrt_sm_count', 'hdrt_build_lookup',
+    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_dop_z',
+    'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64',
+]
+
+
+def default_hypers():
+    h = Hypers()
+    load_library().hdrt_default_hypers(C.byref(h))
+    return h
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One per device: owns the C-side handle, allocates through torch, launches on torch's stream."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise EngineError('hybdrt_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)      # make sure the primary context exists
+        h = _P()
+        self._check(self.lib.hdrt_create(C.byref(h), self.device.index))
+        self.handle = h
+        self.sm_count = self.lib.hdrt_sm_count(h)
+        self._lookups = {}
+        self.launches = 0           # kernels launched through this engine (bench.py reports it)
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.hdrt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _check(self, code):
+        if code != 0:
+            raise EngineError(f'hybdrt_b200 error {code}: {self.lib.hdrt_last_error().decode()}')
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, a, dtype=torch.float64):
+        """numpy / tensor -> contiguous device tensor of dtype."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # -- L1 --------------------------------------------------------------------------------------
+    def build_lookup(self, eps, grid_points=2000, quad_points=1000):
+        """basis.generate_impedance_lookup + generate_response_lookup (basis.py:648-689); cached per eps."""
+        key = (float(eps), grid_points, quad_points)
+        if key not in self._lookups:
+            t = self.empty(6, grid_points)
+            self._check(self.lib.hdrt_build_lookup(float(eps), grid_points, quad_points,
+                                                   *[_ptr(t[i]) for i in range(6)], self._stream()))
+            self.launches += 1
+            self._lookups[key] = dict(re_x=t[0], re_v=t[1], im_x=t[2], im_v=t[3], resp_x=t[4], resp_v=t[5],
+                                      grid_points=grid_points)
+        return self._lookups[key]
+
+    def build_impedance(self, freq, tau, eps, mode=MODE_INTERP, tables=None, quad_points=1000):
+        """mat1d.construct_impedance_matrix for both parts. freq [G,nf], tau [G,nb] -> a_re, a_im [G,nf,nb]."""
+        freq = self.dev(freq).reshape(-1, np.shape(freq)[-1])
+        tau = self.dev(tau).reshape(-1, np.shape(tau)[-1])
+        g, nf = freq.shape
+        nb = tau.shape[1]
+        if tau.shape[0] != g:
+            raise ValueError('freq and tau must have the same number of grids')
+        a_re, a_im = self.empty(g, nf, nb), self.empty(g, nf, nb)
+        if mode == MODE_INTERP:
+            tables = tables or self.build_lookup(eps)
+            targs = (_ptr(tables['re_x']), _ptr(tables['re_v']), _ptr(tables['im_x']), _ptr(tables['im_v']),
+                     tables['grid_points'])
+        else:
+            targs = (None, None, None, None, 0)
+        self._check(self.lib.hdrt_build_impedance(mode, _ptr(freq), _ptr(tau), g, nf, nb, float(eps), *targs,
+                                                  quad_points, _ptr(a_re), _ptr(a_im), self._stream()))
+        self.launches += 1
+        return a_re, a_im
+
+    def build_response(self, times, tau, step_times, step_sizes, eps, mode=MODE_INTERP, tables=None,
+                       quad_points=1000):
+        """mat1d.construct_response_matrix. times [G,nt], tau [G,nb], steps [G,ns] -> rm [G,nt,nb]."""
+        times = self.dev(times).reshape(-1, np.shape(times)[-1])
+        tau = self.dev(tau).reshape(-1, np.shape(tau)[-1])
+        st = self.dev(step_times).reshape(-1, np.shape(step_times)[-1])
+        sa = self.dev(step_sizes).reshape(-1, np.shape(step_sizes)[-1])
+        g, nt = times.shape
+        nb = tau.shape[1]
+        rm = self.empty(g, nt, nb)
+        if mode == MODE_INTERP:
+            tables = tables or self.build_lookup(eps)
+            targs = (_ptr(tables['resp_x']), _ptr(tables['resp_v']), tables['grid_points'])
+        else:
+            targs = (None, None, 0)
+        self._check(self.lib.hdrt_build_response(mode, _ptr(times), _ptr(tau), _ptr(st), _ptr(sa), g, nt, nb,
+                                                 st.shape[1], float(eps), *targs, quad_points, _ptr(rm),
+                                                 self._stream()))
+        self.launches += 1
+        return rm
+
+    def build_penalty(self, grid, eps, toeplitz):
+        """mat1d.construct_integrated_derivative_matrix orders 0..2. grid [G,nb] -> [G,3,nb,nb]."""
+        grid = self.dev(grid).reshape(-1, np.shape(grid)[-1])
+        g, nb = grid.shape
+        m = self.empty(g, 3, nb, nb)
+        self._check(self.lib.hdrt_build_penalty(_ptr(grid), g, nb, float(eps), int(bool(toeplitz)), _ptr(m),
+                                                self._stream()))
+        self.launches += 1
+        return m
+
+    def build_eis_vmm(self, freq, vmm_eps=0.25, reim_cor=0.25, uniform=False):
+        """mat1d.construct_eis_var_matrix. freq [G,nf] -> [G,2nf,2nf]."""
+        freq = self.dev(freq).reshape(-1, np.shape(freq)[-1])
+        g, nf = freq.shape
+        vmm = self.empty(g, 2 * nf, 2 * nf)
+        self._check(self.lib.hdrt_build_eis_vmm(_ptr(freq), g, nf, float(vmm_eps), float(reim_cor),
+                                                int(bool(uniform)), _ptr(vmm), self._stream()))
+        self.launches += 1
+        return vmm
+
+    def build_dop_z(self, freq, nu, nu_eps):
+        """phasance.construct_phasor_z_matrix (gaussian). freq [G,nf], nu [n_nu] -> complex128 [G,nf,n_nu]."""
+        freq = self.dev(freq).reshape(-1, np.shape(freq)[-1])
+        nu = self.dev(nu).reshape(-1)
+        g, nf = freq.shape
+        zm = self.empty(g, nf, nu.numel(), 2)
+        self._check(self.lib.hdrt_build_dop_z(_ptr(freq), _ptr(nu), g, nf, nu.numel(), float(nu_eps), _ptr(zm),
+                                              self._stream()))
+        self.launches += 1
+        return torch.view_as_complex(zm)
+
+    # -- L2 --------------------------------------------------------------------------------------
+    def smem_bytes(self, n_rows, n_cols):
+        return int(self.lib.hdrt_qphb_smem_bytes(n_rows, n_cols))
+
+    def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
+                       dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
+                       hypers=None, want_pq=False, out=None):
+        """Launch the batched QPHB solver.  All inputs are device float64 tensors.
+
+        rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
+        Returns a dict of device tensors (asynchronous; synchronise before reading on the host).
+        """
+        rv = rv.contiguous()
+        b, n_rows = rv.shape
+        n = rm.shape[-1]
+        assert rm.shape[-2] == n_rows and pen.shape[-1] == n and pen.shape[-3] == 3
+        for t in (rm, rv, pen, h, l1):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        hyp = hypers if hypers is not None else default_hypers()
+        o = out if out is not None else {}
+
+        def buf(name, *shape, dtype=torch.float64):
+            t = o.get(name)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = self.empty(*shape, dtype=dtype)
+                o[name] = t
+            return t
+
+        p = Problem()
+        p.batch, p.n_rows, p.n_cols, p.n_special, p.n_chrono = b, n_rows, n, int(n_special), int(n_chrono)
+        p.dop_start, p.dop_end = (dop_range if dop_range is not None else (-1, -1))
+        p.vz_index = int(vz_index)
+        p.vb_start, p.vb_end = vb_range
+        p.hybrid = int(bool(hybrid))
+        p.rm, p.rm_stride = _ptr(rm), (n_rows * n if rm.dim() == 3 else 0)
+        p.rv = _ptr(rv)
+        if vmm_eis is not None:
+            p.vmm_eis, p.vmm_eis_stride = _ptr(vmm_eis), (vmm_eis.shape[-1] ** 2 if vmm_eis.dim() == 3 else 0)
+        if vmm_chrono is not None:
+            p.vmm_chrono, p.vmm_chrono_stride = _ptr(vmm_chrono), (n_chrono ** 2 if vmm_chrono.dim() == 3 else 0)
+        p.pen, p.pen_stride = _ptr(pen), (3 * n * n if pen.dim() == 4 else 0)
+        p.h, p.l1 = _ptr(h), _ptr(l1)
+        p.vz_strength = _ptr(vz_strength)
+        p.hyp = hyp
+        p.x = _ptr(buf('x', b, n))
+        p.weights = _ptr(buf('weights', b, n_rows))
+        p.est_weights = _ptr(buf('est_weights', b, n_rows))
+        p.init_weights = _ptr(buf('init_weights', b, n_rows))
+        p.x_overfit = _ptr(buf('x_overfit', b, n))
+        p.s_vectors = _ptr(buf('s_vectors', b, 3, n))
+        p.rho = _ptr(buf('rho', b, 3))
+        p.xmx_norms = _ptr(buf('xmx_norms', b, 3))
+        if dop_range is not None:
+            p.dop_rho = _ptr(buf('dop_rho', b, 3))
+            p.dop_xmx_norms = _ptr(buf('dop_xmx_norms', b, 3))
+        p.fun = _ptr(buf('fun', b))
+        if vz_index >= 0:
+            p.vz_col = _ptr(buf('vz_col', b, n_rows))
+        if want_pq:
+            p.p_matrix = _ptr(buf('p_matrix', b, n, n))
+            p.q_vector = _ptr(buf('q_vector', b, n))
+        p.n_outer = _ptr(buf('n_outer', b, dtype=torch.int32))
+        p.n_ipm = _ptr(buf('n_ipm', b, dtype=torch.int32))
+        p.status = _ptr(buf('status', b, dtype=torch.int32))
+        self._check(self.lib.hdrt_qphb_fit_batch(self.handle, C.byref(p), self._stream()))
+        self.launches += 1
+        return o
+
+    def probe_fp64(self):
+        """Achieved DFMA TFLOP/s of this GPU (register-resident FMA loop on every SM)."""
+        v = C.c_double()
+        self._check(self.lib.hdrt_probe_fp64(self.handle, C.byref(v)))
+        self.launches += 2
+        return v.value
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -1,0 +1,181 @@
+/*
+ * hybdrt_b200 -- C ABI of the B200-native DRT/DOP inversion engine.
+ *
+ * The reference (jdhuang-csm/hybrid-drt) is pure Python and has no FFI; the boundary this library
+ * replaces is the set of Python functions listed beside each entry point (file:line into the
+ * reference tree).  A maintainer binds these symbols with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all matrices are C-contiguous
+ *     (row-major) float64, exactly numpy's default layout;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and stream-ordered;
+ *   - the caller owns every buffer; the library owns only the per-device handle;
+ *   - return value: 0 = launched, <0 = error (hdrt_last_error() gives the text); there is no CPU
+ *     fallback anywhere behind this interface.
+ */
+#ifndef HYBDRT_B200_H
+#define HYBDRT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDRT_OK 0
+#define HDRT_ERR_ARG (-1)         /* invalid argument                                   */
+#define HDRT_ERR_UNSUPPORTED (-2) /* shape/mode outside what the kernels cover          */
+#define HDRT_ERR_CUDA (-3)        /* CUDA runtime error (no device, launch failure ...) */
+
+#define HDRT_MODE_INTERP 0 /* np.interp into the 2000-point lookup tables (reference default) */
+#define HDRT_MODE_TRAPZ 1  /* per-entry 1000-point trapezoid quadrature                       */
+
+/* per-spectrum status bits written by hdrt_qphb_fit_batch */
+#define HDRT_ST_CONVERGED 1   /* outer loop met qphb.is_converged                                 */
+#define HDRT_ST_MAXITER 2     /* outer loop ran to max_iter (reference: warning only)             */
+#define HDRT_ST_QP_MAXITERS 4 /* some QP hit the interior-point iteration cap (cvxopt 'unknown')  */
+#define HDRT_ST_KKT_FAIL 8    /* Cholesky breakdown inside a QP (cvxopt: singular KKT matrix)     */
+#define HDRT_ST_NAN 16        /* non-finite coefficients                                          */
+
+typedef struct hdrt_handle hdrt_handle;
+
+int hdrt_version(void);
+const char* hdrt_last_error(void);
+
+/* Per-device workspace (work-queue counter, SM count).  One handle per device; thread-safe per handle. */
+int hdrt_create(hdrt_handle** out, int device);
+int hdrt_destroy(hdrt_handle* h);
+int hdrt_sm_count(const hdrt_handle* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * L1: response-matrix builders (reference: hybdrt/matrices/{basis,mat1d,phasance}.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* basis.generate_impedance_lookup (basis.py:648-669) + basis.generate_response_lookup (:672-689).
+ * Six arrays of `grid_points` doubles: ln(omega*tau) grids and values for the real and imaginary
+ * impedance integrals, ln(dt/tau) grid and values for the step response. */
+int hdrt_build_lookup(double eps, int grid_points, int quad_points, double* re_x, double* re_v, double* im_x,
+                      double* im_v, double* td_x, double* td_v, void* stream);
+
+/* mat1d.construct_impedance_matrix (mat1d.py:212-374), both parts at once, for `n_grids` independent
+ * (frequency, tau) grids.  freq [n_grids][nf], tau [n_grids][nb] -> a_re, a_im [n_grids][nf][nb].
+ * Tables are only read in HDRT_MODE_INTERP. */
+int hdrt_build_impedance(int mode, const double* freq, const double* tau, int n_grids, int nf, int nb, double eps,
+                         const double* re_x, const double* re_v, const double* im_x, const double* im_v,
+                         int grid_points, int quad_points, double* a_re, double* a_im, void* stream);
+
+/* mat1d.construct_response_matrix (mat1d.py:16-122), galvanostatic ideal steps, summed over steps.
+ * times [n_grids][nt], tau [n_grids][nb], step_times/step_sizes [n_grids][n_steps] -> rm [n_grids][nt][nb]. */
+int hdrt_build_response(int mode, const double* times, const double* tau, const double* step_times,
+                        const double* step_sizes, int n_grids, int nt, int nb, int n_steps, double eps,
+                        const double* td_x, const double* td_v, int grid_points, int quad_points, double* rm,
+                        void* stream);
+
+/* mat1d.construct_integrated_derivative_matrix orders 0,1,2 (mat1d.py:125-209, basis.py:382-395).
+ * grid [n_grids][nb] (ln tau, or nu for the DOP block) -> m [n_grids][3][nb][nb].
+ * toeplitz != 0 reproduces the reference's uniform-grid shortcut (entry (i,j) from grid[|i-j|]-grid[0]). */
+int hdrt_build_penalty(const double* grid, int n_grids, int nb, double eps, int toeplitz, double* m, void* stream);
+
+/* mat1d.construct_eis_var_matrix (mat1d.py:493-515).  freq [n_grids][nf] -> vmm [n_grids][2nf][2nf]. */
+int hdrt_build_eis_vmm(const double* freq, int n_grids, int nf, double vmm_eps, double reim_cor, int uniform,
+                       double* vmm, void* stream);
+
+/* phasance.construct_phasor_z_matrix, gaussian basis, normalize=False (phasance.py:19-37,61-80,108-118).
+ * freq [n_grids][nf], nu [n_nu] -> interleaved complex128 zm [n_grids][nf][n_nu][2]. */
+int hdrt_build_dop_z(const double* freq, const double* nu, int n_grids, int nf, int n_nu, double nu_eps, double* zm,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * L2: batched QPHB fit (reference: the loop of DRT._qphb_fit_core, drt1d.py:556-1008, which calls
+ * qphb.initialize_weights qphb.py:1609, qphb.iterate_qphb :606, qphb.calculate_pq :1154; the QP is
+ * cvxopt.solvers.qp reached at qphb.py:519)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hdrt_hypers {
+    double derivative_weights[3]; /* qphb.get_default_hypers, qphb.py:208-255 */
+    double sigma_ds[3];
+    double s_alpha[3];
+    double s_0[3];
+    double rho_alpha[3];
+    double rho_0[3];
+    double l2_lambda_0;
+    double dop_derivative_weights[3];
+    double dop_sigma_ds[3];
+    double dop_s_alpha[3];
+    double dop_s_0[3];
+    double dop_rho_alpha[3];
+    double dop_rho_0[3];
+    double dop_l2_lambda_0;
+    double iw_l1_lambda_0; /* drt1d.py:123; added to EVERY entry of q in the init QP (qphb.py:1660) */
+    double iw_l2_lambda_0;
+    double iw_alpha; /* only read when has_iw_prior != 0 (qphb.solve_init_weight_scale :1471) */
+    double iw_beta;
+    double xtol;                 /* drt1d.py:135 */
+    double weight_factor;        /* drt1d.py:129 */
+    double chrono_weight_factor; /* drt1d.py:126, hybrid only */
+    double eis_weight_factor;
+    int has_iw_prior;
+    int max_iter; /* drt1d.py:135 */
+} hdrt_hypers;
+
+typedef struct hdrt_qphb_problem {
+    int batch;     /* number of spectra                                               */
+    int n_rows;    /* N: data rows (chrono samples first, then Re z, then Im z)       */
+    int n_cols;    /* n: special parameters first, then the DRT coefficients          */
+    int n_special; /* DRT block = columns [n_special, n_cols)                         */
+    int n_chrono;  /* leading rows that are chrono samples (0 for fit_eis)            */
+    int dop_start; /* DOP block [dop_start, dop_end) inside the specials; -1 if none  */
+    int dop_end;
+    int vz_index; /* column rewritten every iteration (drt1d.py:972-979); -1 if none */
+    int vb_start; /* v_baseline columns excluded from the vz prediction (:510-511)   */
+    int vb_end;
+    int hybrid; /* apply chrono/eis weight factors (drt1d.py:882-884)               */
+
+    const double* rm;           /* [N][n] design matrix; + b*rm_stride for spectrum b (0 = shared)        */
+    long long rm_stride;
+    const double* rv;           /* [batch][N] scaled data vectors                                         */
+    const double* vmm_eis;      /* [(N-n_chrono)]^2 variance-estimation block (mat1d.py:493); may be NULL */
+    long long vmm_eis_stride;   /*   when N == n_chrono                                                   */
+    const double* vmm_chrono;   /* [n_chrono]^2, or NULL = 'uniform' error structure (mat1d.py:482-488)   */
+    long long vmm_chrono_stride;
+    const double* pen;          /* [3][n][n] embedded penalty matrices m0..m2 (drt1d.py:5863-5910)        */
+    long long pen_stride;
+    const double* h;            /* [n] rhs of -x <= h (qphb.make_h_constraint :521-557), shared           */
+    const double* l1;           /* [n] l1 lambda vector (drt1d.py:557-561), shared                        */
+    const double* vz_strength;  /* [N] (drt1d.py:514-519); NULL if vz_index < 0                           */
+    hdrt_hypers hyp;
+
+    /* outputs, all [batch][...]; optional ones may be NULL */
+    double* x;             /* [n]  cvx_result['x'] of the last QP                          */
+    double* weights;       /* [N]  weights returned by the last iterate_qphb (unscaled)    */
+    double* est_weights;   /* [N]                                                          */
+    double* init_weights;  /* [N]                                                          */
+    double* x_overfit;     /* [n]                                                          */
+    double* s_vectors;     /* [3][n]                                                       */
+    double* rho;           /* [3]                                                          */
+    double* dop_rho;       /* [3]   (NULL if no DOP block)                                 */
+    double* xmx_norms;     /* [3]                                                          */
+    double* dop_xmx_norms; /* [3]   (NULL if no DOP block)                                 */
+    double* fun;           /* [1]   'primal objective' of the last QP                      */
+    double* vz_col;        /* [N]   final vz_offset column (NULL if vz_index < 0)          */
+    double* p_matrix;      /* [n][n] optional: qphb.calculate_pq with the final state      */
+    double* q_vector;      /* [n]    optional                                              */
+    int* n_outer;          /* [1]   outer iterations executed                              */
+    int* n_ipm;            /* [1]   interior-point iterations summed over all QPs          */
+    int* status;           /* [1]   HDRT_ST_* bits                                         */
+} hdrt_qphb_problem;
+
+/* Fills `hyp` with the reference defaults (qphb.py:208-255 eff_hp=True, drt1d.py:102-137). */
+void hdrt_default_hypers(hdrt_hypers* hyp);
+
+/* Bytes of dynamic shared memory one spectrum's CTA needs; <0 if the shape does not fit on sm_100a. */
+long long hdrt_qphb_smem_bytes(int n_rows, int n_cols);
+
+/* One persistent CTA per spectrum in flight; spectra are pulled from a device-side work counter. */
+int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob, void* stream);
+
+/* FP64 FMA probe: runs a register-resident DFMA loop on every SM and returns achieved TFLOP/s
+ * (host-synchronous; used by bench.py for the FP64 roofline denominator). */
+int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYBDRT_B200_H */
