@@ -895,6 +895,7 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
         set_error("invalid sizes");
         return HDRT_ERR_ARG;
     }
+    if (p.batch == 0) return HDRT_OK;
     if (!p.rm || !p.rv || !p.pen || !p.h || !p.l1 || !p.x || !p.est_weights) {
         set_error("rm, rv, pen, h, l1, x and est_weights are required");
         return HDRT_ERR_ARG;
@@ -905,7 +906,6 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (p.n_cols > kMaxCols) { set_error("n_cols %d > %d unsupported", p.n_cols, kMaxCols); return HDRT_ERR_UNSUPPORTED; }
     const long long smem = hdrt_qphb_smem_bytes(p.n_rows, p.n_cols);
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
-    if (p.batch == 0) return HDRT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
     HDRT_CUDA_CHECK(cudaFuncSetAttribute(qphb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,951 @@
+"""Drop-in mirror of hybrid-drt's ``DRT`` model for the QPHB fit path, dispatching to the B200 engine.
+
+Mirrors ``hybdrt.models.DRT`` (reference hybdrt/models/drt1d.py:38, drtbase.py:20): same constructor
+keywords, same ``fit_eis / fit_chrono / fit_hybrid`` signatures (drt1d.py:1197-1268), same result
+attributes (``fit_parameters``, ``qphb_params``, ``cvx_result['x']``, ``special_qp_params``,
+``basis_tau``, ``coefficient_scale`` ...).  New: ``fit_eis_batch / fit_hybrid_batch / fit_chrono_batch``
+fit whole batches of spectra that share a measurement grid in one kernel launch.
+
+Host code here only lays out parameters, scales data (O(N) numpy per spectrum) and unpacks results; the
+response matrices and the whole fit loop run in the CUDA library (engine.py).  Options of the reference
+that lie outside the hot-path scope raise NotImplementedError -- nothing silently falls back to CPU.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+
+
+def _not_supported(what):
+    raise NotImplementedError(f'{what} is outside the B200 hot-path scope of hybdrt_b200 (see DESIGN.md)')
+
+
+# ---- small host helpers (restate reference utilities; O(N) scalar work) ---------------------------
+def is_uniform(x):
+    """utils/array.py:142-151"""
+    d = np.diff(x)
+    return bool(np.std(d) / np.mean(d) <= 0.01)
+
+
+def unit_step(t, ts=0.0):
+    """utils/array.py:172-181"""
+    return (np.asarray(t) >= ts).astype(float)
+
+
+def nearest_index(arr, val, constraint=None):
+    """utils/array.py:207-242"""
+    arr = np.asarray(arr, dtype=float)
+    if constraint is None:
+        return int(np.argmin(np.abs(arr - val)))
+    obj = np.full(arr.shape, np.inf)
+    ok = constraint * arr >= constraint * val
+    obj[ok] = constraint * (arr - val)[ok]
+    idx = int(np.argmin(obj))
+    if obj[idx] == np.inf:
+        raise ValueError(f'No index satisfying {constraint} constraint for value {val}')
+    return idx
+
+
+def identify_steps(y, allow_consecutive=True, rthresh=50, athresh=1e-10):
+    """preprocessing.identify_steps, preprocessing.py:17-38"""
+    dy = np.diff(y)
+    idx = np.where((np.abs(dy) >= np.median(np.abs(dy)) * rthresh) & (np.abs(dy) >= athresh))[0] + 1
+    if not allow_consecutive:
+        gap = np.concatenate(([2], np.diff(idx)))
+        idx = idx[gap > 1]
+    return idx
+
+
+def step_indices_from_times(times, step_times):
+    """preprocessing.get_step_indices_from_step_times, preprocessing.py:161-178"""
+    out = []
+    for st in step_times:
+        d = np.where(times >= st, times - st, np.inf)
+        out.append(int(np.argmin(d)))
+    return np.array(out, dtype=int)
+
+
+def step_sizes_from_signal(times, y, step_times, step_index=None):
+    """preprocessing.get_step_sizes, preprocessing.py:105-129"""
+    if step_index is None:
+        step_index = step_indices_from_times(times, step_times)
+    n = len(step_times)
+    out = np.zeros(n)
+    for k in range(n):
+        end = len(y) if k == n - 1 else step_index[k + 1]
+        prev = 0 if k == 0 else step_index[k - 1]
+        out[k] = np.mean(y[step_index[k]:end]) - np.mean(y[prev:step_index[k]])
+    return out
+
+
+def step_info(times, y, offset_step_times=True, offset_size=None, rthresh=50):
+    """preprocessing.get_step_info (ideal step model), preprocessing.py:57-102"""
+    idx = identify_steps(y, True, rthresh)
+    st = times[idx].copy()
+    if offset_step_times:
+        if offset_size is None:
+            offset_size = -np.min(np.diff(times)) * (1 - 1e-8)
+        st = st + offset_size
+    return st, step_sizes_from_signal(times, y, st, step_index=idx)
+
+
+def time_since_step(times, step_times, prestep_value=None):
+    """preprocessing.get_time_since_step, preprocessing.py:918-945"""
+    t_sample = np.min(np.diff(times)) if len(times) > 1 else times[0]
+    parts = []
+    if prestep_value is not None:
+        parts.append(np.full(int(np.sum(times < step_times[0])), float(prestep_value)))
+    for i, st in enumerate(step_times):
+        en = step_times[i + 1] if i + 1 < len(step_times) else np.inf
+        sel = (times >= st) & (times < en)
+        if sel.any():
+            parts.append(np.maximum(times[sel] - st, t_sample))
+    return np.concatenate(parts)
+
+
+def get_basis_tau(frequencies, times, step_times, ppd=10, extend_decades=1, tau_grid=None):
+    """preprocessing.get_tau_lim + get_basis_tau, preprocessing.py:948-1013"""
+    lo, hi = np.inf, -np.inf
+    if frequencies is not None:
+        lo, hi = 1 / (2 * np.pi * np.max(frequencies)), 1 / (2 * np.pi * np.min(frequencies))
+    if times is not None:
+        td = time_since_step(times, step_times)
+        lo, hi = min(lo, np.min(td)), max(hi, np.max(td))
+    lmin, lmax = np.log10(lo) - extend_decades, np.log10(hi) + extend_decades
+    if tau_grid is not None:
+        tau_grid = np.asarray(tau_grid)
+        left = 0 if 10 ** lmin < np.min(tau_grid) else nearest_index(tau_grid, 10 ** lmin, -1)
+        right = len(tau_grid) if 10 ** lmax > np.max(tau_grid) else nearest_index(tau_grid, 10 ** lmax, 1) + 1
+        return tau_grid[left:right]
+    exact = (lmax - lmin) * ppd + 1
+    num = int(np.ceil(exact))
+    add = 0.5 * (num - exact) / ppd
+    return np.logspace(lmin - add, lmax + add, num)
+
+
+def estimate_rp_batch(times, step_times, step_sizes, response, z):
+    """preprocessing.estimate_rp (ideal steps), preprocessing.py:764-841, vectorised over the batch.
+
+    response [B, Nt] or None; z [B, Nf] complex or None.  Returns rp_est [B].
+    """
+    r_min = np.full(1, np.inf)
+    r_max = np.zeros(1)
+    if times is not None:
+        step_times = np.asarray(step_times, dtype=float)
+        step_sizes = np.asarray(step_sizes, dtype=float)
+        new_idx = np.concatenate(([0], np.where(np.diff(step_times) > 2e-5)[0] + 1))
+        if len(new_idx) < len(step_times):
+            bounds = list(new_idx) + [len(step_sizes)]
+            step_sizes = np.array([np.sum(step_sizes[a:b]) for a, b in zip(bounds[:-1], bounds[1:])])
+            step_times = step_times[new_idx]
+        sidx = step_indices_from_times(times, step_times)
+        mins, maxs = [], []
+        for i, start in enumerate(sidx):
+            end = len(times) if i == len(sidx) - 1 else sidx[i + 1]
+            if start == end:
+                mins.append(np.full(response.shape[0], np.nan))
+                maxs.append(np.full(response.shape[0], np.nan))
+                continue
+            r = (response[:, start:end] - response[:, start - 1:start]) / step_sizes[i]
+            mins.append(np.min(r, axis=1))
+            maxs.append(np.max(r, axis=1))
+        r_min = np.nanmean(np.array(mins), axis=0)
+        r_max = np.nanpercentile(np.array(maxs), 99, axis=0)
+    if z is not None:
+        r_min = np.minimum(r_min, np.min(z.real, axis=1))
+        r_max = np.maximum(r_max, np.max(z.real, axis=1))
+    return r_max - r_min
+
+
+_HYPER_KEYS = ('rp_scale', 'derivative_weights', 'sigma_ds', 'l1_lambda_0', 'l2_lambda_0', 'iw_alpha', 'iw_beta',
+               's_alpha', 's_0', 'rho_alpha', 'rho_0', 'outlier_p')
+_DOP_HYPER_KEYS = ('dop_l2_lambda_0', 'dop_l1_lambda_0', 'dop_derivative_weights', 'dop_s_alpha', 'dop_rho_alpha',
+                   'dop_s_0', 'dop_rho_0', 'dop_sigma_ds')
+
+
+def get_default_hypers(eff_hp=True, fit_dop=False):
+    """qphb.get_default_hypers, qphb.py:208-255"""
+    if not eff_hp:
+        s_alpha, rho_alpha = np.array([1.05, 1.15, 2.5]), np.array([0.05, 0.1, 0.05])
+    else:
+        s_alpha, rho_alpha = np.array([5.0, 10.0, 25.0]), np.array([0.15, 0.2, 0.25])
+    hyp = dict(rp_scale=14, derivative_weights=np.array([1.5, 1.0, 0.5]), sigma_ds=np.array([1.0, 1000.0, 1000.0]),
+               l1_lambda_0=0, l2_lambda_0=142, iw_alpha=None, iw_beta=None, s_alpha=s_alpha, s_0=np.ones(3),
+               rho_alpha=rho_alpha, rho_0=np.ones(3), outlier_p=None)
+    if fit_dop:
+        hyp.update(dop_l2_lambda_0=10, dop_l1_lambda_0=0, dop_derivative_weights=np.array([0.5, 1.0, 0.5]),
+                   dop_s_alpha=np.array([5.0, 10.0, 25.0]), dop_rho_alpha=np.array([0.15, 0.2, 0.25]),
+                   dop_s_0=np.ones(3), dop_rho_0=np.ones(3), dop_sigma_ds=np.array([1.0, 1000.0, 1000.0]))
+    return hyp
+
+
+class BatchFit:
+    """Results of one batched fit: device tensors + the plan that produced them + host-side unpacking."""
+
+    def __init__(self, plan, raw, scales, extra):
+        self.plan = plan
+        self.raw = raw              # dict of device tensors from Engine.qphb_fit_batch
+        self.scales = scales        # dict of per-spectrum host arrays (coefficient_scale, ...)
+        self.extra = extra
+        self._host = None
+
+    def host(self):
+        """Device -> host copy of every output (one synchronisation)."""
+        if self._host is None:
+            self._host = {k: v.cpu().numpy() for k, v in self.raw.items()}
+        return self._host
+
+    @property
+    def x_raw(self):
+        return self.host()['x']
+
+    def fit_parameters(self):
+        """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for the whole batch: dict of [B, ...] arrays."""
+        pl, h, sc = self.plan, self.host(), self.scales
+        x = h['x']
+        cs = sc['coefficient_scale'][:, None]
+        ns = pl['n_special']
+        out = {'x': x[:, ns:] * cs}
+        sp = pl['special_qp_params']
+        out['R_inf'] = x[:, sp['R_inf']['index']] * cs[:, 0] if 'R_inf' in sp else np.zeros(len(x))
+        out['inductance'] = (x[:, sp['inductance']['index']] * cs[:, 0] * pl['inductance_scale']
+                             if 'inductance' in sp else np.zeros(len(x)))
+        out['C_inv'] = (x[:, sp['C_inv']['index']] * cs[:, 0] * pl['capacitance_scale']
+                        if 'C_inv' in sp else np.zeros(len(x)))
+        if 'v_baseline' in sp:
+            a = sp['v_baseline']['index']
+            b = a + sp['v_baseline']['size']
+            vb = x[:, a:b] * (1.0 / pl['v_baseline_scale'])[None, :]
+            vb[:, 0] -= sc['scaled_response_offset']
+            out['v_baseline'] = vb * sc['response_signal_scale'][:, None]
+        if 'vz_offset' in sp:
+            out['vz_offset'] = x[:, sp['vz_offset']['index']]
+        if 'x_dop' in sp:
+            a = sp['x_dop']['index']
+            b = a + sp['x_dop']['size']
+            out['x_dop'] = x[:, a:b] * (pl['dop_scale_vector'][None, :] * cs)
+        # sigma from the unscaled weights (drt1d.py:1082-1092)
+        w_true = h['weights'] * pl['weight_factor']
+        sig = 1.0 / w_true
+        nc, nf = pl['n_chrono'], pl['n_freq']
+        out['v_sigma_tot'] = sig[:, :nc] * sc['response_signal_scale'][:, None] if nc else None
+        out['z_sigma_tot'] = (sig[:, nc:nc + nf] + 1j * sig[:, nc + nf:]) * cs if nf else None
+        return out
+
+    def predict_z(self, frequencies=None):
+        """DRT.predict_z at the fit frequencies (drt1d.py:3500-3542) for the whole batch."""
+        pl = self.plan
+        fp = self.fit_parameters()
+        if frequencies is not None and not np.array_equal(frequencies, pl['frequencies']):
+            _not_supported('batched predict_z at frequencies other than the fit grid')
+        f = pl['frequencies']
+        z = fp['x'] @ pl['zm_drt_host'].T + fp['R_inf'][:, None] + fp['inductance'][:, None] * 2j * np.pi * f[None, :]
+        z = z + fp['C_inv'][:, None] * (2j * np.pi * f[None, :]) ** -1
+        if 'x_dop' in fp:
+            z = z + fp['x_dop'] @ pl['zm_dop_host'].T
+        if 'vz_offset' in fp:
+            z = z * (1 - fp['vz_offset'][:, None] * pl['eis_vz_strength'][None, :])
+        return z
+
+
+class DRT:
+    """Mirror of hybdrt.models.DRT for the QPHB fit path (see module docstring)."""
+
+    def __init__(self, fixed_basis_tau=None, tau_supergrid=None, tau_basis_type='gaussian', tau_epsilon=None,
+                 basis_tau_ppd=10, extend_basis_decades=1,
+                 step_model='ideal', chrono_mode='galv', interpolate_integrals=True, chrono_tau_rise=None,
+                 fixed_basis_nu=None, nu_basis_type='gaussian', nu_epsilon=None, fit_dop=False, normalize_dop=True,
+                 fit_inductance=True, fit_ohmic=True, fit_capacitance=False,
+                 time_precision=10, input_signal_precision=10, frequency_precision=10,
+                 print_diagnostics=False, warn=True, device=0):
+        if tau_basis_type != 'gaussian':
+            _not_supported(f"tau_basis_type '{tau_basis_type}'")
+        if nu_basis_type != 'gaussian':
+            _not_supported(f"nu_basis_type '{nu_basis_type}'")
+        if step_model != 'ideal':
+            _not_supported(f"step_model '{step_model}'")
+        if chrono_mode != 'galv':
+            _not_supported(f"chrono_mode '{chrono_mode}'")
+        if fixed_basis_tau is not None and tau_supergrid is not None:
+            warnings.warn('If fixed_basis_tau is provided, tau_supergrid will be ignored')
+        self.engine = _engine.get_engine(device)
+        self.fixed_basis_tau = None if fixed_basis_tau is None else np.asarray(fixed_basis_tau, dtype=float)
+        self.tau_supergrid = None if tau_supergrid is None else np.asarray(tau_supergrid, dtype=float)
+        self.tau_basis_type, self.nu_basis_type = tau_basis_type, nu_basis_type
+        self.tau_epsilon = tau_epsilon
+        self.extend_basis_decades = extend_basis_decades
+        self.step_model, self.chrono_mode = step_model, chrono_mode
+        self.fixed_basis_nu = fixed_basis_nu
+        self.nu_epsilon = nu_epsilon
+        self.fit_dop, self.normalize_dop = fit_dop, normalize_dop
+        self.fit_inductance, self.fit_ohmic, self.fit_capacitance = fit_inductance, fit_ohmic, fit_capacitance
+        self.time_precision, self.input_signal_precision = time_precision, input_signal_precision
+        self.frequency_precision = frequency_precision
+        self.print_diagnostics, self.warn = print_diagnostics, warn
+        self.basis_tau = self.basis_nu = None
+        self.dop_scale_vector = None
+        self.special_qp_params = {}
+        self.fit_parameters = self.qphb_params = self.qphb_history = self.cvx_result = None
+        self.fit_type = self.fit_kwargs = None
+        self.coefficient_scale = self.impedance_scale = 1.0
+        self.input_signal_scale = self.response_signal_scale = 1.0
+        self.inductance_scale = self.capacitance_scale = None
+        self.step_times = self.step_sizes = self.nonconsec_step_times = None
+        self.t_fit, self.f_fit = [], []
+        self.last_batch = None
+        # drtbase.py:127-135
+        if self.tau_epsilon is None:
+            if self.fixed_basis_tau is not None:
+                self.tau_epsilon = 1 / np.mean(np.diff(np.log(self.fixed_basis_tau)))
+            elif self.tau_supergrid is not None:
+                self.tau_epsilon = 1 / np.mean(np.diff(np.log(self.tau_supergrid)))
+            elif basis_tau_ppd is not None:
+                self.tau_epsilon = 1 / np.log(10 ** (1 / basis_tau_ppd))
+        # drtbase.py:137-159: lookup tables (device resident) or direct quadrature
+        if interpolate_integrals:
+            self.integrate_method = 'interp'
+            self.interpolate_lookups = self.engine.build_lookup(self.tau_epsilon)
+        else:
+            self.integrate_method = 'trapz'
+            self.interpolate_lookups = None
+
+    # ------------------------------------------------------------------------------------------------
+    # reference-compatible bookkeeping
+    # ------------------------------------------------------------------------------------------------
+    def _add_special_qp_param(self, sp, name, nonneg, size=1):
+        sp[name] = {'index': int(sum(v.get('size', 1) for v in sp.values())), 'nonneg': nonneg, 'size': size}
+
+    def get_qp_mat_offset(self):
+        return int(sum(v.get('size', 1) for v in self.special_qp_params.values()))
+
+    def get_special_indices(self, key):
+        a = self.special_qp_params[key]['index']
+        return a, a + self.special_qp_params[key].get('size', 1)
+
+    @property
+    def dop_indices(self):
+        if 'x_dop' in self.special_qp_params:
+            return self.get_special_indices('x_dop')
+        return None, None
+
+    @property
+    def nu_basis_area(self):
+        return np.sqrt(np.pi) / self.nu_epsilon
+
+    @property
+    def tau_basis_area(self):
+        return np.sqrt(np.pi) / self.tau_epsilon
+
+    def get_fit_times(self):
+        return self.t_fit
+
+    def get_fit_frequencies(self):
+        return self.f_fit
+
+    # ------------------------------------------------------------------------------------------------
+    # plan: everything that is shared by the spectra of one batch (one measurement grid)
+    # ------------------------------------------------------------------------------------------------
+    def _mode(self):
+        return _engine.MODE_INTERP if self.integrate_method == 'interp' else _engine.MODE_TRAPZ
+
+    def _build_plan(self, times, i_signal, frequencies, kw):
+        eng = self.engine
+        dev = eng.dev
+        hyp = kw['hypers']
+        data_type = 'eis' if times is None else ('chrono' if frequencies is None else 'hybrid')
+
+        # special parameter layout, drt1d.py:374-410
+        sp = {}
+        if times is not None:
+            self._add_special_qp_param(sp, 'v_baseline', False, kw['v_baseline_deg'] + 1 + int(kw['v_baseline_sqrt']))
+        if kw['vz_offset'] and data_type == 'hybrid':
+            self._add_special_qp_param(sp, 'vz_offset', False)
+        if self.fit_ohmic:
+            self._add_special_qp_param(sp, 'R_inf', True)
+        if self.fit_inductance:
+            self._add_special_qp_param(sp, 'inductance', True)
+        if self.fit_capacitance:
+            self._add_special_qp_param(sp, 'C_inv', True)
+        if self.fit_dop:
+            if self.fixed_basis_nu is None:
+                self.basis_nu = np.concatenate([np.linspace(-1, -0.4, 25), np.linspace(0.4, 1, 25)])
+            else:
+                self.basis_nu = np.asarray(self.fixed_basis_nu, dtype=float)
+            if self.nu_epsilon is None:
+                self.nu_epsilon = 1 / np.median(np.diff(np.sort(self.basis_nu)))
+            self._add_special_qp_param(sp, 'x_dop', True, size=len(self.basis_nu))
+        else:
+            self.basis_nu = None
+        self.special_qp_params = sp
+        ns = self.get_qp_mat_offset()
+
+        # chrono signal processing, drtbase.py:285-373 (no downsampling)
+        if times is not None:
+            times = np.asarray(times, dtype=float)
+            i_signal = np.asarray(i_signal, dtype=float)
+            step_times, step_sizes = kw['step_times'], kw['step_sizes']
+            if step_times is None:
+                step_times, step_sizes = step_info(times, i_signal, kw['offset_steps'], kw['step_offset_size'])
+            else:
+                step_times = np.asarray(step_times, dtype=float)
+                if step_sizes is None:
+                    step_sizes = step_sizes_from_signal(times, i_signal, step_times)
+            if len(step_times) == 0:
+                raise ValueError('no steps found in the input signal')
+            if len(step_times) > 1:
+                t_sample = np.min(np.diff(times))
+                nonconsec = step_times[1:][np.diff(step_times) > 1.1 * t_sample]
+                self.nonconsec_step_times = np.insert(nonconsec, 0, step_times[0])
+            else:
+                self.nonconsec_step_times = step_times
+            self.step_times, self.step_sizes = step_times.copy(), np.asarray(step_sizes, dtype=float).copy()
+            self.t_fit = times
+            self.raw_input_signal = i_signal.copy()
+        else:
+            step_times = step_sizes = None
+            self.t_fit = []
+        if frequencies is not None:
+            frequencies = np.asarray(frequencies, dtype=float)
+            self.f_fit = frequencies
+        else:
+            self.f_fit = []
+
+        # basis grid, drt1d.py:5469-5485
+        if self.fixed_basis_tau is not None:
+            self.basis_tau = self.fixed_basis_tau
+        else:
+            self.basis_tau = get_basis_tau(frequencies, times, step_times, tau_grid=self.tau_supergrid,
+                                           extend_decades=self.extend_basis_decades)
+        if self.tau_epsilon is None:
+            self.tau_epsilon = 1 / np.mean(np.diff(np.log(self.basis_tau)))
+        tau, eps = self.basis_tau, self.tau_epsilon
+        nb = len(tau)
+        n = ns + nb
+        nc = 0 if times is None else len(times)
+        nf = 0 if frequencies is None else len(frequencies)
+        n_rows = nc + 2 * nf
+        mode = self._mode()
+
+        rm = torch.zeros(n_rows, n, dtype=torch.float64, device=eng.device)
+        plan = dict(data_type=data_type, special_qp_params=sp, n_special=ns, n=n, n_rows=n_rows, n_chrono=nc,
+                    n_freq=nf, frequencies=frequencies, times=times, basis_tau=tau,
+                    inductance_scale=kw['inductance_scale'], capacitance_scale=kw['capacitance_scale'],
+                    weight_factor=kw['weight_factor'], hypers=hyp)
+        self.inductance_scale, self.capacitance_scale = kw['inductance_scale'], kw['capacitance_scale']
+
+        # DOP scale vector, drt1d.py:5767-5788
+        if self.fit_dop:
+            if self.normalize_dop:
+                ev = self.tau_supergrid if self.tau_supergrid is not None else tau
+                lt = np.log(ev)
+                q1 = np.exp(lt.min() + 0.25 * (lt.max() - lt.min()))
+                q3 = np.exp(lt.min() + 0.75 * (lt.max() - lt.min()))
+                nu = self.basis_nu
+                self.dop_scale_vector = np.where(nu <= 0, q3 ** nu, q1 ** nu) / self.nu_basis_area
+            else:
+                self.dop_scale_vector = np.ones(len(self.basis_nu))
+            plan['dop_scale_vector'] = self.dop_scale_vector
+            dop_a, dop_b = self.dop_indices
+        else:
+            self.dop_scale_vector = None
+            dop_a = dop_b = None
+
+        # ---- chrono block, drt1d.py:5557-5623 + 5792-5819
+        if times is not None:
+            if self.fit_dop:
+                _not_supported('fit_dop with chrono data (time-domain phasance matrix)')
+            in_scale = float(np.max(np.abs(step_sizes)))        # drtbase.py:463, applied at drt1d.py:5543-5549
+            plan['input_signal_scale'] = in_scale if kw['scale_data'] else 1.0
+            iscale = plan['input_signal_scale']
+            rm_drt = eng.build_response(times[None], tau[None], np.asarray(step_times)[None],
+                                        np.asarray(step_sizes)[None], eps, mode, self.interpolate_lookups)[0]
+            rm[:nc, ns:] = rm_drt / iscale
+            if kw['smooth_inf_response']:                       # mat1d.py:399-421
+                inf_rv = np.zeros(nc)
+                for st, sa in zip(step_times, step_sizes):
+                    inf_rv += sa * unit_step(times, st)
+            else:
+                inf_rv = i_signal - np.mean(i_signal[times < step_times[0]])
+            cap_rv = np.zeros(nc)                               # mat1d.py:424-443
+            for st, sa in zip(step_times, step_sizes):
+                cap_rv[times >= st] += sa * (times[times >= st] - st)
+            a, b = sp['v_baseline']['index'], sp['v_baseline']['index'] + sp['v_baseline']['size']
+            vb = np.zeros((nc, b - a))                          # background.get_baseline_matrix :23-37
+            for d in range(kw['v_baseline_deg'] + 1):
+                vb[:, d] = (times - times[0]) ** d
+            if kw['v_baseline_sqrt']:
+                vb[:, -1] = (times - times[0]) ** 0.5
+            vb_scale = np.max(vb, axis=0)
+            plan['v_baseline_scale'] = vb_scale
+            rm[:nc, a:b] = dev(vb / vb_scale[None, :])
+            if 'R_inf' in sp:
+                rm[:nc, sp['R_inf']['index']] = dev(inf_rv / iscale)
+            if 'C_inv' in sp:
+                rm[:nc, sp['C_inv']['index']] = dev(cap_rv / iscale * kw['capacitance_scale'])
+            # inductance response is identically zero for ideal steps (mat1d.py:378-396)
+            plan['rm_drt_chrono'] = rm_drt
+            plan['inf_rv'], plan['cap_rv'] = inf_rv, cap_rv
+
+        # ---- EIS block, drt1d.py:5625-5671 + 5824-5857
+        if frequencies is not None:
+            a_re, a_im = eng.build_impedance(frequencies[None], tau[None], eps, mode, self.interpolate_lookups)
+            rm[nc:nc + nf, ns:] = a_re[0]
+            rm[nc + nf:, ns:] = a_im[0]
+            omega = 2 * np.pi * frequencies
+            if 'R_inf' in sp:
+                rm[nc:nc + nf, sp['R_inf']['index']] = 1.0
+            if 'inductance' in sp:
+                rm[nc + nf:, sp['inductance']['index']] = dev(omega * kw['inductance_scale'])
+            if 'C_inv' in sp:
+                rm[nc + nf:, sp['C_inv']['index']] = dev(-1.0 / omega * kw['capacitance_scale'])
+            if self.fit_dop:
+                zd = eng.build_dop_z(frequencies[None], self.basis_nu, self.nu_epsilon)[0]
+                zd = zd * dev(self.dop_scale_vector)[None, :]
+                rm[nc:nc + nf, dop_a:dop_b] = zd.real
+                rm[nc + nf:, dop_a:dop_b] = zd.imag
+                plan['zm_dop_dev'] = zd / dev(self.dop_scale_vector)[None, :]
+            plan['a_re'], plan['a_im'] = a_re[0], a_im[0]
+
+        # ---- penalty matrices, drt1d.py:5673-5734 + 5863-5910
+        pen = torch.zeros(3, n, n, dtype=torch.float64, device=eng.device)
+        m_drt = eng.build_penalty(np.log(tau)[None], eps, is_uniform(np.log(tau)))[0]
+        pen[:, ns:, ns:] = m_drt
+        diag = {'R_inf': kw['ohmic_penalty'], 'inductance': kw['inductance_penalty'],
+                'C_inv': kw['capacitance_penalty']}
+        for name, val in diag.items():
+            if name in sp:
+                i = sp[name]['index']
+                pen[:, i, i] = val
+        if 'v_baseline' in sp:
+            a, b = self.get_special_indices('v_baseline')
+            vbp = kw['v_baseline_penalty']
+            vals = np.full(b - a, vbp) if np.isscalar(vbp) else np.asarray(vbp, dtype=float)
+            if len(vals) != b - a:
+                raise ValueError('If v_baseline_penalty is iterable, it must match the number of v_baseline '
+                                 f'parameters. Number of v_baseline parameters is {b - a}')
+            for j, i in enumerate(range(a, b)):
+                pen[:, i, i] = float(vals[j])
+        if 'vz_offset' in sp:
+            i = sp['vz_offset']['index']
+            pen[:, i, i] = 1 / kw['vz_offset_scale']
+        if self.fit_dop:
+            m_dop = eng.build_penalty(self.basis_nu[None], self.nu_epsilon, is_uniform(self.basis_nu))[0]
+            pen[:, dop_a:dop_b, dop_a:dop_b] = m_dop
+        plan['pen'] = pen
+        plan['rm'] = rm
+
+        # ---- variance-estimation matrices, drt1d.py:614-636
+        if times is not None and kw['chrono_error_structure'] != 'uniform':
+            _not_supported("chrono_error_structure other than 'uniform'")
+        if frequencies is not None:
+            es = kw['eis_error_structure']
+            if es not in (None, 'uniform'):
+                raise ValueError(f'Invalid error structure {es}')
+            plan['vmm_eis'] = eng.build_eis_vmm(frequencies[None], kw['eis_vmm_epsilon'], kw['eis_reim_cor'],
+                                                es == 'uniform')[0]
+        else:
+            plan['vmm_eis'] = None
+
+        # ---- constraints and l1 vector, qphb.py:521-557, drt1d.py:556-561
+        h = np.zeros(n)
+        if kw['nonneg']:
+            for v in sp.values():
+                if not v['nonneg']:
+                    h[v['index']:v['index'] + v.get('size', 1)] = 1000
+        else:
+            rng = kw['neg_allowed_tau_range']
+            if rng is not None:
+                for v in sp.values():
+                    if not v['nonneg']:
+                        h[v['index']:v['index'] + v.get('size', 1)] = 1000
+                lo, hi = rng                                    # drt1d._get_neg_allowed_indices
+                idx = np.where((tau >= lo) & (tau <= hi))[0] + ns
+                h[idx] = 1e5
+            else:
+                h[:] = 1e5
+            for v in sp.values():
+                if v['nonneg']:
+                    h[v['index']:v['index'] + v.get('size', 1)] = 0
+        l1 = np.zeros(n)
+        l1[ns:] = hyp['l1_lambda_0']
+        if self.fit_dop:
+            l1[dop_a:dop_b] = hyp['dop_l1_lambda_0']
+        plan['h_host'], plan['l1_host'] = h, l1
+        plan['h'], plan['l1'] = dev(h), dev(l1)
+
+        # ---- hybrid vz_offset strength, drt1d.py:503-522 + 6173-6226
+        if 'vz_offset' in sp:
+            fit_td = time_since_step(times, self.nonconsec_step_times, prestep_value=-1)
+            chrono_tau_min = np.min(fit_td[fit_td > 0])
+            eis_tau_max = np.max(1 / (2 * np.pi * frequencies))
+            veps = kw['vz_offset_eps']
+            cs = np.ones(nc)
+            if veps is not None:
+                sel = fit_td >= eis_tau_max
+                cs[sel] = np.exp(-(veps * np.log(fit_td[sel] / eis_tau_max)) ** 2)
+                cs[fit_td == -1] = 0
+                f_inv = 1 / (2 * np.pi * frequencies)
+                es_ = np.ones(nf)
+                sel = f_inv <= chrono_tau_min
+                es_[sel] = np.exp(-(veps * np.log(f_inv[sel] / chrono_tau_min)) ** 2)
+            else:
+                es_ = np.ones(nf)
+            plan['chrono_vz_strength'], plan['eis_vz_strength'] = cs, es_
+            plan['vz_strength_host'] = np.concatenate([cs, es_, es_])
+            plan['vz_strength'] = dev(plan['vz_strength_host'])
+        return plan
+
+    def _c_hypers(self, kw):
+        hyp = kw['hypers']
+        ch = _engine.default_hypers()
+        for name in ('derivative_weights', 'sigma_ds', 's_alpha', 's_0', 'rho_alpha', 'rho_0'):
+            v = np.broadcast_to(np.asarray(hyp[name], dtype=float), (3,))
+            setattr(ch, name, (_engine._D3)(*v))
+        ch.l2_lambda_0 = float(hyp['l2_lambda_0'])
+        if self.fit_dop:
+            for name in ('dop_derivative_weights', 'dop_sigma_ds', 'dop_s_alpha', 'dop_s_0', 'dop_rho_alpha',
+                         'dop_rho_0'):
+                v = np.broadcast_to(np.asarray(hyp[name], dtype=float), (3,))
+                setattr(ch, name, (_engine._D3)(*v))
+            ch.dop_l2_lambda_0 = float(hyp['dop_l2_lambda_0'])
+        ch.iw_l1_lambda_0, ch.iw_l2_lambda_0 = float(kw['iw_l1_lambda_0']), float(kw['iw_l2_lambda_0'])
+        if hyp['iw_alpha'] is not None:
+            ch.has_iw_prior, ch.iw_alpha, ch.iw_beta = 1, float(hyp['iw_alpha']), float(hyp['iw_beta'])
+        ch.xtol, ch.max_iter = float(kw['xtol']), int(kw['max_iter'])
+        ch.weight_factor = float(kw['weight_factor'])
+        ch.chrono_weight_factor = float(kw['chrono_weight_factor'])
+        ch.eis_weight_factor = float(kw['eis_weight_factor'])
+        return ch
+
+    # ------------------------------------------------------------------------------------------------
+    # the batched fit core
+    # ------------------------------------------------------------------------------------------------
+    def _fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, want_pq=False, step_times=None,
+                        step_sizes=None, nonneg=True, neg_allowed_tau_range=None, series_neg=False,
+                        scale_data=True, update_scale=False, solve_rp=False,
+                        offset_steps=True, step_offset_size=None, discard_first_n=None,
+                        offset_baseline=True, v_baseline_deg=0, v_baseline_sqrt=False,
+                        downsample=False, downsample_kw=None, subtract_background=False, background_type='static',
+                        background_corr_power=None, estimate_background_kw=None, smooth_inf_response=True,
+                        v_baseline_penalty=1e-6, ohmic_penalty=1e-6, inductance_penalty=1e-6,
+                        capacitance_penalty=1e-6, inductance_scale=1e-5, capacitance_scale=1e-3,
+                        background_penalty=1, penalty_type='integral', remove_extremes=False, extreme_kw=None,
+                        init_weights_separately=False, chrono_error_structure='uniform', eis_error_structure=None,
+                        remove_outliers=False, return_outlier_index=False, outlier_thresh=0.75,
+                        chrono_vmm_epsilon=4, eis_vmm_epsilon=0.25, eis_reim_cor=0.25,
+                        iw_l1_lambda_0=1e-4, iw_l2_lambda_0=1e-4,
+                        vz_offset=True, vz_offset_scale=1, vz_offset_eps=1,
+                        eis_weight_factor=None, chrono_weight_factor=None, hybrid_weight_factor_method=None,
+                        eff_hp=True, weight_factor=1, xtol=1e-2, max_iter=50, peak_locations=None, **kw):
+        # options outside the hot path (same keyword names as drt1d.py:102-137)
+        for flag, name in ((series_neg, 'series_neg'), (update_scale, 'update_scale'), (solve_rp, 'solve_rp'),
+                           (downsample, 'downsample'), (subtract_background, 'subtract_background'),
+                           (remove_extremes, 'remove_extremes'), (remove_outliers, 'remove_outliers'),
+                           (return_outlier_index, 'return_outlier_index'),
+                           (init_weights_separately, 'init_weights_separately'),
+                           (discard_first_n is not None, 'discard_first_n'), (peak_locations is not None,
+                                                                            'peak_locations'),
+                           (hybrid_weight_factor_method is not None, 'hybrid_weight_factor_method')):
+            if flag:
+                _not_supported(f'{name}')
+        if penalty_type != 'integral':
+            _not_supported(f"penalty_type '{penalty_type}'")
+        if not eff_hp:
+            _not_supported('eff_hp=False')
+        if nonneg and neg_allowed_tau_range is not None:        # drt1d.py:83-84
+            raise ValueError('If nonneg==True, neg_allowed_tau_range cannot be specified')
+        hypers = get_default_hypers(eff_hp, self.fit_dop)
+        for key in kw:                                          # drt1d.py:415-419
+            if key not in hypers:
+                raise ValueError(f'Invalid keyword argument {key}')
+        hypers.update(kw)
+        if hypers['outlier_p'] is not None:
+            _not_supported('outlier_p')
+        if (eis_weight_factor is None) != (chrono_weight_factor is None):
+            warnings.warn('Both eis_weight_factor and chrono_weight_factor must be provided. '
+                          'If only one is provided, it will be ignored.')
+        if eis_weight_factor is None or chrono_weight_factor is None:
+            eis_weight_factor = chrono_weight_factor = 1
+        opts = dict(hypers=hypers, step_times=step_times, step_sizes=step_sizes, nonneg=nonneg,
+                    neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data, offset_steps=offset_steps,
+                    step_offset_size=step_offset_size, offset_baseline=offset_baseline,
+                    v_baseline_deg=v_baseline_deg, v_baseline_sqrt=v_baseline_sqrt,
+                    smooth_inf_response=smooth_inf_response, v_baseline_penalty=v_baseline_penalty,
+                    ohmic_penalty=ohmic_penalty, inductance_penalty=inductance_penalty,
+                    capacitance_penalty=capacitance_penalty, inductance_scale=inductance_scale,
+                    capacitance_scale=capacitance_scale, chrono_error_structure=chrono_error_structure,
+                    eis_error_structure=eis_error_structure, eis_vmm_epsilon=eis_vmm_epsilon,
+                    eis_reim_cor=eis_reim_cor, iw_l1_lambda_0=iw_l1_lambda_0, iw_l2_lambda_0=iw_l2_lambda_0,
+                    vz_offset=vz_offset, vz_offset_scale=vz_offset_scale, vz_offset_eps=vz_offset_eps,
+                    eis_weight_factor=eis_weight_factor, chrono_weight_factor=chrono_weight_factor,
+                    weight_factor=weight_factor, xtol=xtol, max_iter=max_iter)
+        self.v_baseline_deg, self.v_baseline_sqrt = v_baseline_deg, v_baseline_sqrt
+        if z_batch is not None:
+            z_batch = np.asarray(z_batch)
+            if z_batch.ndim != 2 or z_batch.shape[1] != len(frequencies):
+                raise ValueError('z must have shape [batch, len(frequencies)]')
+        if v_batch is not None:
+            v_batch = np.asarray(v_batch, dtype=float)
+            if v_batch.ndim != 2 or v_batch.shape[1] != len(times):
+                raise ValueError('v_signal must have shape [batch, len(times)]')
+        batch = len(z_batch) if z_batch is not None else len(v_batch)
+
+        plan = self._build_plan(times, i_signal, frequencies, opts)
+        plan['opts'] = opts
+        sp, nc, nf = plan['special_qp_params'], plan['n_chrono'], plan['n_freq']
+        self.fit_kwargs = dict(smooth_inf_response=smooth_inf_response, offset_steps=offset_steps,
+                               step_offset_size=step_offset_size, nonneg=nonneg, eff_hp=eff_hp,
+                               penalty_type=penalty_type, subtract_background=False, background_type=background_type,
+                               background_corr_power=background_corr_power,
+                               neg_allowed_tau_range=neg_allowed_tau_range, **hypers)
+
+        # ---- scale_data (drtbase.py:439-514), vectorised over the batch
+        if scale_data:
+            rp_est = estimate_rp_batch(plan['times'], self.step_times, self.step_sizes, v_batch, z_batch)
+            cscale = rp_est / hypers['rp_scale']
+        else:
+            rp_est = np.ones(batch)
+            cscale = np.ones(batch)
+        scales = dict(coefficient_scale=cscale)
+        rv = np.empty((batch, plan['n_rows']))
+        if nc:
+            rscale = plan['input_signal_scale'] * rp_est / hypers['rp_scale'] if scale_data else np.ones(batch)
+            v_scaled = v_batch / rscale[:, None]
+            pre = plan['times'] < self.step_times[0]
+            baseline = np.median(v_scaled[:, pre], axis=1)                       # drt1d.py:5534-5538
+            offset = -baseline if offset_baseline else np.zeros(batch)          # drt1d.py:525-531
+            rv[:, :nc] = v_scaled + offset[:, None]
+            scales.update(response_signal_scale=rscale, scaled_response_offset=offset)
+        if nf:
+            zs = z_batch / cscale[:, None]
+            rv[:, nc:nc + nf] = zs.real
+            rv[:, nc + nf:] = zs.imag
+        eng = self.engine
+        rv_dev = eng.dev(rv)
+        dop_range = self.dop_indices if self.fit_dop else None
+        vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
+        vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
+        raw = eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
+                                 vmm_eis=plan['vmm_eis'], vmm_chrono=None, n_chrono=nc, dop_range=dop_range,
+                                 vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
+                                 hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
+                                 want_pq=want_pq)
+        if nf:
+            plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
+            if self.fit_dop:
+                plan['zm_dop_host'] = plan['zm_dop_dev'].cpu().numpy()
+        res = BatchFit(plan, raw, scales, dict(rv=rv))
+        self.last_batch = res
+        self.fit_type = f"qphb_{plan['data_type']}"
+        return res
+
+    # ------------------------------------------------------------------------------------------------
+    # public batched API (new; the reference fits one spectrum per call, drtmd.py:311-312)
+    # ------------------------------------------------------------------------------------------------
+    def fit_eis_batch(self, frequencies, z, nonneg=True, neg_allowed_tau_range=None, scale_data=True,
+                      update_scale=False, error_structure=None, vmm_epsilon=0.25, vmm_reim_cor=0.25, **kwargs):
+        """fit_eis for z [batch, len(frequencies)] on a shared frequency grid.  Returns a BatchFit."""
+        return self._fit_core_batch(None, None, None, frequencies, z, nonneg=nonneg,
+                                    neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data,
+                                    update_scale=update_scale, eis_error_structure=error_structure,
+                                    eis_vmm_epsilon=vmm_epsilon, eis_reim_cor=vmm_reim_cor, **kwargs)
+
+    def fit_chrono_batch(self, times, i_signal, v_signal, step_times=None, step_sizes=None, nonneg=True,
+                         error_structure='uniform', vmm_epsilon=4, **kwargs):
+        """fit_chrono for v_signal [batch, len(times)] with a shared time grid and input signal."""
+        return self._fit_core_batch(times, i_signal, v_signal, None, None, step_times=step_times,
+                                    step_sizes=step_sizes, nonneg=nonneg, chrono_error_structure=error_structure,
+                                    chrono_vmm_epsilon=vmm_epsilon, **kwargs)
+
+    def fit_hybrid_batch(self, times, i_signal, v_signal, frequencies, z, step_times=None, step_sizes=None,
+                         nonneg=True, **kwargs):
+        """fit_hybrid for v_signal [batch, Nt], z [batch, Nf] with shared grids and input signal."""
+        return self._fit_core_batch(times, i_signal, v_signal, frequencies, z, step_times=step_times,
+                                    step_sizes=step_sizes, nonneg=nonneg, **kwargs)
+
+    # ------------------------------------------------------------------------------------------------
+    # reference single-spectrum API (drt1d.py:1197-1268)
+    # ------------------------------------------------------------------------------------------------
+    def _qphb_fit_core(self, times, i_signal, v_signal, frequencies, z, **kw):
+        v_b = None if v_signal is None else np.asarray(v_signal, dtype=float)[None, :]
+        z_b = None if z is None else np.asarray(z)[None, :]
+        res = self._fit_core_batch(times, i_signal, v_b, frequencies, z_b, want_pq=True, **kw)
+        self._store_single(res)
+
+    def fit_eis(self, frequencies, z, nonneg=True, neg_allowed_tau_range=None, scale_data=True, update_scale=False,
+                error_structure=None, vmm_epsilon=0.25, vmm_reim_cor=0.25, **kwargs):
+        self._qphb_fit_core(None, None, None, frequencies, z, nonneg=nonneg,
+                            neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data,
+                            update_scale=update_scale, eis_error_structure=error_structure,
+                            eis_vmm_epsilon=vmm_epsilon, eis_reim_cor=vmm_reim_cor, **kwargs)
+
+    def fit_chrono(self, times, i_signal, v_signal, step_times=None, step_sizes=None, nonneg=True,
+                   neg_allowed_tau_range=None, scale_data=True, update_scale=False, offset_baseline=True,
+                   offset_steps=True, step_offset_size=None, discard_first_n=None, subtract_background=False,
+                   estimate_background_kw=None, downsample=False, downsample_kw=None, smooth_inf_response=True,
+                   error_structure='uniform', vmm_epsilon=4, **kwargs):
+        self._qphb_fit_core(times, i_signal, v_signal, None, None, step_times=step_times, step_sizes=step_sizes,
+                            nonneg=nonneg, neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data,
+                            update_scale=update_scale, offset_steps=offset_steps, step_offset_size=step_offset_size,
+                            discard_first_n=discard_first_n, offset_baseline=offset_baseline, downsample=downsample,
+                            downsample_kw=downsample_kw, subtract_background=subtract_background,
+                            estimate_background_kw=estimate_background_kw, smooth_inf_response=smooth_inf_response,
+                            chrono_error_structure=error_structure, chrono_vmm_epsilon=vmm_epsilon, **kwargs)
+
+    def fit_hybrid(self, times, i_signal, v_signal, frequencies, z, step_times=None, step_sizes=None, nonneg=True,
+                   neg_allowed_tau_range=None, scale_data=True, update_scale=False, offset_steps=True,
+                   step_offset_size=None, discard_first_n=None, offset_baseline=True, subtract_background=False,
+                   estimate_background_kw=None, downsample=False, downsample_kw=None, smooth_inf_response=True,
+                   vz_offset=True, vz_offset_scale=1, vz_offset_eps=1, chrono_error_structure='uniform',
+                   eis_error_structure=None, chrono_vmm_epsilon=4, eis_vmm_epsilon=0.25, eis_reim_cor=0.25,
+                   eis_weight_factor=None, chrono_weight_factor=None, **kwargs):
+        self._qphb_fit_core(times, i_signal, v_signal, frequencies, z, step_times=step_times, step_sizes=step_sizes,
+                            nonneg=nonneg, neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data,
+                            update_scale=update_scale, offset_steps=offset_steps, step_offset_size=step_offset_size,
+                            discard_first_n=discard_first_n, offset_baseline=offset_baseline, downsample=downsample,
+                            downsample_kw=downsample_kw, subtract_background=subtract_background,
+                            estimate_background_kw=estimate_background_kw, smooth_inf_response=smooth_inf_response,
+                            chrono_error_structure=chrono_error_structure, eis_error_structure=eis_error_structure,
+                            chrono_vmm_epsilon=chrono_vmm_epsilon, eis_vmm_epsilon=eis_vmm_epsilon,
+                            eis_reim_cor=eis_reim_cor, vz_offset=vz_offset, vz_offset_scale=vz_offset_scale,
+                            vz_offset_eps=vz_offset_eps, eis_weight_factor=eis_weight_factor,
+                            chrono_weight_factor=chrono_weight_factor, **kwargs)
+
+    def _store_single(self, res):
+        """Populate the attributes DRT._qphb_fit_core leaves behind (drt1d.py:1040-1104)."""
+        pl, h, sc, opts = res.plan, res.host(), res.scales, res.plan['opts']
+        st = int(h['status'][0])
+        if st & (_engine.ST_NAN | _engine.ST_KKT_FAIL) and not np.all(np.isfinite(h['x'][0])):
+            raise ValueError('Rank(A) < p or Rank([P; A; G]) < n')          # what cvxopt raises
+        if (st & _engine.ST_MAXITER) and self.warn:
+            warnings.warn(f"Solution did not converge within {opts['max_iter']} iterations. "
+                          'This is usually not an issue.')
+        nc = pl['n_chrono']
+        self.coefficient_scale = float(sc['coefficient_scale'][0])
+        self.impedance_scale = self.coefficient_scale if pl['n_freq'] else 1.0
+        if nc:
+            self.input_signal_scale = pl['input_signal_scale']
+            self.response_signal_scale = float(sc['response_signal_scale'][0])
+            self.scaled_response_offset = float(sc['scaled_response_offset'][0])
+            self.v_baseline_scale = pl['v_baseline_scale']
+        fp_b = res.fit_parameters()
+        fp = {}
+        for k, v in fp_b.items():
+            fp[k] = None if v is None else (v[0] if np.ndim(v) >= 1 else v)
+        fp['v_sigma_res'] = None
+        fp['vz_offset_eps'] = opts['vz_offset_eps']
+        fp['p_matrix'] = h['p_matrix'][0]
+        fp['q_vector'] = h['q_vector'][0]
+        self.fit_parameters = fp
+        self.cvx_result = {'x': h['x'][0], 'primal objective': float(h['fun'][0]),
+                           'status': 'unknown' if st & (_engine.ST_QP_MAXITERS | _engine.ST_KKT_FAIL) else 'optimal'}
+        w_true = h['weights'][0] * opts['weight_factor']
+        w_scaled = w_true.copy()
+        if pl['data_type'] == 'hybrid':
+            w_scaled[:nc] *= opts['chrono_weight_factor']
+            w_scaled[nc:] *= opts['eis_weight_factor']
+        rm = pl['rm'].cpu().numpy()
+        if 'vz_offset' in pl['special_qp_params']:
+            rm[:, pl['special_qp_params']['vz_offset']['index']] = h['vz_col'][0]
+        pen = pl['pen'].cpu().numpy()
+        x_of = h['x_overfit'][0]
+        self.qphb_params = {
+            'est_weights': h['est_weights'][0], 'init_weights': h['init_weights'][0], 'weights': w_scaled,
+            'true_weights': w_true, 'xmx_norms': h['xmx_norms'][0],
+            'dop_xmx_norms': h['dop_xmx_norms'][0] if 'dop_xmx_norms' in h else np.ones(3),
+            'x_overfit_chrono': x_of if pl['data_type'] == 'chrono' else (x_of[:nc] if nc else None),
+            'x_overfit_eis': x_of if pl['data_type'] == 'eis' else (x_of[nc:] if pl['n_freq'] else None),
+            'p_matrix': fp['p_matrix'], 'q_vector': fp['q_vector'], 'rho_vector': h['rho'][0],
+            'dop_rho_vector': h['dop_rho'][0] if 'dop_rho' in h else None,
+            's_vectors': [h['s_vectors'][0, k] for k in range(3)],
+            'vmm': None if pl['vmm_eis'] is None else pl['vmm_eis'].cpu().numpy(),
+            'l1_lambda_vector': pl['l1_host'], 'rm': rm, 'rv': res.extra['rv'][0],
+            'penalty_matrices': {f'm{k}': pen[k] for k in range(3)}, 'hypers': pl['hypers'],
+            'num_eis': pl['n_freq'], 'num_chrono': nc,
+            'chrono_weight_factor': opts['chrono_weight_factor'], 'eis_weight_factor': opts['eis_weight_factor'],
+            'vz_strength_vec': pl.get('vz_strength_host', 1),
+            'n_outer': int(h['n_outer'][0]), 'n_ipm': int(h['n_ipm'][0]), 'status': st,
+        }
+        self.qphb_history = None    # per-iteration history is not exported by the batched kernel
+
+    # ------------------------------------------------------------------------------------------------
+    # prediction (drt1d.py:3363-3542); matrices are rebuilt on the GPU for the requested grid
+    # ------------------------------------------------------------------------------------------------
+    def _vz_strength(self, times=None, frequencies=None):
+        """drt1d._get_vz_strength_vec, drt1d.py:6173-6226"""
+        veps = self.fit_parameters.get('vz_offset_eps', None) if self.fit_parameters else None
+        have = len(self.t_fit) > 0 and len(self.f_fit) > 0 and veps is not None
+        cs = es = None
+        if have:
+            fit_td = time_since_step(self.t_fit, self.nonconsec_step_times, prestep_value=-1)
+            chrono_tau_min = np.min(fit_td[fit_td > 0])
+            eis_tau_max = np.max(1 / (2 * np.pi * np.asarray(self.f_fit)))
+        if times is not None:
+            cs = np.ones(len(times))
+            if have:
+                td = time_since_step(times, self.nonconsec_step_times, prestep_value=-1)
+                sel = td >= eis_tau_max
+                cs[sel] = np.exp(-(veps * np.log(td[sel] / eis_tau_max)) ** 2)
+                cs[td == -1] = 0
+        if frequencies is not None:
+            es = np.ones(len(frequencies))
+            if have:
+                f_inv = 1 / (2 * np.pi * frequencies)
+                sel = f_inv <= chrono_tau_min
+                es[sel] = np.exp(-(veps * np.log(f_inv[sel] / chrono_tau_min)) ** 2)
+        return cs, es
+
+    def predict_z(self, frequencies, include_vz_offset=True, x=None, include_dop=True, include_drt=True,
+                  include_inductance=True, include_ohmic=True, include_cap=True):
+        frequencies = np.asarray(frequencies, dtype=float)
+        fp = self.fit_parameters if x is None else x
+        if not isinstance(fp, dict):
+            _not_supported('predict_z with a raw coefficient vector')
+        a_re, a_im = self.engine.build_impedance(frequencies[None], self.basis_tau[None], self.tau_epsilon,
+                                                 self._mode(), self.interpolate_lookups)
+        zm = (a_re[0] + 1j * a_im[0]).cpu().numpy()
+        z = np.zeros(len(frequencies), dtype=complex)
+        if include_drt:
+            z += zm @ fp['x']
+        if include_ohmic:
+            z += fp.get('R_inf', 0)
+        if include_inductance:
+            z += fp.get('inductance', 0) * 2j * np.pi * frequencies
+        if include_cap:
+            z += fp.get('C_inv', 0) * (2j * np.pi * frequencies) ** -1
+        if fp.get('x_dop') is not None and include_dop:
+            zd = self.engine.build_dop_z(frequencies[None], self.basis_nu, self.nu_epsilon)[0].cpu().numpy()
+            z += zd @ fp['x_dop']
+        if include_vz_offset:
+            _, es = self._vz_strength(None, frequencies)
+            z *= (1 - fp.get('vz_offset', 0) * es)
+        return z
+
+    def predict_response(self, times=None, include_vz_offset=True):
+        """Voltage response at the fit times (drt1d.py:3363-3461)."""
+        if times is not None and not np.array_equal(times, self.t_fit):
+            _not_supported('predict_response at times other than the fit times')
+        pl, fp = self.last_batch.plan, self.fit_parameters
+        times = pl['times']
+        rm_drt = pl['rm_drt_chrono'].cpu().numpy()
+        resp = rm_drt @ fp['x'] + pl['inf_rv'] * fp.get('R_inf', 0) + fp.get('C_inv', 0) * pl['cap_rv']
+        if include_vz_offset:
+            cs, _ = self._vz_strength(times, None)
+            resp = resp * (1 + fp.get('vz_offset', 0) * cs)
+        vb = np.zeros((len(times), len(fp['v_baseline'])))
+        for d in range(self.v_baseline_deg + 1):
+            vb[:, d] = (times - times[0]) ** d
+        if self.v_baseline_sqrt:
+            vb[:, -1] = (times - times[0]) ** 0.5
+        return resp + vb @ fp['v_baseline']
+
+    def predict_r_p(self, absolute=False):
+        """Polarisation resistance: sum of DRT coefficients times basis area (drt1d.py:3552-3590)."""
+        x = self.fit_parameters['x']
+        return float(np.sum(np.abs(x) if absolute else x) * self.tau_basis_area)
+
+    def predict_sigma(self, measurement):
+        key = 'v_sigma_tot' if measurement == 'chrono' else 'z_sigma_tot'
+        return self.fit_parameters.get(key, None)

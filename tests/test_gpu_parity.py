@@ -1,0 +1,328 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs and
+against the fixtures produced by the unmodified reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): response matrices 1e-10 relative; fitted coefficients, predicted
+impedance and the objective 1e-6 relative.  'Relative' is norm-wise, max|a-b|/max|b| (coefficients
+pinned at the non-negativity bound sit at ~1e-7 of the peak)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+MAT_TOL = 1e-10
+FIT_TOL = 1e-6
+
+
+@pytest.fixture(scope='module')
+def eng():
+    import __graft_entry__ as g
+    g.build()
+    from hybdrt_b200 import engine
+    return engine.get_engine(0)
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import drt_oracle
+    return drt_oracle
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# L1: matrix builders
+# ---------------------------------------------------------------------------------------------------
+def test_lookup_tables(eng, lookup_golden):
+    tab = eng.build_lookup(float(lookup_golden['eps']))
+    for key in ('re_x', 're_v', 'im_x', 'im_v', 'resp_x', 'resp_v'):
+        assert rel_err(_np(tab[key]), lookup_golden[key]) < MAT_TOL, key
+
+
+def test_matrix_fixtures(eng, lookup_golden):
+    from hybdrt_b200 import engine as E, synth
+    m = load_golden('matrices.npz')
+    eps = float(m['eps'])
+    for mode, name in ((E.MODE_INTERP, 'interp'), (E.MODE_TRAPZ, 'trapz')):
+        a_re, a_im = eng.build_impedance(m['f_irreg'][None], m['tau_irreg'][None], eps, mode)
+        assert rel_err(_np(a_re[0]), m[f'irreg_{name}_real']) < MAT_TOL
+        assert rel_err(_np(a_im[0]), m[f'irreg_{name}_imag']) < MAT_TOL
+        rm = eng.build_response(m['t_resp'][None], m['tau_resp'][None], m['step_times'][None],
+                                m['step_sizes'][None], eps, mode)
+        assert rel_err(_np(rm[0]), m[f'resp_{name}']) < MAT_TOL
+    a_re, a_im = eng.build_impedance(synth.C2_FREQ[None], m['tau_c2'][None], eps, E.MODE_TRAPZ)
+    assert rel_err(_np(a_re[0]), m['c2_trapz_real']) < MAT_TOL
+    assert rel_err(_np(a_im[0]), m['c2_trapz_imag']) < MAT_TOL
+    pen_i = _np(eng.build_penalty(np.log(m['tau_irreg'])[None], eps, False)[0])
+    pen_u = _np(eng.build_penalty(np.log(m['tau_c2'])[None], eps, True)[0])
+    for k in range(3):
+        assert rel_err(pen_i[k], m[f'pen_irreg_{k}']) < MAT_TOL
+        assert rel_err(pen_u[k], m[f'pen_c2_{k}']) < MAT_TOL
+    assert rel_err(_np(eng.build_eis_vmm(m['f_irreg'][None])[0]), m['vmm_irreg']) < MAT_TOL
+    assert rel_err(_np(eng.build_eis_vmm(m['f_irreg'][None], uniform=True)[0]), m['vmm_uniform']) < MAT_TOL
+    d = load_golden('dop.npz')
+    zd = _np(eng.build_dop_z(d['freq'][None], d['basis_nu'], float(d['nu_epsilon']))[0])
+    assert rel_err(zd, d['zm_dop']) < MAT_TOL
+
+
+def test_matrices_many_grids_vs_oracle(eng, orc, lookup_golden):
+    """Ragged/edge grids: per-spectrum grids, values far outside the table span (edge clamping), one row."""
+    from hybdrt_b200 import engine as E
+    eps = float(lookup_golden['eps'])
+    rng = np.random.default_rng(11)
+    g, nf, nb = 5, 9, 13
+    freq = 10 ** rng.uniform(-4, 7.5, (g, nf))
+    tau = np.sort(10 ** rng.uniform(-9, 4, (g, nb)), axis=1)
+    a_re, a_im = eng.build_impedance(freq, tau, eps, E.MODE_INTERP)
+    for i in range(g):
+        assert rel_err(_np(a_re[i]), orc.impedance_matrix(freq[i], tau[i], eps, 'real', 'interp', lookup_golden)) < MAT_TOL
+        assert rel_err(_np(a_im[i]), orc.impedance_matrix(freq[i], tau[i], eps, 'imag', 'interp', lookup_golden)) < MAT_TOL
+    a_re, a_im = eng.build_impedance(freq[:1, :1], tau[:1], eps, E.MODE_TRAPZ)
+    assert rel_err(_np(a_re[0]), orc.impedance_matrix(freq[0, :1], tau[0], eps, 'real', 'trapz')) < MAT_TOL
+    times = np.sort(rng.uniform(-0.01, 3.0, (g, 40)), axis=1)
+    st = np.stack([np.array([0.0, 1.0 + 0.1 * i]) for i in range(g)])
+    sa = rng.uniform(-1, 1, (g, 2))
+    rm = eng.build_response(times, tau, st, sa, eps, E.MODE_INTERP)
+    for i in range(g):
+        assert rel_err(_np(rm[i]), orc.response_matrix(tau[i], times[i], st[i], sa[i], eps, 'interp', lookup_golden)) < MAT_TOL
+    pen = eng.build_penalty(np.log(tau), eps, False)
+    for i in range(g):
+        for k in range(3):
+            assert rel_err(_np(pen[i, k]), orc.penalty_matrix(np.log(tau[i]), k, eps)) < MAT_TOL
+    vmm = eng.build_eis_vmm(freq)
+    for i in range(g):
+        assert rel_err(_np(vmm[i]), orc.eis_vmm(freq[i])) < MAT_TOL
+        assert np.allclose(_np(vmm[i]).sum(axis=1), 1.0, atol=1e-14)      # rows are averaging weights
+
+
+def test_interp_matrix_properties_at_scale(eng):
+    """Size-independent properties on a large batch of grids: A_re in (0, area], monotone in omega, A_im < 0."""
+    from hybdrt_b200 import engine as E
+    rng = np.random.default_rng(5)
+    g = 2048
+    freq = np.sort(10 ** rng.uniform(-2, 6, (g, 70)), axis=1)[:, ::-1].copy()
+    tau = np.logspace(-7.2, 2.2, 101)[None].repeat(g, axis=0)
+    eps = 1 / np.log(10 ** 0.1)
+    a_re, a_im = eng.build_impedance(freq, tau, eps, E.MODE_INTERP)
+    area = np.sqrt(np.pi) / eps
+    assert float(a_re.max()) <= area * (1 + 1e-12) and float(a_re.min()) > 0
+    assert float(a_im.max()) < 0
+    assert bool((a_re[:, 1:, :] >= a_re[:, :-1, :] - 1e-15).all())        # rows ordered by decreasing frequency
+
+
+# ---------------------------------------------------------------------------------------------------
+# L2: batched QPHB solver vs oracle and reference fixtures
+# ---------------------------------------------------------------------------------------------------
+def _eis_launch(eng, prep, rvs, **kw):
+    d = eng.dev
+    out = eng.qphb_fit_batch(d(prep.rm), d(rvs), d(np.array(prep.pen)), d(prep.h), d(prep.l1), 2,
+                             vmm_eis=d(prep.vmm), **kw)
+    torch.cuda.synchronize()
+    return {k: _np(v) for k, v in out.items()}
+
+
+def test_reference_golden_vector_through_the_kernel(eng, orc, lookup_golden):
+    c1 = load_golden('c1_golden.npz')
+    prep = orc.EisPrep(c1['freq'], tables=lookup_golden)
+    prob, scale = prep.problem(c1['z'])
+    out = _eis_launch(eng, prep, prob['rv'][None], want_pq=True)
+    assert int(out['n_outer'][0]) == int(c1['n_outer'])
+    assert int(out['n_ipm'][0]) == int(c1['qp_log'].sum())
+    assert rel_err(out['x'][0], c1['cvx_x']) < FIT_TOL
+    assert rel_err(out['weights'][0], c1['true_weights']) < FIT_TOL
+    assert rel_err(out['p_matrix'][0], c1['p_matrix']) < FIT_TOL
+    assert rel_err(out['q_vector'][0], c1['q_vector']) < FIT_TOL
+    assert abs(out['fun'][0] - c1['hist_fun'][-1]) <= FIT_TOL * abs(c1['hist_fun'][-1])
+    # the reference's own hard-coded expectations (reference tests/test_drt_fit.py:164-170)
+    assert np.allclose(c1['expected_x'], out['x'][0, 2:] * scale)
+    assert np.allclose(c1['expected_R_inf'], out['x'][0, 0] * scale)
+    assert np.allclose(c1['expected_inductance'], out['x'][0, 1] * scale * 1e-5)
+    assert np.allclose(c1['expected_q_vector'], out['q_vector'][0])
+
+
+def test_qphb_batch_vs_oracle_seeded(eng, orc, lookup_golden):
+    from hybdrt_b200 import synth
+    freq, z = synth.make_eis_batch(40, seed=123)
+    prep = orc.EisPrep(freq, tables=lookup_golden)
+    rvs = np.array([prep.problem(zz)[0]['rv'] for zz in z])
+    out = _eis_launch(eng, prep, rvs)
+    n_same = 0
+    for b in range(len(z)):
+        ref = prep.fit(z[b])
+        if int(out['n_outer'][b]) == ref['n_outer'] and int(out['n_ipm'][b]) == int(ref['ipm_iters'].sum()):
+            n_same += 1
+        assert rel_err(out['x'][b], ref['x']) < FIT_TOL, b
+        assert rel_err(out['weights'][b], ref['weights']) < FIT_TOL, b
+        assert abs(out['fun'][b] - ref['fun']) <= FIT_TOL * abs(ref['fun']), b
+        assert rel_err(out['rho'][b], ref['rho']) < FIT_TOL, b
+        assert rel_err(out['s_vectors'][b], ref['s_vectors']) < 1e-5, b
+        assert rel_err(out['xmx_norms'][b], ref['xmx_norms']) < FIT_TOL, b
+    assert n_same == len(z)       # iteration counts are discrete outcomes; all should agree
+
+
+def test_batch_invariances(eng, orc, lookup_golden):
+    """Size-independent properties: a spectrum's result does not depend on its batch neighbours or slot;
+    per-spectrum matrices (stride != 0) give the same answer as shared ones."""
+    from hybdrt_b200 import synth
+    freq, z = synth.make_eis_batch(600, seed=9)
+    prep = orc.EisPrep(freq, tables=lookup_golden)
+    scale = (z.real.max(axis=1) - z.real.min(axis=1)) / 14.0
+    zs = z / scale[:, None]
+    rvs = np.concatenate([zs.real, zs.imag], axis=1)
+    full = _eis_launch(eng, prep, rvs)
+    perm = np.random.default_rng(0).permutation(len(z))[:64]
+    sub = _eis_launch(eng, prep, rvs[perm])
+    assert np.array_equal(sub['x'], full['x'][perm])                      # bitwise: same code path, same data
+    assert np.array_equal(sub['n_ipm'], full['n_ipm'][perm])
+    d = eng.dev
+    k = 5
+    out = eng.qphb_fit_batch(d(np.repeat(prep.rm[None], k, 0)), d(rvs[:k]), d(np.repeat(np.array(prep.pen)[None], k, 0)),
+                             d(prep.h), d(prep.l1), 2, vmm_eis=d(np.repeat(prep.vmm[None], k, 0)))
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(out['x']), full['x'][:k])
+    st = full['status']
+    assert np.all((st & 3) != 0) and np.all((st & 3) != 3)               # exactly one of converged / max_iter
+    assert np.all(full['x'][:, 0] >= 0) and np.all(np.isfinite(full['x']))
+    assert np.all(full['n_outer'] >= 1) and np.all(full['n_outer'] <= 50)
+
+
+def test_empty_batch_and_bad_arguments(eng, orc, lookup_golden):
+    from hybdrt_b200 import engine as E
+    c1 = load_golden('c1_golden.npz')
+    prep = orc.EisPrep(c1['freq'], tables=lookup_golden)
+    d = eng.dev
+    out = eng.qphb_fit_batch(d(prep.rm), eng.empty(0, prep.rm.shape[0]), d(np.array(prep.pen)), d(prep.h), d(prep.l1), 2,
+                             vmm_eis=d(prep.vmm))
+    assert out['x'].shape[0] == 0
+    with pytest.raises(E.EngineError):      # EIS rows without a vmm block
+        eng.qphb_fit_batch(d(prep.rm), d(np.zeros((1, prep.rm.shape[0]))), d(np.array(prep.pen)), d(prep.h), d(prep.l1), 2)
+    with pytest.raises(E.EngineError):      # nu_epsilon too small for the complex-erf kernel
+        eng.build_dop_z(c1['freq'][None], np.linspace(-1, 1, 5), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the drop-in model class against outputs of the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+def test_model_fit_eis_golden():
+    """The reference's tests/test_drt_fit.py, run against the drop-in class."""
+    from hybdrt_b200.models import DRT
+    c1 = load_golden('c1_golden.npz')
+    drt = DRT(fit_inductance=True, fit_ohmic=True)
+    hypers = dict(rp_scale=14, derivative_weights=np.array([1.5, 1.0, 0.5]), sigma_ds=np.array([1, 1000, 1000]),
+                  l1_lambda_0=0, l2_lambda_0=142, s_alpha=np.array([5, 10, 25]), rho_alpha=np.array([0.15, 0.2, 0.25]),
+                  iw_alpha=None, iw_beta=None, s_0=np.ones(3), rho_0=np.ones(3), outlier_p=None)
+    drt.fit_eis(c1['freq'], c1['z'], **hypers)
+    fp = drt.fit_parameters
+    expected = dict(x=c1['expected_x'], R_inf=c1['expected_R_inf'], inductance=c1['expected_inductance'],
+                    z_sigma_tot=c1['expected_z_sigma_tot'], q_vector=c1['expected_q_vector'])
+    for key, val in expected.items():
+        assert np.allclose(val, fp[key]), key
+    assert fp['C_inv'] == 0 and fp['v_sigma_tot'] is None and fp['v_sigma_res'] is None and fp['vz_offset_eps'] == 1
+    # tighter, against the reference run on the same machine as the fixtures
+    assert rel_err(drt.cvx_result['x'], c1['cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(c1['freq']), c1['z_pred']) < FIT_TOL
+    assert rel_err(drt.qphb_params['rm'], c1['rm']) < MAT_TOL
+    assert rel_err(drt.qphb_params['vmm'], c1['vmm']) < MAT_TOL
+    assert rel_err(drt.basis_tau, c1['basis_tau']) < 1e-14
+    with pytest.raises(ValueError):
+        drt.fit_eis(c1['freq'], c1['z'], not_a_hyper=1)
+
+
+def test_model_eis_batch_fixtures():
+    from hybdrt_b200.models import DRT
+    c2 = load_golden('c2_eis.npz')
+    drt = DRT()
+    res = drt.fit_eis_batch(c2['freq'], c2['z'])
+    h = res.host()
+    fp = res.fit_parameters()
+    assert np.array_equal(h['n_outer'], c2['n_outer'])
+    assert np.array_equal(h['n_ipm'], c2['qp_log_total'])
+    for b in range(len(c2['z'])):
+        assert rel_err(h['x'][b], c2['cvx_x'][b]) < FIT_TOL
+        assert rel_err(fp['x'][b], c2['x'][b]) < FIT_TOL
+        assert abs(fp['R_inf'][b] - c2['R_inf'][b]) < FIT_TOL * abs(c2['R_inf'][b])
+        assert rel_err(fp['z_sigma_tot'][b], c2['z_sigma_tot'][b]) < FIT_TOL
+        assert rel_err(res.predict_z()[b], c2['z_pred'][b]) < FIT_TOL
+    free = load_golden('c2_free.npz')
+    drt.fit_eis(free['freq'], free['z'], nonneg=False)
+    assert rel_err(drt.cvx_result['x'], free['cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(free['freq']), free['z_pred']) < FIT_TOL
+
+
+def test_model_trapz_mode():
+    from hybdrt_b200.models import DRT
+    g = load_golden('c2_trapz_fit.npz')
+    drt = DRT(interpolate_integrals=False)
+    drt.fit_eis(g['freq'], g['z'])
+    assert drt.qphb_params['n_outer'] == int(g['n_outer'])
+    assert rel_err(drt.cvx_result['x'], g['cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['freq']), g['z_pred']) < FIT_TOL
+
+
+def test_model_dop():
+    from hybdrt_b200.models import DRT
+    d = load_golden('dop.npz')
+    drt = DRT(fit_dop=True)
+    res = drt.fit_eis_batch(d['freq'], d['z'])
+    h, fp = res.host(), res.fit_parameters()
+    assert rel_err(_np(res.plan['rm']), d['rm']) < MAT_TOL
+    assert rel_err(drt.dop_scale_vector, d['dop_scale_vector']) < 1e-13
+    assert np.array_equal(h['n_outer'], d['n_outer'])
+    for b in range(len(d['z'])):
+        assert rel_err(h['x'][b], d['cvx_x'][b]) < FIT_TOL
+        assert rel_err(fp['x_dop'][b], d['x_dop'][b]) < FIT_TOL
+        assert rel_err(h['dop_rho'][b], d['dop_rho_vector'][b]) < FIT_TOL
+        assert rel_err(res.predict_z()[b], d['z_pred'][b]) < FIT_TOL
+
+
+def test_model_hybrid_and_chrono():
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200 import synth
+    hs = load_golden('hybrid_small.npz')
+    drt = DRT()
+    drt.fit_hybrid(hs['times'], hs['i_signal'], hs['v_signal'], hs['freq'], hs['z'])
+    qp, fp = drt.qphb_params, drt.fit_parameters
+    assert rel_err(qp['rv'], hs['rv']) < 1e-12
+    assert rel_err(qp['vz_strength_vec'], hs['vz_strength_vec']) < 1e-12
+    assert qp['n_outer'] == int(hs['n_outer']) and qp['n_ipm'] == int(hs['qp_log'].sum())
+    assert rel_err(qp['rm'], hs['rm']) < 1e-9          # includes the final vz_offset column
+    assert rel_err(drt.cvx_result['x'], hs['cvx_x']) < FIT_TOL
+    assert rel_err(fp['x'], hs['x']) < FIT_TOL
+    assert abs(fp['vz_offset'] - hs['vz_offset']) < FIT_TOL * max(1.0, abs(hs['vz_offset']))
+    assert rel_err(fp['v_baseline'], hs['v_baseline']) < 1e-5
+    assert rel_err(fp['z_sigma_tot'], hs['z_sigma_tot']) < FIT_TOL
+    assert rel_err(fp['v_sigma_tot'], hs['v_sigma_tot']) < FIT_TOL
+    assert rel_err(drt.predict_z(hs['freq']), hs['z_pred']) < FIT_TOL
+    assert rel_err(drt.predict_response(), hs['v_pred']) < FIT_TOL
+
+    cs = load_golden('chrono_small.npz')
+    drt.fit_chrono(cs['times'], cs['i_signal'], cs['v_signal'])
+    assert drt.qphb_params['n_outer'] == int(cs['n_outer'])
+    assert rel_err(drt.qphb_params['rm'], cs['rm']) < MAT_TOL
+    assert rel_err(drt.cvx_result['x'], cs['cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_response(), cs['v_pred']) < FIT_TOL
+
+    # full-size C3 spectra (2000 samples + 30 frequencies), outputs of the reference only
+    hf = load_golden('hybrid_full.npz')
+    t, i_sig, v, f, z = synth.make_hybrid_batch(2, seed=1)
+    res = drt.fit_hybrid_batch(t, i_sig, v, f, z)
+    h = res.host()
+    assert np.array_equal(h['n_outer'], hf['n_outer'])
+    for b in range(2):
+        assert rel_err(h['x'][b], hf['cvx_x'][b]) < FIT_TOL
+        assert rel_err(res.predict_z()[b], hf['z_pred'][b]) < FIT_TOL
+
+
+def test_unsupported_options_raise():
+    from hybdrt_b200.models import DRT
+    c2 = load_golden('c2_eis.npz')
+    with pytest.raises(NotImplementedError):
+        DRT(tau_basis_type='Cole-Cole')
+    drt = DRT()
+    for kw in (dict(update_scale=True), dict(outlier_p=0.01), dict(penalty_type='discrete')):
+        with pytest.raises(NotImplementedError):
+            drt.fit_eis(c2['freq'], c2['z'][0], **kw)
