@@ -1,0 +1,359 @@
+"""Benchmark of the DRT hot path: hierarchical-Bayes DRT fits/s on synthetic EIS spectra.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on all host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 10,000 synthetic 2-ZARC spectra per GPU,
+70 frequencies 1e6..1e-2 Hz x 101 Gaussian RBF basis functions, DRT() defaults (hierarchical-Bayes,
+non-negative, interp-mode matrices), FP64.  One step = one pass of the hot path over that batch.
+Scaling is weak (every rank fits its own 10,000 spectra; no data-path collective).
+
+One JSON line on stdout (rank 0): value = fits/s with inputs resident in HBM (CUDA events on the launching
+stream, max over ranks); e2e = the same through DRT.fit_eis_batch with HOST buffers (scaling on the host,
+pinned H2D, fit, D2H of coefficients and weights inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 10000
+N_FREQ, N_BASIS, N_SPECIAL = 70, 101, 2
+L2_FLUSH_BYTES = 256 << 20
+
+
+def fit_flops(n_rows, n, nb, n_outer, n_ipm):
+    """Algorithmic FP64 flops of a batch of fits from the per-spectrum iteration counts the kernel reports
+    (SURVEY.md section 8d): per QP a Gram (2Nn^2 + 4Nn) and an interior-point start (n^3/3 + 2n^2); per
+    interior-point iteration a Cholesky and four triangular solves (n^3/3 + 8n^2); per outer iteration the
+    s/rho updates (24 Nb^2), the L2 assembly (6n^2) and the weights (2N^2 + 2Nn)."""
+    n_qp = n_outer + 1.0                                   # + the initialize_weights QP
+    per_qp = 2.0 * n_rows * n * n + 4.0 * n_rows * n + n ** 3 / 3.0 + 2.0 * n * n
+    per_ipm = n ** 3 / 3.0 + 8.0 * n * n
+    per_outer = 24.0 * nb * nb + 6.0 * n * n + 2.0 * n_rows * n_rows + 2.0 * n_rows * n
+    return float(np.sum(n_qp * per_qp + n_ipm * per_ipm + n_outer * per_outer))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(ln) for ln in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the reference itself is Python and cannot travel; see
+# DESIGN.md).  Also used, on a bounded sample, for the cpu_baseline object of the GPU line.
+# ---------------------------------------------------------------------------------------------------
+_WORKER = {}
+
+
+def _cpu_init(freq):
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import drt_oracle as orc
+    _WORKER['prep'] = orc.EisPrep(freq)
+
+
+def _cpu_fit(z):
+    res = _WORKER['prep'].fit(z)
+    return res['n_outer'], int(res['ipm_iters'].sum())
+
+
+class CpuPool:
+    """One worker process per core, each holding its own EisPrep (lookup tables built once per worker, as
+    DRT() construction does in the reference; excluded from the timing)."""
+
+    def __init__(self, freq, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context('spawn').Pool(cores, initializer=_cpu_init, initargs=(freq,))
+
+    def fits_per_second(self, z):
+        self.pool.map(_cpu_fit, list(z[:self.cores]))      # touch every worker (imports, tables)
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_fit, list(z), chunksize=max(1, len(z) // (self.cores * 8)))
+        dt = time.perf_counter() - t0
+        return len(z) / dt, dt, out
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from hybdrt_b200 import synth
+    cores = host_cores()
+    n_sample = int(min(BATCH_PER_GPU, max(64, 64 * cores)))
+    freq, z = synth.make_eis_batch(BATCH_PER_GPU, seed=0)
+    z = z[:n_sample]
+    vals = []
+    pool = CpuPool(freq, cores)
+    for i in range(args.warmup + args.steps):
+        v, dt, _ = pool.fits_per_second(z)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    pool.close()
+    value = float(np.mean([v for v, _ in vals]))
+    line = {
+        'impl': 'reference', 'metric': 'DRT fits/sec (70f x 101 basis, hierarchical-Bayes, FP64)', 'value': value,
+        'unit': 'fits/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': float(np.mean([dt for _, dt in vals]) * 1e3), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: 10,000 synthetic 2-ZARC EIS spectra, 70 freqs x 101 RBF basis, DRT() defaults',
+                   'sample': f'{n_sample} of the 10,000 spectra per step'},
+        'cpu_baseline': {'value': value, 'unit': 'fits/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_sample} spectra of the same batch; numpy oracle (oracle/drt_oracle.py), one process '
+                                   f'per core, BLAS threads = 1; QP = coneqp restatement (cvxopt not installable)'},
+        'e2e': {'value': value, 'unit': 'fits/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    graft.build()
+    from hybdrt_b200 import engine as E, synth
+    from hybdrt_b200.models import DRT
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    eng = E.get_engine(local)
+    dev = eng.device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    freq, z = synth.make_eis_batch(B, seed=rank)            # every rank fits its own spectra (weak scaling)
+    drt = DRT(device=local)
+
+    # ---- resident-input path: same plan + launch the public API uses, inputs already in HBM
+    res0 = drt.fit_eis_batch(freq, z)
+    plan = res0.plan
+    scale = res0.scales['coefficient_scale']
+    zs = z / scale[:, None]
+    rv_dev = eng.dev(np.concatenate([zs.real, zs.imag], axis=1))
+    hyp = drt._c_hypers(plan['opts'])
+    out = {}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
+                           vmm_eis=plan['vmm_eis'], hypers=hyp, out=out)
+
+    def step_e2e():
+        r = drt.fit_eis_batch(freq, z)
+        fp = r.fit_parameters()                             # D2H of x and weights + unscaling on the host
+        return r, fp
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k)                                      # evict L2 between timed steps
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+    barrier()
+    launches = eng.launches - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    value = world * B * args.steps / total_s
+
+    n_outer = out['n_outer'].cpu().numpy().astype(np.float64)
+    n_ipm = out['n_ipm'].cpu().numpy().astype(np.float64)
+    status = out['status'].cpu().numpy()
+    flops = fit_flops(plan['n_rows'], plan['n'], plan['n'] - plan['n_special'], n_outer, n_ipm)
+    kernel_s = float(np.mean(step_ms)) * 1e-3               # one qphb launch per step
+
+    # ---- end-to-end path through the public API with host buffers
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        r_e2e, fp = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+    h2d = int(r_e2e.extra['h2d_bytes'])
+    d2h = int(sum(v.nbytes for k, v in r_e2e.host(['x', 'weights']).items() if k in ('x', 'weights')))
+
+    # final gather of per-rank summaries (the only collective; off the timed path)
+    summ = torch.tensor([float(np.mean(n_outer)), float(np.mean(n_ipm)), float(np.mean((status & 1) > 0))],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(summ) for _ in range(world)] if rank == 0 else None
+        dist.gather(summ, gathered, dst=0)
+        if rank == 0:
+            summ = torch.stack(gathered).mean(dim=0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        fp64_peak = eng.probe_fp64()
+        # secondary roofline: matrix construction with per-spectrum grids (HBM-write bound)
+        g = B
+        f_dev = eng.dev(np.repeat(freq[None], g, 0) * (1 + 1e-3 * np.arange(g)[:, None] / g))
+        t_dev = eng.dev(np.repeat(plan['basis_tau'][None], g, 0))
+        for _ in range(3):
+            eng.build_impedance(f_dev, t_dev, drt.tau_epsilon, E.MODE_INTERP, drt.interpolate_lookups)
+        mb = []
+        for k in range(5):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.build_impedance(f_dev, t_dev, drt.tau_epsilon, E.MODE_INTERP, drt.interpolate_lookups)
+            b.record()
+            torch.cuda.synchronize()
+            mb.append(a.elapsed_time(b))
+        mat_bytes = 16.0 * g * N_FREQ * N_BASIS
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        mat_gbs = mat_bytes / (float(np.mean(mb)) * 1e-3) / 1e9
+
+        traffic = None
+        prof = os.path.join(ROOT, 'profiles', 'qphb_traffic.json')
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+            except Exception:
+                traffic = None
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            n_sample = int(min(B, max(64, 48 * cores)))
+            pool = CpuPool(freq, cores)
+            v, dt, _ = pool.fits_per_second(z[:n_sample])
+            pool.close()
+            cpu = {'value': v, 'unit': 'fits/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'first {n_sample} spectra of the same batch ({dt:.1f} s); numpy oracle, one process per core, '
+                             f'BLAS threads = 1; QP = coneqp restatement (cvxopt not installable here)'}
+
+        achieved = flops / kernel_s / 1e12
+        line = {
+            'metric': 'DRT fits/sec (70f x 101 basis, hierarchical-Bayes, FP64)', 'value': value, 'unit': 'fits/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(total_s / args.steps * 1e3),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'C2: {B} synthetic 2-ZARC EIS spectra per GPU, 70 freqs 1e6-1e-2 Hz x 101 RBF basis, '
+                                   f'DRT() defaults (non-negative hierarchical-Bayes, interp matrices)',
+                       'batch_per_gpu': B, 'n_rows': plan['n_rows'], 'n_cols': plan['n'],
+                       'l2': f'flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)',
+                       'mean_outer_iters': float(summ[0]), 'mean_ipm_iters': float(summ[1]),
+                       'frac_converged': float(summ[2])},
+            'e2e': {'value': e2e_value, 'unit': 'fits/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                         'frac': achieved / fp64_peak, 'traffic': traffic, 'kernel': 'qphb_kernel',
+                         'peak_source': 'measured in this run: register-resident DFMA loop on every SM '
+                                        '(MEASURED_PEAKS.json has no FP64 entry)',
+                         'flops_per_launch': flops},
+            'roofline_matrix_build': {'bound': 'hbm', 'achieved': mat_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                                      'frac': mat_gbs / hbm_peak, 'traffic': None, 'kernel': 'impedance_interp_kernel',
+                                      'bytes_per_launch': mat_bytes,
+                                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback',
+                                      'workload': f'{g} per-spectrum (freq, tau) grids, A_re + A_im 70 x 101 each'},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='spectra per GPU (default: the C2 workload)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -127,6 +127,7 @@ class Engine:
         self.handle = h
         self.sm_count = self.lib.hdrt_sm_count(h)
         self._lookups = {}
+        self._pinned = {}
         self.launches = 0           # kernels launched through this engine (bench.py reports it)
 
     def close(self):
@@ -156,6 +157,13 @@ class Engine:
 
     def empty(self, *shape, dtype=torch.float64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def pinned(self, *shape, dtype=torch.float64):
+        """Page-locked host staging buffer, cached per shape (reused across calls)."""
+        key = (tuple(shape), dtype)
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(*shape, dtype=dtype, pin_memory=True)
+        return self._pinned[key]
 
     # -- L1 --------------------------------------------------------------------------------------
     def build_lookup(self, eps, grid_points=2000, quad_points=1000):

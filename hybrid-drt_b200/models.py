@@ -191,10 +191,16 @@ class BatchFit:
         self.extra = extra
         self._host = None
 
-    def host(self):
-        """Device -> host copy of every output (one synchronisation)."""
+    def host(self, keys=None):
+        """Device -> host copy of the named outputs (all of them by default); cached per key."""
         if self._host is None:
-            self._host = {k: v.cpu().numpy() for k, v in self.raw.items()}
+            self._host = {}
+        want = list(self.raw.keys()) if keys is None else keys
+        missing = [k for k in want if k not in self._host and k in self.raw]
+        if missing:
+            torch.cuda.current_stream(self.raw[missing[0]].device).synchronize()
+            for k in missing:
+                self._host[k] = self.raw[k].cpu().numpy()
         return self._host
 
     @property
@@ -203,7 +209,7 @@ class BatchFit:
 
     def fit_parameters(self):
         """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for the whole batch: dict of [B, ...] arrays."""
-        pl, h, sc = self.plan, self.host(), self.scales
+        pl, h, sc = self.plan, self.host(['x', 'weights']), self.scales
         x = h['x']
         cs = sc['coefficient_scale'][:, None]
         ns = pl['n_special']
@@ -709,7 +715,8 @@ class DRT:
             rp_est = np.ones(batch)
             cscale = np.ones(batch)
         scales = dict(coefficient_scale=cscale)
-        rv = np.empty((batch, plan['n_rows']))
+        rv_pin = self.engine.pinned(batch, plan['n_rows'])     # pinned host staging buffer for the H2D copy
+        rv = rv_pin.numpy()
         if nc:
             rscale = plan['input_signal_scale'] * rp_est / hypers['rp_scale'] if scale_data else np.ones(batch)
             v_scaled = v_batch / rscale[:, None]
@@ -723,7 +730,9 @@ class DRT:
             rv[:, nc:nc + nf] = zs.real
             rv[:, nc + nf:] = zs.imag
         eng = self.engine
-        rv_dev = eng.dev(rv)
+        rv_dev = rv_pin.to(eng.device, non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record()
         dop_range = self.dop_indices if self.fit_dop else None
         vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
         vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
@@ -736,7 +745,8 @@ class DRT:
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
             if self.fit_dop:
                 plan['zm_dop_host'] = plan['zm_dop_dev'].cpu().numpy()
-        res = BatchFit(plan, raw, scales, dict(rv=rv))
+        copied.synchronize()        # the pinned staging buffer may be refilled by the next call from here on
+        res = BatchFit(plan, raw, scales, dict(rv=rv.copy() if want_pq else None, h2d_bytes=rv.nbytes))
         self.last_batch = res
         self.fit_type = f"qphb_{plan['data_type']}"
         return res
