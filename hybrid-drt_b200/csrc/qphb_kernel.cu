@@ -7,17 +7,18 @@
 // convergence test (:597), xmx normalisation (drt1d.py:946) and the hybrid vz_offset column rewrite
 // (drt1d.py:972).
 //
-// Data layout per CTA (dynamic shared memory, all FP64):
+// Shared memory per CTA (all FP64; offsets of everything but w / r2 / PL are compile-time constants of the
+// instantiation so that loads and stores carry immediate offsets):
+//   16 vectors of length NV = 16 * NBK (pdiag, x broadcast, solve rhs, ...), reduction scratch,
+//   a double-buffered 4-row staging tile for the Gram pass, w[N], r2[N], then
 //   PL   n x ld (ld odd): strict upper triangle = P of the current QP; lower triangle + diagonal =
 //        Cholesky factor L of H = P + diag(1/d^2) of the current interior-point iteration, with each
 //        32 x 32 diagonal block of L replaced by its inverse (the triangular solves are then blocked
-//        matrix-vector products instead of n-step substitution chains)
-//   18 vectors of length nv (pdiag, x broadcast, solve rhs, ...), 2 vectors of length N (w, r^2),
-//   a kStageRows x ldA staging tile for the Gram pass.
-// Register layout (kernels instantiated with NBK = ceil(n/16) <= 10): thread (ty, tx) = (tid/16, tid%16)
-// owns the entries (i, j), i >= j, with i = 16a + ty, j = 16b + tx of the symmetric matrix being built
-// (Gram) or factorised (Cholesky) -- NBK(NBK+1)/2 doubles per thread, so the rank-1 updates of both
-// phases run out of registers and shared memory only carries the broadcast row / column.
+//        matrix-vector products instead of n-step substitution chains).
+// Register layout: thread (ty, tx) = (tid / 16, tid % 16) owns the entries (i, j), i >= j, i = 16a + ty,
+// j = 16b + tx of the symmetric matrix being built (Gram) or factorised (Cholesky) -- NBK (NBK + 1) / 2
+// doubles per thread; the rank-1 updates of both phases run out of registers and shared memory only carries
+// the broadcast row / column.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the
 // batch and stay in global memory (L2 resident, read-only path).
 #include "common.cuh"
@@ -26,10 +27,10 @@ namespace hdrt {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kStageRows = 8;
-constexpr int kMaxCols = 256;
+constexpr int kStageRows = 4;  // per buffer; two buffers
+constexpr int kMaxCols = 160;
 constexpr int kRedSlots = 8;
-constexpr int kNumVec = 18;
+constexpr int kNumVec = 16;
 
 // cvxopt coneqp defaults (cvxopt 1.3 coneprog.py; the reference only sets show_progress, qphb.py:25)
 constexpr double kAbsTol = 1e-7;
@@ -38,31 +39,35 @@ constexpr double kFeasTol = 1e-7;
 constexpr int kMaxIpm = 100;
 constexpr double kStep = 0.99;
 
-struct SmemLayout {
-    int ld;   // leading dimension of PL (odd)
-    int nv;   // padded vector length (16 * NBK of the kernel that runs this shape)
-    int ldA;  // staging leading dimension
-    size_t pl, vec, rows, stage, red, total;  // offsets in doubles
+extern __shared__ __align__(16) double g_smem[];
+
+// compile-time part of the shared-memory layout (offsets in doubles)
+template <int NBK>
+struct SM {
+    static constexpr int NV = 16 * NBK;
+    static constexpr int LDA = NV + 2;  // staged row: NV columns of W*rm (zero padded) + W*rv at column NV
+    static constexpr int kRed = kNumVec * NV;
+    static constexpr int kRbuf = kRed + 2 * kRedSlots * kWarps;
+    static constexpr int kStage = kRbuf + 16;
+    static constexpr int kRows = kStage + 2 * kStageRows * LDA;
+    enum { PDIAG = 0, XS, BS, DSQ, QS, RDIAG, PIV, SV0, SV1, SV2, US0, US1, US2, XH, COLA, COLB };
+    static __device__ __forceinline__ double* vec(int k) { return g_smem + k * NV; }
+    static __device__ __forceinline__ double* red() { return g_smem + kRed; }
+    static __device__ __forceinline__ double* rbuf() { return g_smem + kRbuf; }
+    static __device__ __forceinline__ double* stage() { return g_smem + kStage; }
 };
 
-__host__ __device__ inline SmemLayout make_layout(int N, int n) {
-    SmemLayout L;
-    L.ld = n | 1;
-    const int nbk = (n + 15) / 16;
-    L.nv = nbk <= 7 ? 112 : (nbk <= 10 ? 160 : 16 * nbk);  // = 16 * NBK of the kernel instantiation
-    L.ldA = L.nv + 2;  // column nv holds w*y
-    L.pl = 0;
-    L.vec = L.pl + (size_t)n * L.ld + (((size_t)n * L.ld) & 1);
-    L.rows = L.vec + (size_t)kNumVec * L.nv;
-    L.stage = L.rows + (size_t)2 * ((N + 1) & ~1);
-    L.red = L.stage + (size_t)kStageRows * L.ldA;
-    L.total = L.red + (size_t)2 * kRedSlots * kWarps;
-    return L;
+__host__ __device__ inline int nbk_for(int n) { return (n + 15) / 16 <= 7 ? 7 : 10; }
+
+__host__ __device__ inline long long smem_doubles(int N, int n) {
+    const int nv = 16 * nbk_for(n);
+    const long long fixed = (long long)kNumVec * nv + 2 * kRedSlots * kWarps + 16 + 2 * kStageRows * (nv + 2);
+    const int ld = n | 1;
+    return fixed + 2LL * ((N + 1) & ~1) + (long long)n * ld + 2;
 }
 
 struct Ctx {
-    // problem
-    int N, n, ns, nc, dop_a, dop_b, vz, vb_a, vb_b;
+    int N, n, ns, nc, dop_a, dop_b, vz, vb_a, vb_b, ld;
     const double* __restrict__ rm;
     const double* __restrict__ rv;
     const double* __restrict__ vmm_eis;
@@ -72,21 +77,19 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
-    // shared memory
-    int ld, nv, ldA;
-    double *PL, *pdiag, *xs, *bs, *dsq, *qs, *rdiag, *piv, *sv[3], *us[3], *xh, *colA, *colB, *w, *r2, *stage, *red;
+    double *PL, *w, *r2;
     int red_phase;
 };
 
 // Reduce K per-thread values over the block; bit k of MAXMASK selects max instead of sum.  The result is
 // broadcast to every thread.  One barrier: the scratch buffer alternates between two halves.
-template <int K, unsigned MAXMASK>
+template <int NBK, int K, unsigned MAXMASK>
 __device__ __forceinline__ void block_reduce(double (&v)[K], Ctx& c) {
     static_assert(K <= kRedSlots, "too many reduction slots");
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = ((MAXMASK >> k) & 1u) ? warp_max(v[k]) : warp_sum(v[k]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* red = c.red + (c.red_phase & 1) * (kRedSlots * kWarps);
+    double* red = SM<NBK>::red() + (c.red_phase & 1) * (kRedSlots * kWarps);
     c.red_phase ^= 1;
     if (lane == 0) {
 #pragma unroll
@@ -117,6 +120,7 @@ struct L2Factors {
     bool use[3];    // derivative_weights[k] > 0
 };
 
+template <int NBK>
 __device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int i, int j) {
     double acc = 0.0;
     const bool drt = (i >= c.ns) && (j >= c.ns);
@@ -128,35 +132,49 @@ __device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int
         double m = c.pen[k * nn + i * c.n + j];
         if (drt) m *= f.drt[k];
         if (dop) m *= f.dop[k];
-        acc += (c.us[k][i] * m) * c.us[k][j];
+        const double* us = SM<NBK>::vec(SM<NBK>::US0 + k);
+        acc += (us[i] * m) * us[j];
     }
     return acc;
 }
 
-// stage rows [r0, r0+rows) of W*rm (and W*rv in column nv) into shared memory: one warp per row
-__device__ __forceinline__ void stage_rows(const Ctx& c, int r0, int rows) {
+// Staging: chunk = kStageRows rows; warp w loads row (w & 3), columns (w >> 2) * 32 + lane + 64 u.
+template <int NBK>
+struct StageRegs {
+    static constexpr int U = (SM<NBK>::LDA + 63) / 64;
+    double v[U];
+};
+
+template <int NBK>
+__device__ __forceinline__ void stage_load(const Ctx& c, int r0, StageRegs<NBK>& s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp < rows) {
-        const int r = r0 + warp;
+    const int r = r0 + (warp & 3);
+    const int cbase = (warp >> 2) * 32 + lane;
+#pragma unroll
+    for (int u = 0; u < StageRegs<NBK>::U; ++u) s.v[u] = 0.0;
+    if (r < c.N) {
         const double wr = c.w[r];
         const double* __restrict__ src = c.rm + (size_t)r * c.n;
-        double* dst = c.stage + warp * c.ldA;
-        for (int col = lane; col < c.ldA; col += 32) {
+#pragma unroll
+        for (int u = 0; u < StageRegs<NBK>::U; ++u) {
+            const int col = cbase + 64 * u;
             double v = 0.0;
             if (col < c.n) v = ((col == c.vz) ? c.vzcol[r] : src[col]) * wr;
-            else if (col == c.nv) v = wr * c.rv[r];
-            dst[col] = v;
+            else if (col == SM<NBK>::NV) v = wr * c.rv[r];
+            s.v[u] = v;
         }
     }
 }
 
-__device__ __forceinline__ void store_p_entry(const Ctx& c, const L2Factors& f, int i, int j, double acc, double* p_out) {
-    // i >= j
-    const double val = acc + l2_entry(c, f, j, i);
-    if (i == j) c.pdiag[i] = val; else c.PL[j * c.ld + i] = val;
-    if (p_out) {
-        p_out[(size_t)i * c.n + j] = val;
-        p_out[(size_t)j * c.n + i] = val;
+template <int NBK>
+__device__ __forceinline__ void stage_store(int buf, const StageRegs<NBK>& s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* dst = SM<NBK>::stage() + (buf * kStageRows + (warp & 3)) * SM<NBK>::LDA;
+    const int cbase = (warp >> 2) * 32 + lane;
+#pragma unroll
+    for (int u = 0; u < StageRegs<NBK>::U; ++u) {
+        const int col = cbase + 64 * u;
+        if (col < SM<NBK>::LDA) dst[col] = s.v[u];
     }
 }
 
@@ -164,66 +182,56 @@ template <int NBK>
 __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scalar, double l1_value, double* p_out,
                                            double* q_out) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int n = c.n, N = c.N, ldA = c.ldA;
+    const int n = c.n, N = c.N;
+    constexpr int LDA = SM<NBK>::LDA;
     double qacc = 0.0;
-    if constexpr (NBK > 0) {
-        double C[NBK * (NBK + 1) / 2];
+    double C[NBK * (NBK + 1) / 2];
 #pragma unroll
-        for (int e = 0; e < NBK * (NBK + 1) / 2; ++e) C[e] = 0.0;
-        for (int r0 = 0; r0 < N; r0 += kStageRows) {
-            const int rows = min(kStageRows, N - r0);
-            __syncthreads();
-            stage_rows(c, r0, rows);
-            __syncthreads();
-            for (int rr = 0; rr < rows; ++rr) {
-                const double* row = c.stage + rr * ldA;
-                double ri[NBK], cj[NBK];
+    for (int e = 0; e < NBK * (NBK + 1) / 2; ++e) C[e] = 0.0;
+    StageRegs<NBK> sr;
+    stage_load<NBK>(c, 0, sr);
+    __syncthreads();  // previous users of the staging area are done
+    stage_store<NBK>(0, sr);
+    __syncthreads();
+    int buf = 0;
+    for (int r0 = 0; r0 < N; r0 += kStageRows) {
+        const bool more = r0 + kStageRows < N;
+        if (more) stage_load<NBK>(c, r0 + kStageRows, sr);  // global loads in flight during the FMAs below
+        const double* base = SM<NBK>::stage() + buf * kStageRows * LDA;
 #pragma unroll
-                for (int a = 0; a < NBK; ++a) { ri[a] = row[16 * a + ty]; cj[a] = row[16 * a + tx]; }
+        for (int rr = 0; rr < kStageRows; ++rr) {   // rows beyond N are staged as zeros
+            const double* row = base + rr * LDA;
+            double ri[NBK], cj[NBK];
 #pragma unroll
-                for (int a = 0; a < NBK; ++a)
+            for (int a = 0; a < NBK; ++a) { ri[a] = row[16 * a + ty]; cj[a] = row[16 * a + tx]; }
 #pragma unroll
-                    for (int b = 0; b <= a; ++b) C[tri(a, b)] += ri[a] * cj[b];
-                if (tid < n) qacc += row[tid] * row[c.nv];
-            }
+            for (int a = 0; a < NBK; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) C[tri(a, b)] += ri[a] * cj[b];
+            if (tid < SM<NBK>::NV) qacc += row[tid] * row[SM<NBK>::NV];
         }
+        if (more) stage_store<NBK>(buf ^ 1, sr);
+        __syncthreads();
+        buf ^= 1;
+    }
+    double* pdiag = SM<NBK>::vec(SM<NBK>::PDIAG);
 #pragma unroll
-        for (int a = 0; a < NBK; ++a)
+    for (int a = 0; a < NBK; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const int i = 16 * a + ty, j = 16 * b + tx;
-                if (i < n && j <= i) store_p_entry(c, f, i, j, C[tri(a, b)], p_out);
-            }
-    } else {
-        // generic path (n > 160): one output entry at a time per thread, rows staged the same way
-        const int total = n * (n + 1) / 2;
-        for (int e0 = 0; e0 < total; e0 += kThreads) {
-            const int e = e0 + tid;
-            int i = 0, j = 0;
-            if (e < total) {
-                i = (int)floor((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while (i * (i + 1) / 2 > e) --i;
-                while ((i + 1) * (i + 2) / 2 <= e) ++i;
-                j = e - i * (i + 1) / 2;
-            }
-            double acc = 0.0;
-            for (int r0 = 0; r0 < N; r0 += kStageRows) {
-                const int rows = min(kStageRows, N - r0);
-                __syncthreads();
-                stage_rows(c, r0, rows);
-                __syncthreads();
-                for (int rr = 0; rr < rows; ++rr) {
-                    const double* row = c.stage + rr * ldA;
-                    acc += row[i] * row[j];
-                    if (e0 == 0 && tid < n) qacc += row[tid] * row[c.nv];
+        for (int b = 0; b <= a; ++b) {
+            const int i = 16 * a + ty, j = 16 * b + tx;
+            if (i < n && j <= i) {
+                const double val = C[tri(a, b)] + l2_entry<NBK>(c, f, j, i);
+                if (i == j) pdiag[i] = val; else c.PL[j * c.ld + i] = val;
+                if (p_out) {
+                    p_out[(size_t)i * n + j] = val;
+                    p_out[(size_t)j * n + i] = val;
                 }
             }
-            if (e < total) store_p_entry(c, f, i, j, acc, p_out);
         }
-    }
     if (tid < n) {
         const double qv = -qacc + (l1_scalar ? l1_value : c.l1[tid]);
-        c.qs[tid] = qv;
+        SM<NBK>::vec(SM<NBK>::QS)[tid] = qv;
         if (q_out) q_out[tid] = qv;
     }
     __syncthreads();
@@ -235,12 +243,16 @@ __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_s
 // ------------------------------------------------------------------------------------------------
 template <int NBK>
 __device__ __forceinline__ bool factor_phase(Ctx& c) {
+    using S = SM<NBK>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
     const int n = c.n, ld = c.ld;
     double* PL = c.PL;
+    double* rdiag = S::vec(S::RDIAG);
     bool ok = true;
-    if constexpr (NBK > 0) {
-        const int tx = tid & 15, ty = tid >> 4;
+    {
+        const double* pdiag = S::vec(S::PDIAG);
+        const double* dsq = S::vec(S::DSQ);
         double C[NBK * (NBK + 1) / 2];
 #pragma unroll
         for (int a = 0; a < NBK; ++a)
@@ -248,91 +260,73 @@ __device__ __forceinline__ bool factor_phase(Ctx& c) {
             for (int b = 0; b <= a; ++b) {
                 const int i = 16 * a + ty, j = 16 * b + tx;
                 double v = 0.0;
-                if (i < n && j <= i) v = (i == j) ? (c.pdiag[i] + c.dsq[i]) : PL[j * ld + i];
+                if (i < n && j <= i) v = (i == j) ? (pdiag[i] + dsq[i]) : PL[j * ld + i];
                 C[tri(a, b)] = v;
             }
-        // right-looking, one barrier per column: the owners of column k publish it (unscaled) in shared
-        // memory; every thread then applies C_ij -= a_ik a_jk / a_kk to the entries it holds.
+        // Right-looking, one barrier per column.  The owners of column k (tx == k % 16) publish it unscaled;
+        // the owner of the pivot also publishes 1 / a_kk (NaN on breakdown).  Every thread then applies
+        // C_ij -= a_ik (a_jk / a_kk) to the entries it holds.  Padding rows (i >= n) hold zeros throughout.
+        double* piv = S::vec(S::PIV);
+        double* rb = S::rbuf();
 #pragma unroll
         for (int kb = 0; kb < NBK; ++kb) {
 #pragma unroll 1
             for (int kx = 0; kx < 16; ++kx) {
                 const int k = 16 * kb + kx;
                 if (!ok || k >= n) break;
-                double* col = (k & 1) ? c.colB : c.colA;
+                double* col = S::vec(S::COLA + (k & 1));
                 if (tx == kx) {
 #pragma unroll
-                    for (int a = kb; a < NBK; ++a) {
-                        const int i = 16 * a + ty;
-                        if (i < n && i >= k) col[i] = C[tri(a, kb)];
+                    for (int a = kb; a < NBK; ++a) col[16 * a + ty] = C[tri(a, kb)];
+                    if (ty == kx) {
+                        const double pv = C[tri(kb, kb)];
+                        piv[k] = pv;
+                        rb[k & 1] = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : nan("");
                     }
                 }
                 __syncthreads();
-                const double pv = col[k];
-                if (!(pv > 0.0) || !isfinite(pv)) { ok = false; break; }
-                if (tid == 0) c.piv[k] = pv;
-                const double r = 1.0 / pv;
+                const double r = rb[k & 1];
+                if (isnan(r)) { ok = false; break; }
                 double ri[NBK], cj[NBK];
 #pragma unroll
                 for (int a = kb; a < NBK; ++a) { ri[a] = col[16 * a + ty]; cj[a] = col[16 * a + tx] * r; }
+                if (tx <= kx) cj[kb] = 0.0;  // columns <= k of this block are final
 #pragma unroll
                 for (int a = kb; a < NBK; ++a)
 #pragma unroll
-                    for (int b = kb; b <= a; ++b)
-                        if (b > kb || tx > kx) C[tri(a, b)] -= ri[a] * cj[b];
+                    for (int b = kb; b <= a; ++b) C[tri(a, b)] -= ri[a] * cj[b];
             }
         }
         __syncthreads();
         if (!ok) return false;
-        if (tid < n) c.rdiag[tid] = 1.0 / sqrt(c.piv[tid]);
+        if (tid < n) rdiag[tid] = 1.0 / sqrt(piv[tid]);
         __syncthreads();
 #pragma unroll
         for (int a = 0; a < NBK; ++a)
 #pragma unroll
             for (int b = 0; b <= a; ++b) {
                 const int i = 16 * a + ty, j = 16 * b + tx;
-                if (i < n && j <= i) PL[i * ld + j] = C[tri(a, b)] * c.rdiag[j];
+                if (i < n && j <= i) PL[i * ld + j] = C[tri(a, b)] * rdiag[j];
             }
-    } else {
-        for (int i = warp; i < n; i += kWarps)
-            for (int j = lane; j < i; j += 32) PL[i * ld + j] = PL[j * ld + i];
-        if (tid < n) PL[tid * ld + tid] = c.pdiag[tid] + c.dsq[tid];
-        __syncthreads();
-        const int tx = tid & 15, ty = tid >> 4;
-        for (int k = 0; k < n; ++k) {
-            const double akk = PL[k * ld + k];
-            if (!(akk > 0.0) || !isfinite(akk)) { ok = false; break; }
-            const double r = 1.0 / akk;
-            for (int i = k + 1 + ty; i < n; i += 16) {
-                const double ci = PL[i * ld + k] * r;
-                for (int j = k + 1 + tx; j <= i; j += 16) PL[i * ld + j] -= ci * PL[j * ld + k];
-            }
-            __syncthreads();
-        }
-        if (!ok) { __syncthreads(); return false; }
-        if (tid < n) c.rdiag[tid] = 1.0 / sqrt(PL[tid * ld + tid]);
-        __syncthreads();
-        for (int i = warp; i < n; i += kWarps)
-            for (int j = lane; j <= i; j += 32) PL[i * ld + j] *= c.rdiag[j];
     }
     __syncthreads();
-    // invert the diagonal blocks in place: warp w takes block(s) w, w + 8, ...; lane l builds column l
+    // Invert the diagonal blocks in place: warp w takes block w (n <= 160 -> at most 5 blocks); lane l builds
+    // column l of the inverse row by row: x_i = -(1 / L_ii) sum_{k < i} L_ik x_k, x_l = 1 / L_ll, x_{k<l} = 0.
     const int nblk = (n + 31) >> 5;
-    for (int blk = warp; blk < nblk; blk += kWarps) {
-        const int r0 = 32 * blk, m = min(32, n - r0);
+    if (warp < nblk) {
+        const int r0 = 32 * warp, m = min(32, n - r0);
         double x[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = 0.0;
+        for (int i = 0; i < 32; ++i) {
+            x[i] = 0.0;
+            if (i < m) {
+                const double* lr = PL + (r0 + i) * ld + r0;
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if (k < m) {
-                double xk = 0.0;
-                if (k == lane) xk = c.rdiag[r0 + k];
-                else if (k > lane) xk = -c.rdiag[r0 + k] * x[k];
-                x[k] = xk;
-#pragma unroll
-                for (int i = k + 1; i < 32; ++i)
-                    if (i < m) x[i] += PL[(r0 + i) * ld + r0 + k] * xk;
+                for (int k = 0; k < i; ++k) acc[k & 3] += lr[k] * x[k];
+                const double rd = rdiag[r0 + i];
+                const double dot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                x[i] = (i == lane) ? rd : ((i > lane) ? -rd * dot : 0.0);
             }
         }
         __syncwarp();
@@ -347,39 +341,47 @@ __device__ __forceinline__ bool factor_phase(Ctx& c) {
 }
 
 // Solve L L^T u = bs in place with the block-inverted factor.
+template <int NBK>
 __device__ __forceinline__ void solve_phase(Ctx& c) {
+    using S = SM<NBK>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = c.n, ld = c.ld;
     const double* PL = c.PL;
-    double* bs = c.bs;
+    double* bs = S::vec(S::BS);
     const int nblk = (n + 31) >> 5;
     __syncthreads();
     // forward: y = L^-1 b
     for (int blk = 0; blk < nblk; ++blk) {
         const int r0 = 32 * blk, m = min(32, n - r0);
         if (warp == 0) {
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             if (lane < m) {
                 const double* xr = PL + (r0 + lane) * ld + r0;
-                int k = 0;
-                for (; k + 1 <= lane; k += 2) { a0 += xr[k] * bs[r0 + k]; a1 += xr[k + 1] * bs[r0 + k + 1]; }
-                if (k <= lane) a0 += xr[k] * bs[r0 + k];
+                const double* bb = bs + r0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    if (k <= lane) a0 += xr[k] * bb[k];
+                    if (k + 1 <= lane) a1 += xr[k + 1] * bb[k + 1];
+                    if (k + 2 <= lane) a2 += xr[k + 2] * bb[k + 2];
+                    if (k + 3 <= lane) a3 += xr[k + 3] * bb[k + 3];
+                }
             }
             __syncwarp();
-            if (lane < m) bs[r0 + lane] = a0 + a1;
+            if (lane < m) bs[r0 + lane] = (a0 + a1) + (a2 + a3);
         }
         if (r0 + m >= n) break;
         __syncthreads();
-        const int i = r0 + m + tid;
+        const int i = r0 + 32 + tid;
         if (i < n) {
             const double* lr = PL + i * ld + r0;
+            const double* bb = bs + r0;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 2
+#pragma unroll
             for (int k = 0; k < 32; k += 4) {
-                a0 += lr[k] * bs[r0 + k];
-                a1 += lr[k + 1] * bs[r0 + k + 1];
-                a2 += lr[k + 2] * bs[r0 + k + 2];
-                a3 += lr[k + 3] * bs[r0 + k + 3];
+                a0 += lr[k] * bb[k];
+                a1 += lr[k + 1] * bb[k + 1];
+                a2 += lr[k + 2] * bb[k + 2];
+                a3 += lr[k + 3] * bb[k + 3];
             }
             bs[i] -= (a0 + a1) + (a2 + a3);
         }
@@ -390,25 +392,39 @@ __device__ __forceinline__ void solve_phase(Ctx& c) {
     for (int blk = nblk - 1; blk >= 0; --blk) {
         const int r0 = 32 * blk, m = min(32, n - r0);
         if (warp == 0) {
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             if (lane < m) {
                 const double* xc = PL + r0 * ld + r0 + lane;
-                int k = lane;
-                for (; k + 1 < m; k += 2) { a0 += xc[k * ld] * bs[r0 + k]; a1 += xc[(k + 1) * ld] * bs[r0 + k + 1]; }
-                if (k < m) a0 += xc[k * ld] * bs[r0 + k];
+                const double* bb = bs + r0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    if (k >= lane && k < m) a0 += xc[k * ld] * bb[k];
+                    if (k + 1 >= lane && k + 1 < m) a1 += xc[(k + 1) * ld] * bb[k + 1];
+                    if (k + 2 >= lane && k + 2 < m) a2 += xc[(k + 2) * ld] * bb[k + 2];
+                    if (k + 3 >= lane && k + 3 < m) a3 += xc[(k + 3) * ld] * bb[k + 3];
+                }
             }
             __syncwarp();
-            if (lane < m) bs[r0 + lane] = a0 + a1;
+            if (lane < m) bs[r0 + lane] = (a0 + a1) + (a2 + a3);
         }
         if (blk == 0) break;
         __syncthreads();
         if (tid < r0) {
             const double* lc = PL + r0 * ld + tid;
-            double a0 = 0.0, a1 = 0.0;
-            int k = 0;
-            for (; k + 1 < m; k += 2) { a0 += lc[k * ld] * bs[r0 + k]; a1 += lc[(k + 1) * ld] * bs[r0 + k + 1]; }
-            if (k < m) a0 += lc[k * ld] * bs[r0 + k];
-            bs[tid] -= a0 + a1;
+            const double* bb = bs + r0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (m == 32) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    a0 += lc[k * ld] * bb[k];
+                    a1 += lc[(k + 1) * ld] * bb[k + 1];
+                    a2 += lc[(k + 2) * ld] * bb[k + 2];
+                    a3 += lc[(k + 3) * ld] * bb[k + 3];
+                }
+            } else {
+                for (int k = 0; k < m; ++k) a0 += lc[k * ld] * bb[k];
+            }
+            bs[tid] -= (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
@@ -429,10 +445,13 @@ struct QpOut {
 
 template <int NBK>
 __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
+    using S = SM<NBK>;
     const int tid = threadIdx.x;
     const int n = c.n, ld = c.ld;
     const bool act = tid < n;
-    const double qi = act ? c.qs[tid] : 0.0;
+    double* xs = S::vec(S::XS);
+    double* bs = S::vec(S::BS);
+    const double qi = act ? S::vec(S::QS)[tid] : 0.0;
     const double hi = act ? c.hvec[tid] : 0.0;
     QpOut out;
     out.xi = 0.0; out.pcost = 0.0; out.iters = 0; out.status = 0; out.fatal = false;
@@ -440,7 +459,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
     double resx0, resz0;
     {
         double t2[2] = {qi * qi, hi * hi};
-        block_reduce<2, 0u>(t2, c);
+        block_reduce<NBK, 2, 0u>(t2, c);
         resx0 = fmax(1.0, sqrt(t2[0]));
         resz0 = fmax(1.0, sqrt(t2[1]));
     }
@@ -451,29 +470,29 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
 #pragma unroll 1
     for (iters = -1; iters <= kMaxIpm; ++iters) {
         if (iters >= 0) {
-            if (act) c.xs[tid] = xi;
+            if (act) xs[tid] = xi;
             __syncthreads();
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             if (act) {
                 const double* colp = c.PL + tid;       // P[j][tid], j < tid  (upper triangle, column tid)
                 int j = 0;
                 for (; j + 3 < tid; j += 4) {
-                    a0 += colp[j * ld] * c.xs[j];
-                    a1 += colp[(j + 1) * ld] * c.xs[j + 1];
-                    a2 += colp[(j + 2) * ld] * c.xs[j + 2];
-                    a3 += colp[(j + 3) * ld] * c.xs[j + 3];
+                    a0 += colp[j * ld] * xs[j];
+                    a1 += colp[(j + 1) * ld] * xs[j + 1];
+                    a2 += colp[(j + 2) * ld] * xs[j + 2];
+                    a3 += colp[(j + 3) * ld] * xs[j + 3];
                 }
-                for (; j < tid; ++j) a0 += colp[j * ld] * c.xs[j];
-                a1 += c.pdiag[tid] * xi;
+                for (; j < tid; ++j) a0 += colp[j * ld] * xs[j];
+                a1 += S::vec(S::PDIAG)[tid] * xi;
                 const double* rowp = c.PL + tid * ld;  // P[tid][j], j > tid
                 j = tid + 1;
                 for (; j + 3 < n; j += 4) {
-                    a0 += rowp[j] * c.xs[j];
-                    a1 += rowp[j + 1] * c.xs[j + 1];
-                    a2 += rowp[j + 2] * c.xs[j + 2];
-                    a3 += rowp[j + 3] * c.xs[j + 3];
+                    a0 += rowp[j] * xs[j];
+                    a1 += rowp[j + 1] * xs[j + 1];
+                    a2 += rowp[j + 2] * xs[j + 2];
+                    a3 += rowp[j + 3] * xs[j + 3];
                 }
-                for (; j < n; ++j) a0 += rowp[j] * c.xs[j];
+                for (; j < n; ++j) a0 += rowp[j] * xs[j];
             }
             rxi = ((a0 + a1) + (a2 + a3)) + qi;
             const double f0p = act ? (xi * rxi + xi * qi) : 0.0;
@@ -481,7 +500,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             rzi = si - hi - xi;
             double t5[5] = {f0p, act ? rxi * rxi : 0.0, act ? rzi * rzi : 0.0, act ? zi * rzi : 0.0,
                             act ? (iters == 0 ? si * zi : lam * lam) : 0.0};
-            block_reduce<5, 0u>(t5, c);
+            block_reduce<NBK, 5, 0u>(t5, c);
             const double f0 = 0.5 * t5[0];
             const double resx = sqrt(t5[1]), resz = sqrt(t5[2]);
             gap = t5[4];
@@ -503,7 +522,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
                 lam = sqrt(si * zi);
             }
         }
-        if (act) c.dsq[tid] = dinv * dinv;
+        if (act) S::vec(S::DSQ)[tid] = dinv * dinv;
         __syncthreads();
         if (!factor_phase<NBK>(c)) {
             out.status |= HDRT_ST_KKT_FAIL;
@@ -512,13 +531,13 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
         }
         if (iters < 0) {
             // solve [P+I] x = -q - h ; z = -x - h ; s = -z, shifted into the cone
-            if (act) c.bs[tid] = -qi - hi;
-            solve_phase(c);
-            xi = act ? c.bs[tid] : 0.0;
+            if (act) bs[tid] = -qi - hi;
+            solve_phase<NBK>(c);
+            xi = act ? bs[tid] : 0.0;
             zi = -xi - hi;
             si = -zi;
             double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
-            block_reduce<4, 0xAu>(t4, c);
+            block_reduce<NBK, 4, 0xAu>(t4, c);
             const double nrms = sqrt(t4[0]), ts = t4[1], nrmz = sqrt(t4[2]), tz = t4[3];
             if (ts >= -1e-8 * fmax(nrms, 1.0)) si += 1.0 + ts;
             if (tz >= -1e-8 * fmax(nrmz, 1.0)) zi += 1.0 + tz;
@@ -539,9 +558,9 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             dsi = dsi / lam;
             dzi = dzi - di * dsi;
             const double zs = dinv * dzi;
-            if (act) c.bs[tid] = dxi - dinv * zs;
-            solve_phase(c);
-            dxi = act ? c.bs[tid] : 0.0;
+            if (act) bs[tid] = dxi - dinv * zs;
+            solve_phase<NBK>(c);
+            dxi = act ? bs[tid] : 0.0;
             dzi = -dinv * dxi - zs;
             dsi = dsi - dzi;
             const double prod = dsi * dzi;
@@ -549,7 +568,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             dsi = dsi / lam;
             dzi = dzi / lam;
             double t3[3] = {act ? prod : 0.0, act ? -dsi : -INFINITY, act ? -dzi : -INFINITY};
-            block_reduce<3, 0x6u>(t3, c);
+            block_reduce<NBK, 3, 0x6u>(t3, c);
             const double t = fmax(0.0, fmax(t3[1], t3[2]));
             if (t == 0.0) step = 1.0;
             else if (pass == 0) step = fmin(1.0, 1.0 / t);
@@ -585,42 +604,46 @@ struct BlockHyp {
     bool use_gmat;  // DRT block: k = 0 gets G = Xh M1 Xh (qphb.py:769-772); DOP block: 0 (drt1d.py quirk)
 };
 
+template <int NBK>
 __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, int len, double* rho, double* xmx,
                                             bool first_iter) {
+    using S = SM<NBK>;
     const int tid = threadIdx.x;
     const int n = c.n, nn = c.n * c.n;
     const bool act = tid < len;
     const int gi = start + tid;
-    const double xi = act ? c.xs[gi] : 0.0;
+    const double* xs = S::vec(S::XS);
+    double* xh = S::vec(S::XH);
+    const double xi = act ? xs[gi] : 0.0;
     if (act) {
         const double ax = fabs(xi);
-        c.xh[gi] = (xi > 0.0 ? 1.0 : (xi < 0.0 ? -1.0 : 0.0)) * sqrt(ax);
+        xh[gi] = (xi > 0.0 ? 1.0 : (xi < 0.0 ? -1.0 : 0.0)) * sqrt(ax);
     }
     __syncthreads();
-    const double xhi = act ? c.xh[gi] : 0.0;
+    const double xhi = act ? xh[gi] : 0.0;
     double bsum[3] = {0, 0, 0}, gd[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
     if (act) {
         const double inv2s0 = 1.0 / (2.0 * hp.sigma[0] * hp.sigma[0]);
         const double* __restrict__ pcol = c.pen + (start * n + gi);  // symmetric: read column-wise (coalesced)
         for (int j = 0; j < len; ++j) {
             const int gj = start + j;
-            const double xj = c.xs[gj];
+            const double xj = xs[gj];
             const double m0 = pcol[j * n], m1 = pcol[nn + j * n], m2 = pcol[2 * nn + j * n];
             double gam[3] = {(xi * m0) * xj, (xi * m1) * xj, (xi * m2) * xj};
-            if (hp.use_gmat) gam[0] += ((xhi * m1) * c.xh[gj]) * inv2s0;
+            if (hp.use_gmat) gam[0] += ((xhi * m1) * xh[gj]) * inv2s0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 if (j == tid) {
                     gd[k] = gam[k] + (hp.s_alpha[k] - 1.0) / hp.s_0[k];
                 } else {
-                    const double g = gam[k] * c.us[k][gj];
+                    const double g = gam[k] * S::vec(S::US0 + k)[gj];
                     bsum[k] += g;
                     mx[k] = fmax(mx[k], fabs(g));
                 }
             }
         }
     }
-    block_reduce<3, 0x7u>(mx, c);
+    block_reduce<NBK, 3, 0x7u>(mx, c);
     if (act) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -637,13 +660,13 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
             }
             if (isnan(s_hat)) s_hat = 1.0;
             if (s_hat <= 0.0) s_hat = 1e-15;
-            c.sv[k][gi] = s_hat;
+            S::vec(S::SV0 + k)[gi] = s_hat;
         }
     }
     __syncthreads();
     if (act) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) c.us[k][gi] = sqrt(c.sv[k][gi]);
+        for (int k = 0; k < 3; ++k) S::vec(S::US0 + k)[gi] = sqrt(S::vec(S::SV0 + k)[gi]);
     }
     __syncthreads();
     // rho: alpha / (x' S^1/2 M S^1/2 x / xmx + beta)
@@ -652,11 +675,11 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
         const double* __restrict__ pcol = c.pen + (start * n + gi);
         for (int j = 0; j < len; ++j) {
             const int gj = start + j;
-            const double xj = c.xs[gj];
+            const double xj = xs[gj];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const double m = pcol[k * nn + j * n];
-                tr[k] += (xj * c.us[k][gj]) * m;
+                tr[k] += (xj * S::vec(S::US0 + k)[gj]) * m;
                 tx[k] += xj * m;
             }
         }
@@ -664,10 +687,10 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
     double t6[6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        t6[k] = act ? (tr[k] * c.us[k][gi]) * xi : 0.0;
+        t6[k] = act ? (tr[k] * S::vec(S::US0 + k)[gi]) * xi : 0.0;
         t6[3 + k] = act ? tx[k] * xi : 0.0;
     }
-    block_reduce<6, 0u>(t6, c);
+    block_reduce<NBK, 6, 0u>(t6, c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (hp.dw[k] > 0.0) {
@@ -684,14 +707,16 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
 // ------------------------------------------------------------------------------------------------
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
+template <int NBK>
 __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double var_floor, bool update_vz) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, n = c.n, nc = c.nc;
+    const double* xs = SM<NBK>::vec(SM<NBK>::XS);
     for (int r = warp; r < N; r += kWarps) {
         double acc = 0.0, accv = 0.0;
         const double* __restrict__ src = c.rm + (size_t)r * n;
         for (int col = lane; col < n; col += 32) {
-            const double xv = c.xs[col];
+            const double xv = xs[col];
             if (col == c.vz) {
                 acc += c.vzcol[r] * xv;
             } else {
@@ -716,7 +741,7 @@ __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double 
     if (nc > 0 && c.vmm_chrono == nullptr) {
         double t1[1] = {0.0};
         for (int r = tid; r < nc; r += kThreads) t1[0] += c.r2[r];
-        block_reduce<1, 0u>(t1, c);
+        block_reduce<NBK, 1, 0u>(t1, c);
         chrono_mean = t1[0] / (double)nc;
     }
     for (int r = warp; r < N; r += kWarps) {
@@ -756,6 +781,7 @@ __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double 
 // ------------------------------------------------------------------------------------------------
 template <int NBK>
 __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& c) {
+    using S = SM<NBK>;
     const int tid = threadIdx.x;
     const int N = p.n_rows, n = p.n_cols;
     const hdrt_hypers& hy = p.hyp;
@@ -772,22 +798,20 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     {
         double t1[1] = {0.0};
         for (int r = tid; r < N; r += kThreads) t1[0] += c.rv[r];
-        block_reduce<1, 0u>(t1, c);
+        block_reduce<NBK, 1, 0u>(t1, c);
         const double mean = t1[0] / (double)N;
         double t2[1] = {0.0};
         for (int r = tid; r < N; r += kThreads) { const double d = c.rv[r] - mean; t2[0] += d * d; }
-        block_reduce<1, 0u>(t2, c);
+        block_reduce<NBK, 1, 0u>(t2, c);
         var_floor = (t2[0] / (double)N) * 1e-7;
     }
 
     double rho[3], dop_rho[3], xmx[3] = {1, 1, 1}, dop_xmx[3] = {1, 1, 1};
 #pragma unroll
     for (int k = 0; k < 3; ++k) { rho[k] = hy.rho_0[k]; dop_rho[k] = hy.dop_rho_0[k]; }
-    if (tid < c.nv) {
+    if (tid < S::NV) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { c.sv[k][tid] = hy.s_0[k]; c.us[k][tid] = sqrt(hy.s_0[k]); }
-        c.colA[tid] = 0.0;
-        c.colB[tid] = 0.0;
+        for (int k = 0; k < 3; ++k) { S::vec(S::SV0 + k)[tid] = hy.s_0[k]; S::vec(S::US0 + k)[tid] = sqrt(hy.s_0[k]); }
     }
     for (int r = tid; r < N; r += kThreads) {
         c.w[r] = 1.0;
@@ -850,11 +874,11 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         status |= qo.status;
         n_ipm += qo.iters;
         if (qo.fatal) { fatal = true; xi = qo.xi; break; }
-        if (tid < n) c.xs[tid] = qo.xi;
+        if (tid < n) S::vec(S::XS)[tid] = qo.xi;
         __syncthreads();
         if (init) {
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
-            weights_phase(c, nullptr, var_floor, false);
+            weights_phase<NBK>(c, nullptr, var_floor, false);
             for (int r = tid; r < N; r += kThreads) {
                 const double e = c.w[r];
                 est_g[r] = e;
@@ -874,14 +898,14 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
         xi = qo.xi;
         fun = qo.pcost;
-        hyper_block(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
-        if (c.dop_a >= 0) hyper_block(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
-        weights_phase(c, est_g, var_floor, c.vz >= 0);
+        hyper_block<NBK>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
+        if (c.dop_a >= 0) hyper_block<NBK>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
+        weights_phase<NBK>(c, est_g, var_floor, c.vz >= 0);
         {   // convergence, qphb.py:597-603,969-970
             const bool act = tid < n;
             const double dx = xi - x_in;
             double t3[3] = {act ? fabs(dx / (x_in + 1e-15)) : 0.0, act ? fabs(dx) : 0.0, act ? x_in : 0.0};
-            block_reduce<3, 0x3u>(t3, c);
+            block_reduce<NBK, 3, 0x3u>(t3, c);
             const double atol = (t3[2] / (double)n) * 1e-3;
             conv = (t3[0] <= hy.xtol) || (t3[1] <= atol);
         }
@@ -898,13 +922,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         p.x[(size_t)b * n + tid] = xi;
         if (p.s_vectors) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p.s_vectors[((size_t)b * 3 + k) * n + tid] = c.sv[k][tid];
+            for (int k = 0; k < 3; ++k) p.s_vectors[((size_t)b * 3 + k) * n + tid] = S::vec(S::SV0 + k)[tid];
         }
     }
     {
         const bool act = tid < n;
         double t1[1] = {act && !isfinite(xi) ? 1.0 : 0.0};
-        block_reduce<1, 0x1u>(t1, c);
+        block_reduce<NBK, 1, 0x1u>(t1, c);
         if (t1[0] > 0.0 || fatal) status |= HDRT_ST_NAN;
     }
     if (conv) status |= HDRT_ST_CONVERGED;
@@ -927,28 +951,22 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
 }
 
 template <int NBK>
-__global__ void __launch_bounds__(kThreads, (NBK > 0 && NBK <= 7) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, NBK <= 7 ? 2 : 1)
 qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
-    extern __shared__ __align__(16) double smem[];
     __shared__ int s_work;
     Ctx c;
     c.N = p.n_rows; c.n = p.n_cols; c.ns = p.n_special; c.nc = p.n_chrono;
     c.dop_a = p.dop_start; c.dop_b = p.dop_end; c.vz = p.vz_index; c.vb_a = p.vb_start; c.vb_b = p.vb_end;
     c.hvec = p.h; c.l1 = p.l1; c.vz_strength = p.vz_strength;
-    const SmemLayout L = make_layout(p.n_rows, p.n_cols);
-    c.ld = L.ld; c.nv = L.nv; c.ldA = L.ldA;
-    c.PL = smem + L.pl;
-    double* v = smem + L.vec;
-    const int nv = L.nv;
-    c.pdiag = v; c.xs = v + nv; c.bs = v + 2 * nv; c.dsq = v + 3 * nv; c.qs = v + 4 * nv; c.rdiag = v + 5 * nv;
-    c.piv = v + 6 * nv;
-    for (int k = 0; k < 3; ++k) { c.sv[k] = v + (7 + k) * nv; c.us[k] = v + (10 + k) * nv; }
-    c.xh = v + 13 * nv; c.colA = v + 14 * nv; c.colB = v + 15 * nv;
-    c.w = smem + L.rows;
-    c.r2 = c.w + ((p.n_rows + 1) & ~1);
-    c.stage = smem + L.stage;
-    c.red = smem + L.red;
+    c.ld = p.n_cols | 1;
+    const int npad = (p.n_rows + 1) & ~1;
+    c.w = g_smem + SM<NBK>::kRows;
+    c.r2 = c.w + npad;
+    c.PL = c.r2 + npad;
     c.red_phase = 0;
+    // zero the whole vector area once: padding entries (index >= n) of the column buffers must read as zero
+    for (int i = threadIdx.x; i < kNumVec * SM<NBK>::NV; i += kThreads) g_smem[i] = 0.0;
+    __syncthreads();
 
     while (true) {
         if (threadIdx.x == 0) s_work = atomicAdd(work_counter, 1);
@@ -976,8 +994,7 @@ using namespace hdrt;
 
 extern "C" long long hdrt_qphb_smem_bytes(int n_rows, int n_cols) {
     if (n_rows <= 0 || n_cols <= 0 || n_cols > kMaxCols) return -1;
-    const SmemLayout L = make_layout(n_rows, n_cols);
-    const long long bytes = (long long)L.total * 8;
+    const long long bytes = smem_doubles(n_rows, n_cols) * 8;
     if (bytes > 227 * 1024) return -1;
     return bytes;
 }
@@ -1017,10 +1034,8 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
-    const int nbk = (p.n_cols + 15) / 16;
-    if (nbk <= 7) return launch_qphb<7>(h, p, (size_t)smem, st);
-    if (nbk <= 10) return launch_qphb<10>(h, p, (size_t)smem, st);
-    return launch_qphb<0>(h, p, (size_t)smem, st);
+    if (nbk_for(p.n_cols) == 7) return launch_qphb<7>(h, p, (size_t)smem, st);
+    return launch_qphb<10>(h, p, (size_t)smem, st);
 }
 
 extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host) {

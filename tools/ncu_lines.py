@@ -72,3 +72,29 @@ for key, s in per_line.most_common(45):
             text = src_cache[fn][key[1] - 1].strip()[:90]
     top = ', '.join(f'{k[6:]}:{v}' for k, v in per_line_stall[key].most_common(3))
     print(f'{100.0 * s / tot:5.1f}%  exec {per_line_exec[key]:>12}  {key}  {text}   [{top}]')
+
+# ---- per-function summary (device functions located by scanning the source for their first lines)
+import bisect
+fn = os.path.join(os.path.dirname(lib), '..', 'csrc', 'qphb_kernel.cu')
+if os.path.exists(fn):
+    src = open(fn).read().splitlines()
+    marks = []
+    for i, l in enumerate(src, 1):
+        m = re.match(r'\s*(?:template.*\n)?__device__.*?(\w+)\(', l) or re.match(r'^qphb_kernel\(|^__global__.*?(\w+)\(', l)
+        if l.startswith('__device__') or l.startswith('__global__') or l.startswith('qphb_kernel('):
+            name = re.findall(r'(\w+)\(', l)
+            marks.append((i, name[0] if name else l[:30]))
+    starts = [m[0] for m in marks]
+    agg_s, agg_e = collections.Counter(), collections.Counter()
+    for key, s in per_line.items():
+        if key and key[0] == 'qphb_kernel.cu':
+            idx = bisect.bisect_right(starts, key[1]) - 1
+            nm = marks[idx][1] if idx >= 0 else 'header'
+        else:
+            nm = str(key[0]) if key else 'unknown'
+        agg_s[nm] += s
+        agg_e[nm] += per_line_exec[key]
+    te = sum(agg_e.values())
+    print('\nper function: samples%  instr%  (instr)')
+    for nm, s in agg_s.most_common():
+        print(f'  {nm:28s} {100.0*s/tot:5.1f}%  {100.0*agg_e[nm]/te:5.1f}%  {agg_e[nm]}')
