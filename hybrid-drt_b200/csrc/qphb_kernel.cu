@@ -1,4 +1,4 @@
-// Batched QPHB solver: one persistent CTA per spectrum in flight.
+// Batched QPHB solver: one persistent CTA per spectrum in flight, FP64 tensor cores (DMMA) for the dense algebra.
 //
 // Replaces, for a whole batch of spectra at once, the loop of DRT._qphb_fit_core
 // (reference hybdrt/models/drt1d.py:556-1008): qphb.initialize_weights (qphb.py:1609),
@@ -7,30 +7,33 @@
 // convergence test (:597), xmx normalisation (drt1d.py:946) and the hybrid vz_offset column rewrite
 // (drt1d.py:972).
 //
-// Shared memory per CTA (all FP64; offsets of everything but w / r2 / PL are compile-time constants of the
-// instantiation so that loads and stores carry immediate offsets):
-//   16 vectors of length NV = 16 * NBK (pdiag, x broadcast, solve rhs, ...), reduction scratch,
-//   a double-buffered 4-row staging tile for the Gram pass, w[N], r2[N], then
-//   PL   n x ld (ld odd): strict upper triangle = P of the current QP; lower triangle + diagonal =
-//        Cholesky factor L of H = P + diag(1/d^2) of the current interior-point iteration, with each
-//        32 x 32 diagonal block of L replaced by its inverse (the triangular solves are then blocked
-//        matrix-vector products instead of n-step substitution chains).
-// Register layout: thread (ty, tx) = (tid / 16, tid % 16) owns the entries (i, j), i >= j, i = 16a + ty,
-// j = 16b + tx of the symmetric matrix being built (Gram) or factorised (Cholesky) -- NBK (NBK + 1) / 2
-// doubles per thread; the rank-1 updates of both phases run out of registers and shared memory only carries
-// the broadcast row / column.
-// The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the
-// batch and stay in global memory (L2 resident, read-only path).
+// Data layout.  Every n x n symmetric / triangular matrix of the QP is cut into 8 x 8 tiles; tile (j, i), j >= i,
+// belongs to warp (j % WR, i % WC) of a WR x WC warp grid and lives in that warp's registers in the accumulator
+// layout of mma.sync.m8n8k4.f64 (lane (g, q) = (lane / 4, lane % 4) holds [g][2q] and [g][2q + 1]).  In that
+// layout a tile is at the same time a valid A operand and a valid B^T operand of the instruction (the k index is
+// summed over, so the k permutation {2q} / {2q + 1} of the two issues is immaterial):  D += X Z^T costs two DMMAs
+// and no data movement.  Everything is phrased in that form:
+//   Gram      P_ji  = sum over 8-row chunks of (W rm)^T_j (W rm)^T_i^T           (operands staged through smem)
+//   Cholesky  right-looking over tile columns k, fused with the inversion of the factor (Gauss-Jordan on the
+//             identity): after step k the register tile (j, i) holds  -Schur_ji          for i > k,
+//                                                                     -(L^-T)_ij (partial) for i <= k < j,
+//                                                                      (L^-T)_ij (final)   for j <= k,
+//             and the step itself is  "finalise column k: tile <- tile (-L_kk^-1)^T",  "publish column k",
+//             "every tile (j, i) with j > k:  tile += pan_j pan_i^T  (or pan_i pan_j^T for i <= k)".
+//             The 8 x 8 diagonal tile is factorised and inverted by its owner warp with shuffles.
+//   Solves    u = Y (Y^T b) with Y = L^-T straight from the register tiles (DFMA + shuffle reductions).
+// Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the negated P tiles of the current QP
+// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N].
+// The Gram staging buffers alias the pan / partial area.
+// The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
+// stay in global memory (L2 resident, read-only path).
 #include "common.cuh"
 
 namespace hdrt {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kStageRows = 4;  // per buffer; two buffers
 constexpr int kMaxCols = 160;
 constexpr int kRedSlots = 8;
-constexpr int kNumVec = 16;
+constexpr int kNumVec = 12;
 
 // cvxopt coneqp defaults (cvxopt 1.3 coneprog.py; the reference only sets show_progress, qphb.py:25)
 constexpr double kAbsTol = 1e-7;
@@ -41,33 +44,79 @@ constexpr double kStep = 0.99;
 
 extern __shared__ __align__(16) double g_smem[];
 
-// compile-time part of the shared-memory layout (offsets in doubles)
-template <int NBK>
-struct SM {
-    static constexpr int NV = 16 * NBK;
-    static constexpr int LDA = NV + 2;  // staged row: NV columns of W*rm (zero padded) + W*rv at column NV
-    static constexpr int kRed = kNumVec * NV;
-    static constexpr int kRbuf = kRed + 2 * kRedSlots * kWarps;
-    static constexpr int kStage = kRbuf + 16;
-    static constexpr int kRows = kStage + 2 * kStageRows * LDA;
-    enum { PDIAG = 0, XS, BS, DSQ, QS, RDIAG, PIV, SV0, SV1, SV2, US0, US1, US2, XH, COLA, COLB };
+// ------------------------------------------------------------------------------------------------
+// compile-time configuration: tile grid, register slots, shared-memory offsets (in doubles)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int slot_bcount(int TMAX, int WR, int WC, int a) {
+    const int B = (TMAX + WC - 1) / WC;
+    const int m = (WR * a + WR - 1) / WC + 1;  // columns i = WC b + wc <= j = WR a + wr  for some (wr, wc)
+    return m < B ? m : B;
+}
+__host__ __device__ constexpr int slot_base(int TMAX, int WR, int WC, int a) {
+    int s = 0;
+    for (int t = 0; t < a; ++t) s += slot_bcount(TMAX, WR, WC, t);
+    return s;
+}
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+template <int TMAX_, int WR_, int WC_, int MINB_>
+struct Cfg {
+    static constexpr int TMAX = TMAX_, WR = WR_, WC = WC_, MINB = MINB_;
+    static constexpr int kWarps = WR * WC, kThreads = 32 * kWarps;
+    static constexpr int NV = 8 * TMAX;                              // padded vector length
+    static constexpr int A = (TMAX + WR - 1) / WR, B = (TMAX + WC - 1) / WC;
+    static constexpr int NSLOT = slot_base(TMAX, WR, WC, A);
+    static constexpr int NTILE = TMAX * (TMAX + 1) / 2;
+    static constexpr int LDA = (NV % 16 == 8) ? NV + 16 : NV + 8;   // staged row, = 8 (mod 16): conflict-free fragments
+    static constexpr int kStageRows = 8;
+    static constexpr int WPR = kWarps / kStageRows;                  // warps per staged row
+    static constexpr int NPART = WR + WC;
+    // offsets
+    static constexpr int oRed = kNumVec * NV;
+    static constexpr int oRbuf = oRed + 2 * kRedSlots * kWarps;
+    static constexpr int oUnion = oRbuf + 16;
+    static constexpr int oPart = oUnion;                             // QP view: NPART x NV matvec partials
+    static constexpr int oBinv = oPart + NPART * NV;                 //          -L_kk^-1 (64)
+    static constexpr int oScr = oBinv + 64;                          //          diagonal-tile scratch (96)
+    static constexpr int oPan = oScr + 96;                           //          TMAX tiles: column k
+    static constexpr int oStage = oUnion;                            // Gram view: 2 x 8 x LDA
+    static constexpr int oTiles = cmax(oPan + TMAX * 64, oStage + 2 * kStageRows * LDA);
+    static constexpr int oRows = oTiles + NTILE * 64;                // w[N], r2[N]
+    enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH, SPARE };
+    static_assert(kWarps % kStageRows == 0, "staging assumes a multiple of 8 warps");
     static __device__ __forceinline__ double* vec(int k) { return g_smem + k * NV; }
-    static __device__ __forceinline__ double* red() { return g_smem + kRed; }
-    static __device__ __forceinline__ double* rbuf() { return g_smem + kRbuf; }
-    static __device__ __forceinline__ double* stage() { return g_smem + kStage; }
+    static __device__ __forceinline__ double* red() { return g_smem + oRed; }
+    static __device__ __forceinline__ double* rbuf() { return g_smem + oRbuf; }
+    static __device__ __forceinline__ double* part(int p) { return g_smem + oPart + p * NV; }
+    static __device__ __forceinline__ double* binv() { return g_smem + oBinv; }
+    static __device__ __forceinline__ double* scr() { return g_smem + oScr; }
+    static __device__ __forceinline__ double* pan(int t) { return g_smem + oPan + t * 64; }
+    static __device__ __forceinline__ double* stage() { return g_smem + oStage; }
+    static __device__ __forceinline__ double* tile(int j, int i) { return g_smem + oTiles + (j * (j + 1) / 2 + i) * 64; }
+    __host__ __device__ static constexpr int bcount(int a) { return slot_bcount(TMAX, WR, WC, a); }
+    __host__ __device__ static constexpr int sidx(int a, int b) { return slot_base(TMAX, WR, WC, a) + b; }
 };
 
-__host__ __device__ inline int nbk_for(int n) { return (n + 15) / 16 <= 7 ? 7 : 10; }
+using CfgS = Cfg<13, 4, 2, 2>;  // n <= 104: 8 warps, 19 register tiles per warp, two CTAs per SM
+using CfgL = Cfg<20, 4, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, one CTA per SM
 
+template <class C>
+__host__ __device__ inline long long smem_doubles_cfg(int N) {
+    return (long long)C::oRows + 2LL * ((N + 1) & ~1) + 2;
+}
+__host__ __device__ inline bool small_cfg(int n) { return n <= CfgS::NV; }
 __host__ __device__ inline long long smem_doubles(int N, int n) {
-    const int nv = 16 * nbk_for(n);
-    const long long fixed = (long long)kNumVec * nv + 2 * kRedSlots * kWarps + 16 + 2 * kStageRows * (nv + 2);
-    const int ld = n | 1;
-    return fixed + 2LL * ((N + 1) & ~1) + (long long)n * ld + 2;
+    return small_cfg(n) ? smem_doubles_cfg<CfgS>(N) : smem_doubles_cfg<CfgL>(N);
 }
 
+// every slot (a, b) of the calling warp; after unrolling a and b are compile-time constants
+#define HDRT_FOR_SLOTS(C, a, b)                             \
+    _Pragma("unroll") for (int a = 0; a < C::A; ++a)        \
+        _Pragma("unroll") for (int b = 0; b < C::bcount(a); ++b)
+
 struct Ctx {
-    int N, n, ns, nc, dop_a, dop_b, vz, vb_a, vb_b, ld;
+    int N, n, T, ns, nc, dop_a, dop_b, vz, vb_a, vb_b;
+    int wr, wc, lane, g, q;  // warp grid position, lane, accumulator-layout coordinates
     const double* __restrict__ rm;
     const double* __restrict__ rv;
     const double* __restrict__ vmm_eis;
@@ -77,42 +126,49 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
-    double *PL, *w, *r2;
+    double *w, *r2;
+    int* flag;      // shared: factorisation status of the current tile column
     int red_phase;
 };
 
+// D += X Z^T for 8 x 8 tiles in accumulator layout (see the header comment)
+__device__ __forceinline__ void tile_mma(double2& d, const double2& x, const double2& z) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d.x), "+d"(d.y) : "d"(x.x), "d"(z.x));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d.x), "+d"(d.y) : "d"(x.y), "d"(z.y));
+}
+
 // Reduce K per-thread values over the block; bit k of MAXMASK selects max instead of sum.  The result is
 // broadcast to every thread.  One barrier: the scratch buffer alternates between two halves.
-template <int NBK, int K, unsigned MAXMASK>
+template <class C, int K, unsigned MAXMASK>
 __device__ __forceinline__ void block_reduce(double (&v)[K], Ctx& c) {
     static_assert(K <= kRedSlots, "too many reduction slots");
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = ((MAXMASK >> k) & 1u) ? warp_max(v[k]) : warp_sum(v[k]);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* red = SM<NBK>::red() + (c.red_phase & 1) * (kRedSlots * kWarps);
+    double* red = C::red() + (c.red_phase & 1) * (kRedSlots * C::kWarps);
     c.red_phase ^= 1;
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) red[k * kWarps + w] = v[k];
+        for (int k = 0; k < K; ++k) red[k * C::kWarps + w] = v[k];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        double a = red[k * kWarps];
+        double a = red[k * C::kWarps];
 #pragma unroll
-        for (int ww = 1; ww < kWarps; ++ww) {
-            const double t = red[k * kWarps + ww];
+        for (int ww = 1; ww < C::kWarps; ++ww) {
+            const double t = red[k * C::kWarps + ww];
             a = ((MAXMASK >> k) & 1u) ? fmax(a, t) : a + t;
         }
         v[k] = a;
     }
 }
 
-__host__ __device__ constexpr int tri(int a, int b) { return a * (a + 1) / 2 + b; }
-
 // ------------------------------------------------------------------------------------------------
-// Gram: P = (W rm)^T (W rm) + L2  (upper triangle + diagonal),  q = -(W rm)^T (W rv) + l1
-// L2 = sum_k S_k^1/2 M~_k S_k^1/2 as in qphb.calculate_qp_l2_matrix (qphb.py:53-120)
+// Gram: P = (W rm)^T (W rm) + L2,  q = -(W rm)^T (W rv) + l1.  The negated lower tiles of P go to shared
+// memory.  L2 = sum_k S_k^1/2 M~_k S_k^1/2 as in qphb.calculate_qp_l2_matrix (qphb.py:53-120).
 // ------------------------------------------------------------------------------------------------
 struct L2Factors {
     double drt[3];  // l2_lambda_0 * dw_k * rho_k
@@ -120,7 +176,7 @@ struct L2Factors {
     bool use[3];    // derivative_weights[k] > 0
 };
 
-template <int NBK>
+template <class C>
 __device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int i, int j) {
     double acc = 0.0;
     const bool drt = (i >= c.ns) && (j >= c.ns);
@@ -132,303 +188,411 @@ __device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int
         double m = c.pen[k * nn + i * c.n + j];
         if (drt) m *= f.drt[k];
         if (dop) m *= f.dop[k];
-        const double* us = SM<NBK>::vec(SM<NBK>::US0 + k);
+        const double* us = C::vec(C::US0 + k);
         acc += (us[i] * m) * us[j];
     }
     return acc;
 }
 
-// Staging: chunk = kStageRows rows; warp w loads row (w & 3), columns (w >> 2) * 32 + lane + 64 u.
-template <int NBK>
+// Staging: one chunk = 8 rows of [W rm | 0 .. | W rv at column NV]; warp w loads row (w & 7), columns
+// (w >> 3) * 32 + lane + 32 WPR u.
+template <class C>
 struct StageRegs {
-    static constexpr int U = (SM<NBK>::LDA + 63) / 64;
+    static constexpr int U = (C::LDA + 32 * C::WPR - 1) / (32 * C::WPR);
     double v[U];
 };
 
-template <int NBK>
-__device__ __forceinline__ void stage_load(const Ctx& c, int r0, StageRegs<NBK>& s) {
+template <class C>
+__device__ __forceinline__ void stage_load(const Ctx& c, int r0, StageRegs<C>& s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = r0 + (warp & 3);
-    const int cbase = (warp >> 2) * 32 + lane;
+    const int r = r0 + (warp & 7);
+    const int cbase = (warp >> 3) * 32 + lane;
 #pragma unroll
-    for (int u = 0; u < StageRegs<NBK>::U; ++u) s.v[u] = 0.0;
+    for (int u = 0; u < StageRegs<C>::U; ++u) s.v[u] = 0.0;
     if (r < c.N) {
         const double wr = c.w[r];
         const double* __restrict__ src = c.rm + (size_t)r * c.n;
 #pragma unroll
-        for (int u = 0; u < StageRegs<NBK>::U; ++u) {
-            const int col = cbase + 64 * u;
+        for (int u = 0; u < StageRegs<C>::U; ++u) {
+            const int col = cbase + 32 * C::WPR * u;
             double v = 0.0;
             if (col < c.n) v = ((col == c.vz) ? c.vzcol[r] : src[col]) * wr;
-            else if (col == SM<NBK>::NV) v = wr * c.rv[r];
+            else if (col == C::NV) v = wr * c.rv[r];
             s.v[u] = v;
         }
     }
 }
 
-template <int NBK>
-__device__ __forceinline__ void stage_store(int buf, const StageRegs<NBK>& s) {
+template <class C>
+__device__ __forceinline__ void stage_store(int buf, const StageRegs<C>& s) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* dst = SM<NBK>::stage() + (buf * kStageRows + (warp & 3)) * SM<NBK>::LDA;
-    const int cbase = (warp >> 2) * 32 + lane;
+    double* dst = C::stage() + (buf * C::kStageRows + (warp & 7)) * C::LDA;
+    const int cbase = (warp >> 3) * 32 + lane;
 #pragma unroll
-    for (int u = 0; u < StageRegs<NBK>::U; ++u) {
-        const int col = cbase + 64 * u;
-        if (col < SM<NBK>::LDA) dst[col] = s.v[u];
+    for (int u = 0; u < StageRegs<C>::U; ++u) {
+        const int col = cbase + 32 * C::WPR * u;
+        if (col < C::LDA) dst[col] = s.v[u];
     }
 }
 
-template <int NBK>
+template <class C>
 __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scalar, double l1_value, double* p_out,
                                            double* q_out) {
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int n = c.n, N = c.N;
-    constexpr int LDA = SM<NBK>::LDA;
+    const int tid = threadIdx.x;
+    const int n = c.n, N = c.N, T = c.T;
+    const int g = c.g, q = c.q;
+    constexpr int LDA = C::LDA;
     double qacc = 0.0;
-    double C[NBK * (NBK + 1) / 2];
+    double2 S[C::NSLOT];
 #pragma unroll
-    for (int e = 0; e < NBK * (NBK + 1) / 2; ++e) C[e] = 0.0;
-    StageRegs<NBK> sr;
-    stage_load<NBK>(c, 0, sr);
-    __syncthreads();  // previous users of the staging area are done
-    stage_store<NBK>(0, sr);
+    for (int e = 0; e < C::NSLOT; ++e) S[e] = make_double2(0.0, 0.0);
+    StageRegs<C> sr;
+    stage_load<C>(c, 0, sr);
+    __syncthreads();  // previous users of the union area are done
+    stage_store<C>(0, sr);
     __syncthreads();
     int buf = 0;
-    for (int r0 = 0; r0 < N; r0 += kStageRows) {
-        const bool more = r0 + kStageRows < N;
-        if (more) stage_load<NBK>(c, r0 + kStageRows, sr);  // global loads in flight during the FMAs below
-        const double* base = SM<NBK>::stage() + buf * kStageRows * LDA;
+    for (int r0 = 0; r0 < N; r0 += C::kStageRows) {
+        const bool more = r0 + C::kStageRows < N;
+        if (more) stage_load<C>(c, r0 + C::kStageRows, sr);  // global loads in flight during the DMMAs below
+        const double* base = C::stage() + buf * C::kStageRows * LDA;
+        // fragment of tile column X: .x = (W rm)[r0 + q][8X + g], .y = (W rm)[r0 + 4 + q][8X + g]
+        double2 Fa[C::A];
 #pragma unroll
-        for (int rr = 0; rr < kStageRows; ++rr) {   // rows beyond N are staged as zeros
-            const double* row = base + rr * LDA;
-            double ri[NBK], cj[NBK];
-#pragma unroll
-            for (int a = 0; a < NBK; ++a) { ri[a] = row[16 * a + ty]; cj[a] = row[16 * a + tx]; }
-#pragma unroll
-            for (int a = 0; a < NBK; ++a)
-#pragma unroll
-                for (int b = 0; b <= a; ++b) C[tri(a, b)] += ri[a] * cj[b];
-            if (tid < SM<NBK>::NV) qacc += row[tid] * row[SM<NBK>::NV];
+        for (int a = 0; a < C::A; ++a) {
+            const int j = C::WR * a + c.wr;
+            Fa[a] = make_double2(0.0, 0.0);
+            if (j < T) Fa[a] = make_double2(base[q * LDA + 8 * j + g], base[(4 + q) * LDA + 8 * j + g]);
         }
-        if (more) stage_store<NBK>(buf ^ 1, sr);
-        __syncthreads();
-        buf ^= 1;
-    }
-    double* pdiag = SM<NBK>::vec(SM<NBK>::PDIAG);
 #pragma unroll
-    for (int a = 0; a < NBK; ++a)
+        for (int b = 0; b < C::B; ++b) {
+            const int i = C::WC * b + c.wc;
+            if (i < T) {
+                const double2 Fb = make_double2(base[q * LDA + 8 * i + g], base[(4 + q) * LDA + 8 * i + g]);
 #pragma unroll
-        for (int b = 0; b <= a; ++b) {
-            const int i = 16 * a + ty, j = 16 * b + tx;
-            if (i < n && j <= i) {
-                const double val = C[tri(a, b)] + l2_entry<NBK>(c, f, j, i);
-                if (i == j) pdiag[i] = val; else c.PL[j * c.ld + i] = val;
-                if (p_out) {
-                    p_out[(size_t)i * n + j] = val;
-                    p_out[(size_t)j * n + i] = val;
+                for (int a = 0; a < C::A; ++a) {
+                    if (b < C::bcount(a)) {
+                        const int j = C::WR * a + c.wr;
+                        if (j < T && i <= j) tile_mma(S[C::sidx(a, b)], Fa[a], Fb);
+                    }
                 }
             }
         }
+        if (tid < C::NV) {
+#pragma unroll
+            for (int rr = 0; rr < C::kStageRows; ++rr) qacc += base[rr * LDA + tid] * base[rr * LDA + C::NV];
+        }
+        if (more) stage_store<C>(buf ^ 1, sr);
+        __syncthreads();
+        buf ^= 1;
+    }
+    // add the penalty, write -P tiles (padding rows / columns: identity) and the optional dense copy
+    HDRT_FOR_SLOTS(C, a, b) {
+        const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
+        if (j < T && i <= j) {
+            const int r = 8 * j + g, c0 = 8 * i + 2 * q;
+            double v[2] = {S[C::sidx(a, b)].x, S[C::sidx(a, b)].y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cc = c0 + e;
+                if (r < n && cc < n) {
+                    v[e] += l2_entry<C>(c, f, r, cc);
+                    if (p_out && cc <= r) {
+                        p_out[(size_t)r * n + cc] = v[e];
+                        p_out[(size_t)cc * n + r] = v[e];
+                    }
+                } else {
+                    v[e] = (r == cc) ? 1.0 : 0.0;
+                }
+            }
+            *reinterpret_cast<double2*>(C::tile(j, i) + 2 * c.lane) = make_double2(-v[0], -v[1]);
+        }
+    }
     if (tid < n) {
         const double qv = -qacc + (l1_scalar ? l1_value : c.l1[tid]);
-        SM<NBK>::vec(SM<NBK>::QS)[tid] = qv;
+        C::vec(C::QS)[tid] = qv;
         if (q_out) q_out[tid] = qv;
     }
     __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky of H = P + diag(dsq) into the lower triangle of PL, then in-place inversion of the 32 x 32
-// diagonal blocks.  rdiag[j] = 1 / L_jj.  Returns false on breakdown (uniform across the block).
+// Matrix-vector products on tiles in accumulator layout.  Lane (g, q) of a tile with row block R and column
+// block C holds t[g][2q], t[g][2q + 1]:
+//   "N" part:  out[8R + g]            += t[g][2q] v[8C + 2q] + t[g][2q + 1] v[8C + 2q + 1]   (reduce over q)
+//   "T" part:  out[8C + 2q (+1)]      += t[g][2q (+1)] v[8R + g]                               (reduce over g)
+// Warps that share a row block (same wr) or a column block (same wc) write separate partial vectors.
 // ------------------------------------------------------------------------------------------------
-template <int NBK>
-__device__ __forceinline__ bool factor_phase(Ctx& c) {
-    using S = SM<NBK>;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = tid & 15, ty = tid >> 4;
-    const int n = c.n, ld = c.ld;
-    double* PL = c.PL;
-    double* rdiag = S::vec(S::RDIAG);
-    bool ok = true;
-    {
-        const double* pdiag = S::vec(S::PDIAG);
-        const double* dsq = S::vec(S::DSQ);
-        double C[NBK * (NBK + 1) / 2];
-#pragma unroll
-        for (int a = 0; a < NBK; ++a)
-#pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const int i = 16 * a + ty, j = 16 * b + tx;
-                double v = 0.0;
-                if (i < n && j <= i) v = (i == j) ? (pdiag[i] + dsq[i]) : PL[j * ld + i];
-                C[tri(a, b)] = v;
-            }
-        // Right-looking, one barrier per column.  The owners of column k (tx == k % 16) publish it unscaled;
-        // the owner of the pivot also publishes 1 / a_kk (NaN on breakdown).  Every thread then applies
-        // C_ij -= a_ik (a_jk / a_kk) to the entries it holds.  Padding rows (i >= n) hold zeros throughout.
-        double* piv = S::vec(S::PIV);
-        double* rb = S::rbuf();
-#pragma unroll
-        for (int kb = 0; kb < NBK; ++kb) {
-#pragma unroll 1
-            for (int kx = 0; kx < 16; ++kx) {
-                const int k = 16 * kb + kx;
-                if (!ok || k >= n) break;
-                double* col = S::vec(S::COLA + (k & 1));
-                if (tx == kx) {
-#pragma unroll
-                    for (int a = kb; a < NBK; ++a) col[16 * a + ty] = C[tri(a, kb)];
-                    if (ty == kx) {
-                        const double pv = C[tri(kb, kb)];
-                        piv[k] = pv;
-                        rb[k & 1] = (pv > 0.0 && isfinite(pv)) ? 1.0 / pv : nan("");
-                    }
-                }
-                __syncthreads();
-                const double r = rb[k & 1];
-                if (isnan(r)) { ok = false; break; }
-                double ri[NBK], cj[NBK];
-#pragma unroll
-                for (int a = kb; a < NBK; ++a) { ri[a] = col[16 * a + ty]; cj[a] = col[16 * a + tx] * r; }
-                if (tx <= kx) cj[kb] = 0.0;  // columns <= k of this block are final
-#pragma unroll
-                for (int a = kb; a < NBK; ++a)
-#pragma unroll
-                    for (int b = kb; b <= a; ++b) C[tri(a, b)] -= ri[a] * cj[b];
-            }
-        }
-        __syncthreads();
-        if (!ok) return false;
-        if (tid < n) rdiag[tid] = 1.0 / sqrt(piv[tid]);
-        __syncthreads();
-#pragma unroll
-        for (int a = 0; a < NBK; ++a)
-#pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const int i = 16 * a + ty, j = 16 * b + tx;
-                if (i < n && j <= i) PL[i * ld + j] = C[tri(a, b)] * rdiag[j];
-            }
-    }
-    __syncthreads();
-    // Invert the diagonal blocks in place: warp w takes block w (n <= 160 -> at most 5 blocks); lane l builds
-    // column l of the inverse row by row: x_i = -(1 / L_ii) sum_{k < i} L_ik x_k, x_l = 1 / L_ll, x_{k<l} = 0.
-    const int nblk = (n + 31) >> 5;
-    if (warp < nblk) {
-        const int r0 = 32 * warp, m = min(32, n - r0);
-        double x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            x[i] = 0.0;
-            if (i < m) {
-                const double* lr = PL + (r0 + i) * ld + r0;
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int k = 0; k < i; ++k) acc[k & 3] += lr[k] * x[k];
-                const double rd = rdiag[r0 + i];
-                const double dot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-                x[i] = (i == lane) ? rd : ((i > lane) ? -rd * dot : 0.0);
-            }
-        }
-        __syncwarp();
-        if (lane < m) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i >= lane && i < m) PL[(r0 + i) * ld + r0 + lane] = x[i];
-        }
-    }
-    __syncthreads();
-    return true;
+__device__ __forceinline__ double reduce_q(double v) {
+    v += __shfl_xor_sync(kFull, v, 1);
+    v += __shfl_xor_sync(kFull, v, 2);
+    return v;
+}
+__device__ __forceinline__ double reduce_g(double v) {
+    v += __shfl_xor_sync(kFull, v, 4);
+    v += __shfl_xor_sync(kFull, v, 8);
+    v += __shfl_xor_sync(kFull, v, 16);
+    return v;
 }
 
-// Solve L L^T u = bs in place with the block-inverted factor.
-template <int NBK>
-__device__ __forceinline__ void solve_phase(Ctx& c) {
-    using S = SM<NBK>;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = c.n, ld = c.ld;
-    const double* PL = c.PL;
-    double* bs = S::vec(S::BS);
-    const int nblk = (n + 31) >> 5;
-    __syncthreads();
-    // forward: y = L^-1 b
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int r0 = 32 * blk, m = min(32, n - r0);
-        if (warp == 0) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if (lane < m) {
-                const double* xr = PL + (r0 + lane) * ld + r0;
-                const double* bb = bs + r0;
+// part[0 .. WC) <- N parts (indexed by wc), part[WC .. WC + WR) <- T parts (indexed by wr) of -P xs
+template <class C>
+__device__ __forceinline__ void matvec_p(const Ctx& c, const double* xs) {
+    const int T = c.T, g = c.g, q = c.q;
+    double accN[C::A];
+    double2 accT[C::B];
+    double xg[C::A];
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    if (k <= lane) a0 += xr[k] * bb[k];
-                    if (k + 1 <= lane) a1 += xr[k + 1] * bb[k + 1];
-                    if (k + 2 <= lane) a2 += xr[k + 2] * bb[k + 2];
-                    if (k + 3 <= lane) a3 += xr[k + 3] * bb[k + 3];
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::WR * a + c.wr;
+        accN[a] = 0.0;
+        xg[a] = (j < T) ? xs[8 * j + g] : 0.0;
+    }
+#pragma unroll
+    for (int b = 0; b < C::B; ++b) {
+        const int i = C::WC * b + c.wc;
+        accT[b] = make_double2(0.0, 0.0);
+        if (i < T) {
+            const double2 xb = *reinterpret_cast<const double2*>(xs + 8 * i + 2 * q);
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) {
+                if (b < C::bcount(a)) {
+                    const int j = C::WR * a + c.wr;
+                    if (j < T && i <= j) {
+                        const double2 p = *reinterpret_cast<const double2*>(C::tile(j, i) + 2 * c.lane);
+                        accN[a] = fma(p.x, xb.x, accN[a]);
+                        accN[a] = fma(p.y, xb.y, accN[a]);
+                        if (i != j) {
+                            accT[b].x = fma(p.x, xg[a], accT[b].x);
+                            accT[b].y = fma(p.y, xg[a], accT[b].y);
+                        }
+                    }
                 }
             }
-            __syncwarp();
-            if (lane < m) bs[r0 + lane] = (a0 + a1) + (a2 + a3);
         }
-        if (r0 + m >= n) break;
-        __syncthreads();
-        const int i = r0 + 32 + tid;
-        if (i < n) {
-            const double* lr = PL + i * ld + r0;
-            const double* bb = bs + r0;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    }
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                a0 += lr[k] * bb[k];
-                a1 += lr[k + 1] * bb[k + 1];
-                a2 += lr[k + 2] * bb[k + 2];
-                a3 += lr[k + 3] * bb[k + 3];
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::WR * a + c.wr;
+        const double v = reduce_q(accN[a]);
+        if (q == 0 && j < T) C::part(c.wc)[8 * j + g] = v;
+    }
+#pragma unroll
+    for (int b = 0; b < C::B; ++b) {
+        const int i = C::WC * b + c.wc;
+        const double v0 = reduce_g(accT[b].x), v1 = reduce_g(accT[b].y);
+        if (g == 0 && i < T) *reinterpret_cast<double2*>(C::part(C::WC + c.wr) + 8 * i + 2 * q) = make_double2(v0, v1);
+    }
+}
+
+// Solve H u = bs with the register tiles Y = L^-T of factor_invert:  u = Y (Y^T bs).  Tile slot (a, b) holds
+// Y_ij (row block i, column block j).  On return u[t] = sum_{p < WR} part(WC + p)[t].
+template <class C>
+__device__ __forceinline__ void solve_phase(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
+    const int T = c.T, g = c.g, q = c.q;
+    {   // t = Y^T bs: T part (reduce over g), partial per wc
+        double2 acc[C::A];
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) acc[a] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < C::B; ++b) {
+            const int i = C::WC * b + c.wc;
+            if (i < T) {
+                const double bg = bs[8 * i + g];
+#pragma unroll
+                for (int a = 0; a < C::A; ++a) {
+                    if (b < C::bcount(a)) {
+                        const int j = C::WR * a + c.wr;
+                        if (j < T && i <= j) {
+                            acc[a].x = fma(S[C::sidx(a, b)].x, bg, acc[a].x);
+                            acc[a].y = fma(S[C::sidx(a, b)].y, bg, acc[a].y);
+                        }
+                    }
+                }
             }
-            bs[i] -= (a0 + a1) + (a2 + a3);
         }
-        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) {
+            const int j = C::WR * a + c.wr;
+            const double v0 = reduce_g(acc[a].x), v1 = reduce_g(acc[a].y);
+            if (g == 0 && j < T) *reinterpret_cast<double2*>(C::part(c.wc) + 8 * j + 2 * q) = make_double2(v0, v1);
+        }
     }
     __syncthreads();
-    // backward: x = L^-T y
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int r0 = 32 * blk, m = min(32, n - r0);
-        if (warp == 0) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if (lane < m) {
-                const double* xc = PL + r0 * ld + r0 + lane;
-                const double* bb = bs + r0;
+    {   // u = Y t: N part (reduce over q), partial per wr
+        double2 tv[C::A];
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    if (k >= lane && k < m) a0 += xc[k * ld] * bb[k];
-                    if (k + 1 >= lane && k + 1 < m) a1 += xc[(k + 1) * ld] * bb[k + 1];
-                    if (k + 2 >= lane && k + 2 < m) a2 += xc[(k + 2) * ld] * bb[k + 2];
-                    if (k + 3 >= lane && k + 3 < m) a3 += xc[(k + 3) * ld] * bb[k + 3];
+        for (int a = 0; a < C::A; ++a) {
+            const int j = C::WR * a + c.wr;
+            tv[a] = make_double2(0.0, 0.0);
+            if (j < T) {
+#pragma unroll
+                for (int p = 0; p < C::WC; ++p) {
+                    const double2 t = *reinterpret_cast<const double2*>(C::part(p) + 8 * j + 2 * q);
+                    tv[a].x += t.x;
+                    tv[a].y += t.y;
                 }
             }
-            __syncwarp();
-            if (lane < m) bs[r0 + lane] = (a0 + a1) + (a2 + a3);
         }
-        if (blk == 0) break;
-        __syncthreads();
-        if (tid < r0) {
-            const double* lc = PL + r0 * ld + tid;
-            const double* bb = bs + r0;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if (m == 32) {
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    a0 += lc[k * ld] * bb[k];
-                    a1 += lc[(k + 1) * ld] * bb[k + 1];
-                    a2 += lc[(k + 2) * ld] * bb[k + 2];
-                    a3 += lc[(k + 3) * ld] * bb[k + 3];
+        for (int b = 0; b < C::B; ++b) {
+            const int i = C::WC * b + c.wc;
+            double acc = 0.0;
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) {
+                if (b < C::bcount(a)) {
+                    const int j = C::WR * a + c.wr;
+                    if (j < T && i <= j) {
+                        acc = fma(S[C::sidx(a, b)].x, tv[a].x, acc);
+                        acc = fma(S[C::sidx(a, b)].y, tv[a].y, acc);
+                    }
                 }
-            } else {
-                for (int k = 0; k < m; ++k) a0 += lc[k * ld] * bb[k];
             }
-            bs[tid] -= (a0 + a1) + (a2 + a3);
+            acc = reduce_q(acc);
+            if (q == 0 && i < T) C::part(C::WC + c.wr)[8 * i + g] = acc;
         }
-        __syncthreads();
     }
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Cholesky C_kk = L L^T by rows (lane r = lane % 8
+// owns row r; the four lane groups of 8 compute it redundantly) fused with Gauss-Jordan on the identity, each
+// group carrying two columns of W = L^-1.  Publishes -W (row-major) to `binv`; returns Y_kk = W^T in accumulator
+// layout.  false on breakdown (non-positive or non-finite pivot), uniformly over the warp.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool diag_factor(const double2 s, double* scr, double* binv, double2& ykk, int lane) {
+    const int g = lane >> 2, q = lane & 3, r = lane & 7, rep = lane >> 3;
+    const int grp = lane & 24;
+    *reinterpret_cast<double2*>(scr + g * 10 + 2 * q) = make_double2(-s.x, -s.y);
+    __syncwarp();
+    double a[8];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const double2 t = *reinterpret_cast<const double2*>(scr + r * 10 + 2 * m);
+        a[2 * m] = t.x;
+        a[2 * m + 1] = t.y;
+    }
+    double dg = scr[r * 10 + r];
+    double w0 = (r == 2 * rep) ? 1.0 : 0.0, w1 = (r == 2 * rep + 1) ? 1.0 : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        const double piv = __shfl_sync(kFull, dg, grp | cc);
+        ok = ok && (piv > 0.0) && (piv < INFINITY);
+        const double rinv = rsqrt(piv);
+        const double lc = a[cc] * rinv;  // l[r][cc] for r >= cc
+        dg = fma(-lc, lc, dg);
+#pragma unroll
+        for (int m = cc + 1; m < 8; ++m) {
+            const double lm = __shfl_sync(kFull, lc, grp | m);
+            a[m] = fma(-lc, lm, a[m]);
+        }
+        const double wc0 = __shfl_sync(kFull, w0 * rinv, grp | cc);
+        const double wc1 = __shfl_sync(kFull, w1 * rinv, grp | cc);
+        w0 = (r == cc) ? wc0 : ((r > cc) ? fma(-lc, wc0, w0) : w0);
+        w1 = (r == cc) ? wc1 : ((r > cc) ? fma(-lc, wc1, w1) : w1);
+    }
+    *reinterpret_cast<double2*>(binv + r * 8 + 2 * rep) = make_double2(-w0, -w1);
+    __syncwarp();
+    ykk = make_double2(-binv[(2 * q) * 8 + g], -binv[(2 * q + 1) * 8 + g]);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H = P + diag(dsq) -> register tiles Y = L^-T (H = L L^T).  See the header comment for the invariant.
+// Returns false on breakdown (uniform across the block).
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
+    const int T = c.T, g = c.g, q = c.q, lane = c.lane;
+    const double* dsq = C::vec(C::DSQ);
+    HDRT_FOR_SLOTS(C, a, b) {
+        const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < T && i <= j) {
+            v = *reinterpret_cast<const double2*>(C::tile(j, i) + 2 * lane);
+            if (i == j) {
+                const double d = dsq[8 * j + g];
+                if (g == 2 * q) v.x -= d;
+                if (g == 2 * q + 1) v.y -= d;
+            }
+        }
+        S[C::sidx(a, b)] = v;
+    }
+#pragma unroll 1
+    for (int k = 0; k < T; ++k) {
+        if ((k % C::WR) == c.wr && (k % C::WC) == c.wc) {  // owner of the diagonal tile
+            double2 sk = make_double2(0.0, 0.0);
+            HDRT_FOR_SLOTS(C, a, b) {
+                if (C::WR * a + c.wr == k && C::WC * b + c.wc == k) sk = S[C::sidx(a, b)];
+            }
+            double2 ykk;
+            const bool ok = diag_factor(sk, C::scr(), C::binv(), ykk, lane);
+            HDRT_FOR_SLOTS(C, a, b) {
+                if (C::WR * a + c.wr == k && C::WC * b + c.wc == k) S[C::sidx(a, b)] = ykk;
+            }
+            if (lane == 0) *c.flag = ok ? 1 : 0;
+        }
+        __syncthreads();  // (A) -L_kk^-1 published
+        if (*c.flag == 0) return false;
+        const double2 bn = *reinterpret_cast<const double2*>(C::binv() + 2 * lane);
+        // finalise column k of the combined matrix [Y above the diagonal; L below] and publish it
+        HDRT_FOR_SLOTS(C, a, b) {
+            const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
+            if (j < T && i <= j) {
+                if (i == k && j > k) {         // L_jk = C_jk L_kk^-T; the slot restarts as the accumulator of -Y_kj
+                    double2 r2 = make_double2(0.0, 0.0);
+                    tile_mma(r2, S[C::sidx(a, b)], bn);
+                    *reinterpret_cast<double2*>(C::pan(j) + 2 * lane) = r2;
+                    S[C::sidx(a, b)] = make_double2(0.0, 0.0);
+                } else if (j == k && i < k) {  // Y_ik = (accumulated) L_kk^-T, final
+                    double2 r2 = make_double2(0.0, 0.0);
+                    tile_mma(r2, S[C::sidx(a, b)], bn);
+                    *reinterpret_cast<double2*>(C::pan(i) + 2 * lane) = r2;
+                    S[C::sidx(a, b)] = r2;
+                } else if (j == k && i == k) {
+                    *reinterpret_cast<double2*>(C::pan(k) + 2 * lane) = S[C::sidx(a, b)];
+                }
+            }
+        }
+        __syncthreads();  // (B) column k published
+        if (k + 1 < T) {
+            double2 Fa[C::A];
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) {
+                const int j = C::WR * a + c.wr;
+                Fa[a] = make_double2(0.0, 0.0);
+                if (j < T && j > k) Fa[a] = *reinterpret_cast<const double2*>(C::pan(j) + 2 * lane);
+            }
+#pragma unroll
+            for (int b = 0; b < C::B; ++b) {
+                const int i = C::WC * b + c.wc;
+                if (i < T) {
+                    const double2 Fb = *reinterpret_cast<const double2*>(C::pan(i) + 2 * lane);
+                    if (i <= k) {
+#pragma unroll
+                        for (int a = 0; a < C::A; ++a) {
+                            if (b < C::bcount(a)) {
+                                const int j = C::WR * a + c.wr;
+                                if (j < T && j > k && i <= j) tile_mma(S[C::sidx(a, b)], Fb, Fa[a]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < C::A; ++a) {
+                            if (b < C::bcount(a)) {
+                                const int j = C::WR * a + c.wr;
+                                if (j < T && j > k && i <= j) tile_mma(S[C::sidx(a, b)], Fa[a], Fb);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    (void)g; (void)q;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -443,15 +607,23 @@ struct QpOut {
     bool fatal;  // Cholesky failed before the first iterate existed (cvxopt raises ValueError)
 };
 
-template <int NBK>
+template <class C>
+__device__ __forceinline__ double sum_parts(int first, int count, int t) {
+    double v = 0.0;
+#pragma unroll
+    for (int p = 0; p < C::NPART; ++p)
+        if (p >= first && p < first + count) v += C::part(p)[t];
+    return v;
+}
+
+template <class C>
 __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
-    using S = SM<NBK>;
     const int tid = threadIdx.x;
-    const int n = c.n, ld = c.ld;
+    const int n = c.n;
     const bool act = tid < n;
-    double* xs = S::vec(S::XS);
-    double* bs = S::vec(S::BS);
-    const double qi = act ? S::vec(S::QS)[tid] : 0.0;
+    double* xs = C::vec(C::XS);
+    double* bs = C::vec(C::BS);
+    const double qi = act ? C::vec(C::QS)[tid] : 0.0;
     const double hi = act ? c.hvec[tid] : 0.0;
     QpOut out;
     out.xi = 0.0; out.pcost = 0.0; out.iters = 0; out.status = 0; out.fatal = false;
@@ -459,10 +631,11 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
     double resx0, resz0;
     {
         double t2[2] = {qi * qi, hi * hi};
-        block_reduce<NBK, 2, 0u>(t2, c);
+        block_reduce<C, 2, 0u>(t2, c);
         resx0 = fmax(1.0, sqrt(t2[0]));
         resz0 = fmax(1.0, sqrt(t2[1]));
     }
+    double2 S[C::NSLOT];
     double xi = 0.0, si = 1.0, zi = 1.0, di = 1.0, dinv = 1.0, lam = 1.0;
     double rxi = 0.0, rzi = 0.0, gap = 0.0, pcost = 0.0;
     int iters;
@@ -472,35 +645,16 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
         if (iters >= 0) {
             if (act) xs[tid] = xi;
             __syncthreads();
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            if (act) {
-                const double* colp = c.PL + tid;       // P[j][tid], j < tid  (upper triangle, column tid)
-                int j = 0;
-                for (; j + 3 < tid; j += 4) {
-                    a0 += colp[j * ld] * xs[j];
-                    a1 += colp[(j + 1) * ld] * xs[j + 1];
-                    a2 += colp[(j + 2) * ld] * xs[j + 2];
-                    a3 += colp[(j + 3) * ld] * xs[j + 3];
-                }
-                for (; j < tid; ++j) a0 += colp[j * ld] * xs[j];
-                a1 += S::vec(S::PDIAG)[tid] * xi;
-                const double* rowp = c.PL + tid * ld;  // P[tid][j], j > tid
-                j = tid + 1;
-                for (; j + 3 < n; j += 4) {
-                    a0 += rowp[j] * xs[j];
-                    a1 += rowp[j + 1] * xs[j + 1];
-                    a2 += rowp[j + 2] * xs[j + 2];
-                    a3 += rowp[j + 3] * xs[j + 3];
-                }
-                for (; j < n; ++j) a0 += rowp[j] * xs[j];
-            }
-            rxi = ((a0 + a1) + (a2 + a3)) + qi;
+            matvec_p<C>(c, xs);
+            __syncthreads();
+            const double px = act ? -sum_parts<C>(0, C::NPART, tid) : 0.0;
+            rxi = px + qi;
             const double f0p = act ? (xi * rxi + xi * qi) : 0.0;
             rxi -= zi;
             rzi = si - hi - xi;
             double t5[5] = {f0p, act ? rxi * rxi : 0.0, act ? rzi * rzi : 0.0, act ? zi * rzi : 0.0,
                             act ? (iters == 0 ? si * zi : lam * lam) : 0.0};
-            block_reduce<NBK, 5, 0u>(t5, c);
+            block_reduce<C, 5, 0u>(t5, c);
             const double f0 = 0.5 * t5[0];
             const double resx = sqrt(t5[1]), resz = sqrt(t5[2]);
             gap = t5[4];
@@ -522,9 +676,9 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
                 lam = sqrt(si * zi);
             }
         }
-        if (act) S::vec(S::DSQ)[tid] = dinv * dinv;
+        if (act) C::vec(C::DSQ)[tid] = dinv * dinv;
         __syncthreads();
-        if (!factor_phase<NBK>(c)) {
+        if (!factor_invert<C>(c, S)) {
             out.status |= HDRT_ST_KKT_FAIL;
             if (iters <= 0) { out.fatal = true; xi = nan(""); }
             break;
@@ -532,12 +686,13 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
         if (iters < 0) {
             // solve [P+I] x = -q - h ; z = -x - h ; s = -z, shifted into the cone
             if (act) bs[tid] = -qi - hi;
-            solve_phase<NBK>(c);
-            xi = act ? bs[tid] : 0.0;
+            __syncthreads();
+            solve_phase<C>(c, S, bs);
+            xi = act ? sum_parts<C>(C::WC, C::WR, tid) : 0.0;
             zi = -xi - hi;
             si = -zi;
             double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
-            block_reduce<NBK, 4, 0xAu>(t4, c);
+            block_reduce<C, 4, 0xAu>(t4, c);
             const double nrms = sqrt(t4[0]), ts = t4[1], nrmz = sqrt(t4[2]), tz = t4[3];
             if (ts >= -1e-8 * fmax(nrms, 1.0)) si += 1.0 + ts;
             if (tz >= -1e-8 * fmax(nrmz, 1.0)) zi += 1.0 + tz;
@@ -559,8 +714,9 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             dzi = dzi - di * dsi;
             const double zs = dinv * dzi;
             if (act) bs[tid] = dxi - dinv * zs;
-            solve_phase<NBK>(c);
-            dxi = act ? bs[tid] : 0.0;
+            __syncthreads();
+            solve_phase<C>(c, S, bs);
+            dxi = act ? sum_parts<C>(C::WC, C::WR, tid) : 0.0;
             dzi = -dinv * dxi - zs;
             dsi = dsi - dzi;
             const double prod = dsi * dzi;
@@ -568,7 +724,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             dsi = dsi / lam;
             dzi = dzi / lam;
             double t3[3] = {act ? prod : 0.0, act ? -dsi : -INFINITY, act ? -dzi : -INFINITY};
-            block_reduce<NBK, 3, 0x6u>(t3, c);
+            block_reduce<C, 3, 0x6u>(t3, c);
             const double t = fmax(0.0, fmax(t3[1], t3[2]));
             if (t == 0.0) step = 1.0;
             else if (pass == 0) step = fmin(1.0, 1.0 / t);
@@ -595,7 +751,6 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
     out.iters = iters < 0 ? 0 : iters;
     return out;
 }
-
 // ------------------------------------------------------------------------------------------------
 // Hyper-parameter updates for one coefficient block (DRT or DOP): qphb.solve_s / solve_rho
 // ------------------------------------------------------------------------------------------------
@@ -604,16 +759,15 @@ struct BlockHyp {
     bool use_gmat;  // DRT block: k = 0 gets G = Xh M1 Xh (qphb.py:769-772); DOP block: 0 (drt1d.py quirk)
 };
 
-template <int NBK>
+template <class C>
 __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, int len, double* rho, double* xmx,
                                             bool first_iter) {
-    using S = SM<NBK>;
     const int tid = threadIdx.x;
     const int n = c.n, nn = c.n * c.n;
     const bool act = tid < len;
     const int gi = start + tid;
-    const double* xs = S::vec(S::XS);
-    double* xh = S::vec(S::XH);
+    const double* xs = C::vec(C::XS);
+    double* xh = C::vec(C::XH);
     const double xi = act ? xs[gi] : 0.0;
     if (act) {
         const double ax = fabs(xi);
@@ -636,14 +790,14 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
                 if (j == tid) {
                     gd[k] = gam[k] + (hp.s_alpha[k] - 1.0) / hp.s_0[k];
                 } else {
-                    const double g = gam[k] * S::vec(S::US0 + k)[gj];
+                    const double g = gam[k] * C::vec(C::US0 + k)[gj];
                     bsum[k] += g;
                     mx[k] = fmax(mx[k], fabs(g));
                 }
             }
         }
     }
-    block_reduce<NBK, 3, 0x7u>(mx, c);
+    block_reduce<C, 3, 0x7u>(mx, c);
     if (act) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -660,13 +814,13 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
             }
             if (isnan(s_hat)) s_hat = 1.0;
             if (s_hat <= 0.0) s_hat = 1e-15;
-            S::vec(S::SV0 + k)[gi] = s_hat;
+            C::vec(C::SV0 + k)[gi] = s_hat;
         }
     }
     __syncthreads();
     if (act) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) S::vec(S::US0 + k)[gi] = sqrt(S::vec(S::SV0 + k)[gi]);
+        for (int k = 0; k < 3; ++k) C::vec(C::US0 + k)[gi] = sqrt(C::vec(C::SV0 + k)[gi]);
     }
     __syncthreads();
     // rho: alpha / (x' S^1/2 M S^1/2 x / xmx + beta)
@@ -679,7 +833,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const double m = pcol[k * nn + j * n];
-                tr[k] += (xj * S::vec(S::US0 + k)[gj]) * m;
+                tr[k] += (xj * C::vec(C::US0 + k)[gj]) * m;
                 tx[k] += xj * m;
             }
         }
@@ -687,10 +841,10 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
     double t6[6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        t6[k] = act ? (tr[k] * S::vec(S::US0 + k)[gi]) * xi : 0.0;
+        t6[k] = act ? (tr[k] * C::vec(C::US0 + k)[gi]) * xi : 0.0;
         t6[3 + k] = act ? tx[k] * xi : 0.0;
     }
-    block_reduce<NBK, 6, 0u>(t6, c);
+    block_reduce<C, 6, 0u>(t6, c);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (hp.dw[k] > 0.0) {
@@ -707,12 +861,12 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
 // ------------------------------------------------------------------------------------------------
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
-template <int NBK>
+template <class C>
 __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double var_floor, bool update_vz) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, n = c.n, nc = c.nc;
-    const double* xs = SM<NBK>::vec(SM<NBK>::XS);
-    for (int r = warp; r < N; r += kWarps) {
+    const double* xs = C::vec(C::XS);
+    for (int r = warp; r < N; r += C::kWarps) {
         double acc = 0.0, accv = 0.0;
         const double* __restrict__ src = c.rm + (size_t)r * n;
         for (int col = lane; col < n; col += 32) {
@@ -740,11 +894,11 @@ __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double 
     double chrono_mean = 0.0;
     if (nc > 0 && c.vmm_chrono == nullptr) {
         double t1[1] = {0.0};
-        for (int r = tid; r < nc; r += kThreads) t1[0] += c.r2[r];
-        block_reduce<NBK, 1, 0u>(t1, c);
+        for (int r = tid; r < nc; r += C::kThreads) t1[0] += c.r2[r];
+        block_reduce<C, 1, 0u>(t1, c);
         chrono_mean = t1[0] / (double)nc;
     }
-    for (int r = warp; r < N; r += kWarps) {
+    for (int r = warp; r < N; r += C::kWarps) {
         double s_hat;
         if (r < nc) {
             if (c.vmm_chrono == nullptr) {
@@ -778,10 +932,8 @@ __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double 
 // ------------------------------------------------------------------------------------------------
 // One spectrum.  The outer loop runs phase -1 (initialize_weights), 0..max_iter-1 (iterate_qphb) and,
 // when P/q are requested, one final Gram-only phase (calculate_pq) through the same code.
-// ------------------------------------------------------------------------------------------------
-template <int NBK>
+template <class C>
 __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& c) {
-    using S = SM<NBK>;
     const int tid = threadIdx.x;
     const int N = p.n_rows, n = p.n_cols;
     const hdrt_hypers& hy = p.hyp;
@@ -797,23 +949,23 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     double var_floor;
     {
         double t1[1] = {0.0};
-        for (int r = tid; r < N; r += kThreads) t1[0] += c.rv[r];
-        block_reduce<NBK, 1, 0u>(t1, c);
+        for (int r = tid; r < N; r += C::kThreads) t1[0] += c.rv[r];
+        block_reduce<C, 1, 0u>(t1, c);
         const double mean = t1[0] / (double)N;
         double t2[1] = {0.0};
-        for (int r = tid; r < N; r += kThreads) { const double d = c.rv[r] - mean; t2[0] += d * d; }
-        block_reduce<NBK, 1, 0u>(t2, c);
+        for (int r = tid; r < N; r += C::kThreads) { const double d = c.rv[r] - mean; t2[0] += d * d; }
+        block_reduce<C, 1, 0u>(t2, c);
         var_floor = (t2[0] / (double)N) * 1e-7;
     }
 
     double rho[3], dop_rho[3], xmx[3] = {1, 1, 1}, dop_xmx[3] = {1, 1, 1};
 #pragma unroll
     for (int k = 0; k < 3; ++k) { rho[k] = hy.rho_0[k]; dop_rho[k] = hy.dop_rho_0[k]; }
-    if (tid < S::NV) {
+    if (tid < C::NV) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { S::vec(S::SV0 + k)[tid] = hy.s_0[k]; S::vec(S::US0 + k)[tid] = sqrt(hy.s_0[k]); }
+        for (int k = 0; k < 3; ++k) { C::vec(C::SV0 + k)[tid] = hy.s_0[k]; C::vec(C::US0 + k)[tid] = sqrt(hy.s_0[k]); }
     }
-    for (int r = tid; r < N; r += kThreads) {
+    for (int r = tid; r < N; r += C::kThreads) {
         c.w[r] = 1.0;
         if (c.vz >= 0) c.vzcol[r] = 0.0;
     }
@@ -844,7 +996,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         const double x_in = xi;
         // weights entering the Gram: 1 (init) / weight factors (drt1d.py:881-892) / scaled weights (:991-1008)
         if (!init) {
-            for (int r = tid; r < N; r += kThreads) {
+            for (int r = tid; r < N; r += C::kThreads) {
                 double w = c.w[r];
                 if (final_pq) {
                     w *= hy.weight_factor;
@@ -866,20 +1018,20 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             }
         }
         __syncthreads();
-        gram_phase<NBK>(c, f, init, hy.iw_l1_lambda_0, final_pq ? p.p_matrix + (size_t)b * n * n : nullptr,
+        gram_phase<C>(c, f, init, hy.iw_l1_lambda_0, final_pq ? p.p_matrix + (size_t)b * n * n : nullptr,
                         (final_pq && p.q_vector) ? p.q_vector + (size_t)b * n : nullptr);
         if (final_pq) break;
 
-        QpOut qo = qp_phase<NBK>(c);
+        QpOut qo = qp_phase<C>(c);
         status |= qo.status;
         n_ipm += qo.iters;
         if (qo.fatal) { fatal = true; xi = qo.xi; break; }
-        if (tid < n) S::vec(S::XS)[tid] = qo.xi;
+        if (tid < n) C::vec(C::XS)[tid] = qo.xi;
         __syncthreads();
         if (init) {
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
-            weights_phase<NBK>(c, nullptr, var_floor, false);
-            for (int r = tid; r < N; r += kThreads) {
+            weights_phase<C>(c, nullptr, var_floor, false);
+            for (int r = tid; r < N; r += C::kThreads) {
                 const double e = c.w[r];
                 est_g[r] = e;
                 double wi = e;
@@ -898,21 +1050,21 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
         xi = qo.xi;
         fun = qo.pcost;
-        hyper_block<NBK>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
-        if (c.dop_a >= 0) hyper_block<NBK>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
-        weights_phase<NBK>(c, est_g, var_floor, c.vz >= 0);
+        hyper_block<C>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
+        if (c.dop_a >= 0) hyper_block<C>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
+        weights_phase<C>(c, est_g, var_floor, c.vz >= 0);
         {   // convergence, qphb.py:597-603,969-970
             const bool act = tid < n;
             const double dx = xi - x_in;
             double t3[3] = {act ? fabs(dx / (x_in + 1e-15)) : 0.0, act ? fabs(dx) : 0.0, act ? x_in : 0.0};
-            block_reduce<NBK, 3, 0x3u>(t3, c);
+            block_reduce<C, 3, 0x3u>(t3, c);
             const double atol = (t3[2] / (double)n) * 1e-3;
             conv = (t3[0] <= hy.xtol) || (t3[1] <= atol);
         }
         ++it;
         if (conv || it >= hy.max_iter) {
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
-            if (p.weights) for (int r = tid; r < N; r += kThreads) p.weights[(size_t)b * N + r] = c.w[r];
+            if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = c.w[r];
             if (p.p_matrix == nullptr) break;
             final_pq = true;
         }
@@ -922,13 +1074,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         p.x[(size_t)b * n + tid] = xi;
         if (p.s_vectors) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) p.s_vectors[((size_t)b * 3 + k) * n + tid] = S::vec(S::SV0 + k)[tid];
+            for (int k = 0; k < 3; ++k) p.s_vectors[((size_t)b * 3 + k) * n + tid] = C::vec(C::SV0 + k)[tid];
         }
     }
     {
         const bool act = tid < n;
         double t1[1] = {act && !isfinite(xi) ? 1.0 : 0.0};
-        block_reduce<NBK, 1, 0x1u>(t1, c);
+        block_reduce<C, 1, 0x1u>(t1, c);
         if (t1[0] > 0.0 || fatal) status |= HDRT_ST_NAN;
     }
     if (conv) status |= HDRT_ST_CONVERGED;
@@ -946,26 +1098,30 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (p.n_ipm) p.n_ipm[b] = n_ipm;
         if (p.status) p.status[b] = status;
     }
-    if (fatal && p.weights) for (int r = tid; r < N; r += kThreads) p.weights[(size_t)b * N + r] = c.w[r];
+    if (fatal && p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = c.w[r];
     __syncthreads();
 }
 
-template <int NBK>
-__global__ void __launch_bounds__(kThreads, NBK <= 7 ? 2 : 1)
+template <class C>
+__global__ void __launch_bounds__(C::kThreads, C::MINB)
 qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     __shared__ int s_work;
+    __shared__ int s_flag;
     Ctx c;
     c.N = p.n_rows; c.n = p.n_cols; c.ns = p.n_special; c.nc = p.n_chrono;
     c.dop_a = p.dop_start; c.dop_b = p.dop_end; c.vz = p.vz_index; c.vb_a = p.vb_start; c.vb_b = p.vb_end;
     c.hvec = p.h; c.l1 = p.l1; c.vz_strength = p.vz_strength;
-    c.ld = p.n_cols | 1;
+    c.T = (p.n_cols + 7) >> 3;
+    c.lane = threadIdx.x & 31;
+    c.g = c.lane >> 2; c.q = c.lane & 3;
+    c.wr = (threadIdx.x >> 5) / C::WC; c.wc = (threadIdx.x >> 5) % C::WC;
+    c.flag = &s_flag;
     const int npad = (p.n_rows + 1) & ~1;
-    c.w = g_smem + SM<NBK>::kRows;
+    c.w = g_smem + C::oRows;
     c.r2 = c.w + npad;
-    c.PL = c.r2 + npad;
     c.red_phase = 0;
     // zero the whole vector area once: padding entries (index >= n) of the column buffers must read as zero
-    for (int i = threadIdx.x; i < kNumVec * SM<NBK>::NV; i += kThreads) g_smem[i] = 0.0;
+    for (int i = threadIdx.x; i < kNumVec * C::NV; i += C::kThreads) g_smem[i] = 0.0;
     __syncthreads();
 
     while (true) {
@@ -974,7 +1130,7 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
         const int b = s_work;
         __syncthreads();
         if (b >= p.batch) break;
-        fit_one<NBK>(p, b, c);
+        fit_one<C>(p, b, c);
     }
 }
 
@@ -999,16 +1155,16 @@ extern "C" long long hdrt_qphb_smem_bytes(int n_rows, int n_cols) {
     return bytes;
 }
 
-template <int NBK>
+template <class C>
 static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, cudaStream_t st) {
-    HDRT_CUDA_CHECK(cudaFuncSetAttribute(qphb_kernel<NBK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HDRT_CUDA_CHECK(cudaFuncSetAttribute(qphb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    HDRT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qphb_kernel<NBK>, kThreads, smem));
+    HDRT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qphb_kernel<C>, C::kThreads, smem));
     if (occ < 1) { set_error("kernel cannot be resident (smem %zu)", smem); return HDRT_ERR_UNSUPPORTED; }
     int grid = h->sm_count * occ;
     if (grid > p.batch) grid = p.batch;
     HDRT_CUDA_CHECK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
-    qphb_kernel<NBK><<<grid, kThreads, smem, st>>>(p, h->work_counter);
+    qphb_kernel<C><<<grid, C::kThreads, smem, st>>>(p, h->work_counter);
     HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }
@@ -1034,8 +1190,8 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
-    if (nbk_for(p.n_cols) == 7) return launch_qphb<7>(h, p, (size_t)smem, st);
-    return launch_qphb<10>(h, p, (size_t)smem, st);
+    if (small_cfg(p.n_cols)) return launch_qphb<CfgS>(h, p, (size_t)smem, st);
+    return launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }
 
 extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host) {
