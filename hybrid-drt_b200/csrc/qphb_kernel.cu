@@ -8,23 +8,24 @@
 // (drt1d.py:972).
 //
 // Data layout.  Every n x n symmetric / triangular matrix of the QP is cut into 8 x 8 tiles; tile (j, i), j >= i,
-// belongs to warp (j % WR, i % WC) of a WR x WC warp grid and lives in that warp's registers in the accumulator
-// layout of mma.sync.m8n8k4.f64 (lane (g, q) = (lane / 4, lane % 4) holds [g][2q] and [g][2q + 1]).  In that
-// layout a tile is at the same time a valid A operand and a valid B^T operand of the instruction (the k index is
-// summed over, so the k permutation {2q} / {2q + 1} of the two issues is immaterial):  D += X Z^T costs two DMMAs
-// and no data movement.  Everything is phrased in that form:
-//   Gram      P_ji  = sum over 8-row chunks of (W rm)^T_j (W rm)^T_i^T           (operands staged through smem)
+// belongs to warp (j % W, i % W) of a W x W warp grid and lives in that warp's registers ("slot" (a, b) =
+// (j / W, i / W), b <= a) in the accumulator layout of mma.sync.m8n8k4.f64: lane (g, q) = (lane / 4, lane % 4)
+// holds [g][2q] and [g][2q + 1].  In that layout a tile is at the same time a valid A operand and a valid B^T
+// operand of the instruction (the k index is summed over, so the k permutation {2q} / {2q + 1} of the two issues
+// is immaterial):  D += X Z^T costs two DMMAs and no data movement.  Everything is phrased in that form:
+//   Gram      P_ji = sum over 8-row chunks of rm^T_j diag(w^2) rm^T_i^T   (rm chunks staged transposed by cp.async)
 //   Cholesky  right-looking over tile columns k, fused with the inversion of the factor (Gauss-Jordan on the
-//             identity): after step k the register tile (j, i) holds  -Schur_ji          for i > k,
-//                                                                     -(L^-T)_ij (partial) for i <= k < j,
-//                                                                      (L^-T)_ij (final)   for j <= k,
-//             and the step itself is  "finalise column k: tile <- tile (-L_kk^-1)^T",  "publish column k",
-//             "every tile (j, i) with j > k:  tile += pan_j pan_i^T  (or pan_i pan_j^T for i <= k)".
-//             The 8 x 8 diagonal tile is factorised and inverted by its owner warp with shuffles.
+//             identity).  After step k the register tile (j, i) holds   -Schur_ji                     for i > k,
+//                                                      sum_{m <= k} L_jm (L^-1)_mi  (lower orient.)  for i <= k < j,
+//                                                      (L^-T)_ij  (upper orientation, final)         for j <= k.
+//             Step k: the owner of tile (k, k) factorises and inverts it with shuffles and publishes -L_kk^-1;
+//             the owners of column k (j > k) form L_jk = tile (-L_kk^-1)^T, the owners of row k (i < k) form
+//             (L^-T)_ik = tile^T (-L_kk^-1)^T; all of column k of [L^-T above; L below] is published to shared
+//             memory ("pan"), and every tile (j, i) with j > k gets  tile += pan_j pan_i^T.
 //   Solves    u = Y (Y^T b) with Y = L^-T straight from the register tiles (DFMA + shuffle reductions).
 // Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the negated P tiles of the current QP
-// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N].
-// The Gram staging buffers alias the pan / partial area.
+// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N]
+// and one more N-vector.  The Gram staging buffers alias the pan / partial area.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
 #include "common.cuh"
@@ -47,76 +48,61 @@ extern __shared__ __align__(16) double g_smem[];
 // ------------------------------------------------------------------------------------------------
 // compile-time configuration: tile grid, register slots, shared-memory offsets (in doubles)
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int slot_bcount(int TMAX, int WR, int WC, int a) {
-    const int B = (TMAX + WC - 1) / WC;
-    const int m = (WR * a + WR - 1) / WC + 1;  // columns i = WC b + wc <= j = WR a + wr  for some (wr, wc)
-    return m < B ? m : B;
-}
-__host__ __device__ constexpr int slot_base(int TMAX, int WR, int WC, int a) {
-    int s = 0;
-    for (int t = 0; t < a; ++t) s += slot_bcount(TMAX, WR, WC, t);
-    return s;
-}
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int TMAX_, int WR_, int WC_, int MINB_>
+template <int TMAX_, int W_, int MINB_>
 struct Cfg {
-    static constexpr int TMAX = TMAX_, WR = WR_, WC = WC_, MINB = MINB_;
-    static constexpr int kWarps = WR * WC, kThreads = 32 * kWarps;
-    static constexpr int NV = 8 * TMAX;                              // padded vector length
-    static constexpr int A = (TMAX + WR - 1) / WR, B = (TMAX + WC - 1) / WC;
-    static constexpr int NSLOT = slot_base(TMAX, WR, WC, A);
+    static constexpr int TMAX = TMAX_, W = W_, MINB = MINB_;
+    static constexpr int kWarps = W * W, kThreads = 32 * kWarps;
+    static constexpr int NV = 8 * TMAX;               // padded vector length
+    static constexpr int A = (TMAX + W - 1) / W;      // slot rows per warp; slot (a, b), b <= a
+    static constexpr int NSLOT = A * (A + 1) / 2;
     static constexpr int NTILE = TMAX * (TMAX + 1) / 2;
-    static constexpr int LDA = (NV % 16 == 8) ? NV + 16 : NV + 8;   // staged row, = 8 (mod 16): conflict-free fragments
-    static constexpr int kStageRows = 8;
-    static constexpr int WPR = kWarps / kStageRows;                  // warps per staged row
-    static constexpr int NPART = WR + WC;
+    static constexpr int NPART = 2 * W;
+    static constexpr int kChunk = 8;                  // rows of rm per Gram step (two DMMA k-steps)
     // offsets
     static constexpr int oRed = kNumVec * NV;
     static constexpr int oRbuf = oRed + 2 * kRedSlots * kWarps;
     static constexpr int oUnion = oRbuf + 16;
-    static constexpr int oPart = oUnion;                             // QP view: NPART x NV matvec partials
-    static constexpr int oBinv = oPart + NPART * NV;                 //          -L_kk^-1 (64)
-    static constexpr int oScr = oBinv + 64;                          //          diagonal-tile scratch (96)
-    static constexpr int oPan = oScr + 96;                           //          TMAX tiles: column k
-    static constexpr int oStage = oUnion;                            // Gram view: 2 x 8 x LDA
-    static constexpr int oTiles = cmax(oPan + TMAX * 64, oStage + 2 * kStageRows * LDA);
-    static constexpr int oRows = oTiles + NTILE * 64;                // w[N], r2[N]
+    static constexpr int oPart = oUnion;                       // QP view: NPART x NV matvec partials
+    static constexpr int oBinv = oPart + NPART * NV;           //          -L_kk^-1 (64)
+    static constexpr int oScr = oBinv + 64;                    //          diagonal-tile scratch (160)
+    static constexpr int oTr = oScr + 160;                     //          per-warp transpose scratch (80 each)
+    static constexpr int oPan = oTr + 80 * kWarps;             //          TMAX tiles: column k
+    static constexpr int oStage = oUnion;                      // Gram view: 2 x NV x 8 (transposed chunks)
+    static constexpr int oTiles = cmax(oPan + TMAX * 64, oStage + 2 * NV * kChunk);
+    static constexpr int oRows = oTiles + NTILE * 64;          // w[N], r2[N], aux[N]
     enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH, SPARE };
-    static_assert(kWarps % kStageRows == 0, "staging assumes a multiple of 8 warps");
     static __device__ __forceinline__ double* vec(int k) { return g_smem + k * NV; }
     static __device__ __forceinline__ double* red() { return g_smem + oRed; }
     static __device__ __forceinline__ double* rbuf() { return g_smem + oRbuf; }
     static __device__ __forceinline__ double* part(int p) { return g_smem + oPart + p * NV; }
     static __device__ __forceinline__ double* binv() { return g_smem + oBinv; }
     static __device__ __forceinline__ double* scr() { return g_smem + oScr; }
-    static __device__ __forceinline__ double* pan(int t) { return g_smem + oPan + t * 64; }
+    static __device__ __forceinline__ double* tr(int warp) { return g_smem + oTr + 80 * warp; }
+    static __device__ __forceinline__ double* pan() { return g_smem + oPan; }
     static __device__ __forceinline__ double* stage() { return g_smem + oStage; }
-    static __device__ __forceinline__ double* tile(int j, int i) { return g_smem + oTiles + (j * (j + 1) / 2 + i) * 64; }
-    __host__ __device__ static constexpr int bcount(int a) { return slot_bcount(TMAX, WR, WC, a); }
-    __host__ __device__ static constexpr int sidx(int a, int b) { return slot_base(TMAX, WR, WC, a) + b; }
+    static __device__ __forceinline__ double* tiles() { return g_smem + oTiles; }
+    __host__ __device__ static constexpr int sidx(int a, int b) { return a * (a + 1) / 2 + b; }
 };
 
-using CfgS = Cfg<13, 4, 2, 2>;  // n <= 104: 8 warps, 19 register tiles per warp, two CTAs per SM
-using CfgL = Cfg<20, 4, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, one CTA per SM
+using CfgS = Cfg<13, 2, 3>;  // n <= 104:  4 warps, 28 register tiles per warp, three CTAs per SM
+using CfgL = Cfg<20, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, one CTA per SM
 
+__host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>
 __host__ __device__ inline long long smem_doubles_cfg(int N) {
-    return (long long)C::oRows + 2LL * ((N + 1) & ~1) + 2;
+    return (long long)C::oRows + 3LL * rows_pad(N) + 2;
 }
 __host__ __device__ inline bool small_cfg(int n) { return n <= CfgS::NV; }
 __host__ __device__ inline long long smem_doubles(int N, int n) {
     return small_cfg(n) ? smem_doubles_cfg<CfgS>(N) : smem_doubles_cfg<CfgL>(N);
 }
 
-// every slot (a, b) of the calling warp; after unrolling a and b are compile-time constants
-#define HDRT_FOR_SLOTS(C, a, b)                             \
-    _Pragma("unroll") for (int a = 0; a < C::A; ++a)        \
-        _Pragma("unroll") for (int b = 0; b < C::bcount(a); ++b)
-
 struct Ctx {
     int N, n, T, ns, nc, dop_a, dop_b, vz, vb_a, vb_b;
     int wr, wc, lane, g, q;  // warp grid position, lane, accumulator-layout coordinates
+    bool dv;                 // the diagonal slots (a, a) of this warp are inside the lower triangle (wc <= wr)
     const double* __restrict__ rm;
     const double* __restrict__ rv;
     const double* __restrict__ vmm_eis;
@@ -126,7 +112,7 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
-    double *w, *r2;
+    double *w, *r2, *aux;
     int* flag;      // shared: factorisation status of the current tile column
     int red_phase;
 };
@@ -137,6 +123,30 @@ __device__ __forceinline__ void tile_mma(double2& d, const double2& x, const dou
         : "+d"(d.x), "+d"(d.y) : "d"(x.x), "d"(z.x));
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d.x), "+d"(d.y) : "d"(x.y), "d"(z.y));
+}
+
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void sts2(double* p, const double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int bytes = valid ? 8 : 0;  // zero-fill when !valid
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ double reduce_q(double v) {
+    v += __shfl_xor_sync(kFull, v, 1);
+    v += __shfl_xor_sync(kFull, v, 2);
+    return v;
+}
+__device__ __forceinline__ double reduce_g(double v) {
+    v += __shfl_xor_sync(kFull, v, 4);
+    v += __shfl_xor_sync(kFull, v, 8);
+    v += __shfl_xor_sync(kFull, v, 16);
+    return v;
 }
 
 // Reduce K per-thread values over the block; bit k of MAXMASK selects max instead of sum.  The result is
@@ -167,7 +177,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gram: P = (W rm)^T (W rm) + L2,  q = -(W rm)^T (W rv) + l1.  The negated lower tiles of P go to shared
+// Gram: P = rm^T diag(w^2) rm + L2,  q = -rm^T (w^2 rv) + l1.  The negated lower tiles of P go to shared
 // memory.  L2 = sum_k S_k^1/2 M~_k S_k^1/2 as in qphb.calculate_qp_l2_matrix (qphb.py:53-120).
 // ------------------------------------------------------------------------------------------------
 struct L2Factors {
@@ -194,45 +204,25 @@ __device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int
     return acc;
 }
 
-// Staging: one chunk = 8 rows of [W rm | 0 .. | W rv at column NV]; warp w loads row (w & 7), columns
-// (w >> 3) * 32 + lane + 32 WPR u.
+// One chunk = 8 rows of rm, staged transposed: stage[col][rr] = rm[r0 + rr][col] (zero beyond N / n).  One warp
+// instruction copies a 4-column x 8-row block (lane = 4 rr + cl): 32-byte global segments, conflict-free stores.
+// The vz_offset column of a hybrid fit is read from its per-spectrum buffer.
 template <class C>
-struct StageRegs {
-    static constexpr int U = (C::LDA + 32 * C::WPR - 1) / (32 * C::WPR);
-    double v[U];
-};
-
-template <class C>
-__device__ __forceinline__ void stage_load(const Ctx& c, int r0, StageRegs<C>& s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = r0 + (warp & 7);
-    const int cbase = (warp >> 3) * 32 + lane;
+__device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
+    const int warp = threadIdx.x >> 5, cl = c.lane & 3, rr = c.lane >> 2;
+    const bool rok = r0 + rr < c.N;
+    const double* srow = c.rm + (size_t)(r0 + rr) * c.n;
+    double* drow = C::stage() + buf * C::NV * C::kChunk + rr;
 #pragma unroll
-    for (int u = 0; u < StageRegs<C>::U; ++u) s.v[u] = 0.0;
-    if (r < c.N) {
-        const double wr = c.w[r];
-        const double* __restrict__ src = c.rm + (size_t)r * c.n;
-#pragma unroll
-        for (int u = 0; u < StageRegs<C>::U; ++u) {
-            const int col = cbase + 32 * C::WPR * u;
-            double v = 0.0;
-            if (col < c.n) v = ((col == c.vz) ? c.vzcol[r] : src[col]) * wr;
-            else if (col == C::NV) v = wr * c.rv[r];
-            s.v[u] = v;
+    for (int u = 0; u < (C::NV / 4 + C::kWarps - 1) / C::kWarps; ++u) {
+        const int col = 4 * (warp + C::kWarps * u) + cl;
+        if (col < C::NV) {
+            const bool ok = rok && col < c.n;
+            const double* src = (col == c.vz) ? (c.vzcol + r0 + rr) : (srow + col);
+            cp_async8(drow + col * C::kChunk, ok ? src : c.rm, ok);
         }
     }
-}
-
-template <class C>
-__device__ __forceinline__ void stage_store(int buf, const StageRegs<C>& s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* dst = C::stage() + (buf * C::kStageRows + (warp & 7)) * C::LDA;
-    const int cbase = (warp >> 3) * 32 + lane;
-#pragma unroll
-    for (int u = 0; u < StageRegs<C>::U; ++u) {
-        const int col = cbase + 32 * C::WPR * u;
-        if (col < C::LDA) dst[col] = s.v[u];
-    }
+    cp_async_commit();
 }
 
 template <class C>
@@ -240,78 +230,99 @@ __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_s
                                            double* q_out) {
     const int tid = threadIdx.x;
     const int n = c.n, N = c.N, T = c.T;
-    const int g = c.g, q = c.q;
-    constexpr int LDA = C::LDA;
-    double qacc = 0.0;
+    const int g = c.g, q = c.q, lane = c.lane;
+    double* w2 = c.r2;      // w^2, zero padded to a multiple of 8
+    double* w2rv = c.aux;   // w^2 rv
+    __syncthreads();        // previous users of the union area and of r2 are done
+    stage_chunk<C>(c, 0, 0);
+    for (int r = tid; r < rows_pad(N); r += C::kThreads) {
+        double ww = 0.0, wv = 0.0;
+        if (r < N) { ww = c.w[r] * c.w[r]; wv = ww * c.rv[r]; }
+        w2[r] = ww;
+        w2rv[r] = wv;
+    }
+    constexpr int QU = (4 * C::NV + C::kThreads - 1) / C::kThreads;  // q: lane group of 4 per column
+    double qacc[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) qacc[u] = 0.0;
     double2 S[C::NSLOT];
 #pragma unroll
     for (int e = 0; e < C::NSLOT; ++e) S[e] = make_double2(0.0, 0.0);
-    StageRegs<C> sr;
-    stage_load<C>(c, 0, sr);
-    __syncthreads();  // previous users of the union area are done
-    stage_store<C>(0, sr);
-    __syncthreads();
     int buf = 0;
-    for (int r0 = 0; r0 < N; r0 += C::kStageRows) {
-        const bool more = r0 + C::kStageRows < N;
-        if (more) stage_load<C>(c, r0 + C::kStageRows, sr);  // global loads in flight during the DMMAs below
-        const double* base = C::stage() + buf * C::kStageRows * LDA;
-        // fragment of tile column X: .x = (W rm)[r0 + q][8X + g], .y = (W rm)[r0 + 4 + q][8X + g]
-        double2 Fa[C::A];
+    for (int r0 = 0; r0 < N; r0 += C::kChunk) {
+        const bool more = r0 + C::kChunk < N;
+        if (more) stage_chunk<C>(c, r0 + C::kChunk, buf ^ 1);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        const double* base = C::stage() + buf * C::NV * C::kChunk;
+        // fragment of tile column X: .x = rm[r0 + 2q][8X + g], .y = rm[r0 + 2q + 1][8X + g]
+        const double* frow = base + (8 * c.wr + g) * C::kChunk + 2 * q;
+        const double* fcol = base + (8 * c.wc + g) * C::kChunk + 2 * q;
+        const double2 wq = lds2(w2 + r0 + 2 * q);
 #pragma unroll
         for (int a = 0; a < C::A; ++a) {
-            const int j = C::WR * a + c.wr;
-            Fa[a] = make_double2(0.0, 0.0);
-            if (j < T) Fa[a] = make_double2(base[q * LDA + 8 * j + g], base[(4 + q) * LDA + 8 * j + g]);
+            if (C::W * a + c.wr < T) {
+                double2 Fa = lds2(frow + a * (C::W * 64));
+                Fa.x *= wq.x;
+                Fa.y *= wq.y;
+#pragma unroll
+                for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(fcol + b * (C::W * 64)));
+                if (c.dv) tile_mma(S[C::sidx(a, a)], Fa, lds2(fcol + a * (C::W * 64)));
+            }
         }
+        {
+            const double2 wv = lds2(w2rv + r0 + 2 * (tid & 3));
 #pragma unroll
-        for (int b = 0; b < C::B; ++b) {
-            const int i = C::WC * b + c.wc;
-            if (i < T) {
-                const double2 Fb = make_double2(base[q * LDA + 8 * i + g], base[(4 + q) * LDA + 8 * i + g]);
-#pragma unroll
-                for (int a = 0; a < C::A; ++a) {
-                    if (b < C::bcount(a)) {
-                        const int j = C::WR * a + c.wr;
-                        if (j < T && i <= j) tile_mma(S[C::sidx(a, b)], Fa[a], Fb);
-                    }
+            for (int u = 0; u < QU; ++u) {
+                const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
+                if (e < 4 * C::NV) {
+                    const double2 v = lds2(base + 2 * e);
+                    qacc[u] = fma(v.x, wv.x, qacc[u]);
+                    qacc[u] = fma(v.y, wv.y, qacc[u]);
                 }
             }
         }
-        if (tid < C::NV) {
-#pragma unroll
-            for (int rr = 0; rr < C::kStageRows; ++rr) qacc += base[rr * LDA + tid] * base[rr * LDA + C::NV];
-        }
-        if (more) stage_store<C>(buf ^ 1, sr);
-        __syncthreads();
+        __syncthreads();  // the buffer is free for the chunk after next
         buf ^= 1;
     }
     // add the penalty, write -P tiles (padding rows / columns: identity) and the optional dense copy
-    HDRT_FOR_SLOTS(C, a, b) {
-        const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
-        if (j < T && i <= j) {
-            const int r = 8 * j + g, c0 = 8 * i + 2 * q;
-            double v[2] = {S[C::sidx(a, b)].x, S[C::sidx(a, b)].y};
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int cc = c0 + e;
-                if (r < n && cc < n) {
-                    v[e] += l2_entry<C>(c, f, r, cc);
-                    if (p_out && cc <= r) {
-                        p_out[(size_t)r * n + cc] = v[e];
-                        p_out[(size_t)cc * n + r] = v[e];
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::W * a + c.wr;
+        if (j < T) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                const int i = C::W * b + c.wc;
+                if (b < a || c.dv) {
+                    const int r = 8 * j + g, c0 = 8 * i + 2 * q;
+                    double v[2] = {S[C::sidx(a, b)].x, S[C::sidx(a, b)].y};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = c0 + e;
+                        if (r < n && cc < n) {
+                            v[e] += l2_entry<C>(c, f, r, cc);
+                            if (p_out && cc <= r) {
+                                p_out[(size_t)r * n + cc] = v[e];
+                                p_out[(size_t)cc * n + r] = v[e];
+                            }
+                        } else {
+                            v[e] = (r == cc) ? 1.0 : 0.0;
+                        }
                     }
-                } else {
-                    v[e] = (r == cc) ? 1.0 : 0.0;
+                    sts2(C::tiles() + (j * (j + 1) / 2 + i) * 64 + 2 * lane, make_double2(-v[0], -v[1]));
                 }
             }
-            *reinterpret_cast<double2*>(C::tile(j, i) + 2 * c.lane) = make_double2(-v[0], -v[1]);
         }
     }
-    if (tid < n) {
-        const double qv = -qacc + (l1_scalar ? l1_value : c.l1[tid]);
-        C::vec(C::QS)[tid] = qv;
-        if (q_out) q_out[tid] = qv;
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+        const int col = (tid + C::kThreads * u) >> 2;
+        const double s = reduce_q(qacc[u]);
+        if ((tid & 3) == 0 && col < n) {
+            const double qv = -s + (l1_scalar ? l1_value : c.l1[col]);
+            C::vec(C::QS)[col] = qv;
+            if (q_out) q_out[col] = qv;
+        }
     }
     __syncthreads();
 }
@@ -323,179 +334,150 @@ __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_s
 //   "T" part:  out[8C + 2q (+1)]      += t[g][2q (+1)] v[8R + g]                               (reduce over g)
 // Warps that share a row block (same wr) or a column block (same wc) write separate partial vectors.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double reduce_q(double v) {
-    v += __shfl_xor_sync(kFull, v, 1);
-    v += __shfl_xor_sync(kFull, v, 2);
-    return v;
-}
-__device__ __forceinline__ double reduce_g(double v) {
-    v += __shfl_xor_sync(kFull, v, 4);
-    v += __shfl_xor_sync(kFull, v, 8);
-    v += __shfl_xor_sync(kFull, v, 16);
-    return v;
-}
-
-// part[0 .. WC) <- N parts (indexed by wc), part[WC .. WC + WR) <- T parts (indexed by wr) of -P xs
+// part[0 .. W) <- N parts (indexed by wc), part[W .. 2W) <- T parts (indexed by wr) of -P xs
 template <class C>
 __device__ __forceinline__ void matvec_p(const Ctx& c, const double* xs) {
     const int T = c.T, g = c.g, q = c.q;
-    double accN[C::A];
-    double2 accT[C::B];
-    double xg[C::A];
+    double2 accT[C::A];
+#pragma unroll
+    for (int b = 0; b < C::A; ++b) accT[b] = make_double2(0.0, 0.0);
+    const double* xr = xs + 8 * c.wr + g;
+    const double* xc = xs + 8 * c.wc + 2 * q;
 #pragma unroll
     for (int a = 0; a < C::A; ++a) {
-        const int j = C::WR * a + c.wr;
-        accN[a] = 0.0;
-        xg[a] = (j < T) ? xs[8 * j + g] : 0.0;
-    }
+        const int j = C::W * a + c.wr;
+        if (j < T) {
+            const double xg = xr[a * (8 * C::W)];
+            const double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * c.lane;
+            double accN = 0.0;
 #pragma unroll
-    for (int b = 0; b < C::B; ++b) {
-        const int i = C::WC * b + c.wc;
-        accT[b] = make_double2(0.0, 0.0);
-        if (i < T) {
-            const double2 xb = *reinterpret_cast<const double2*>(xs + 8 * i + 2 * q);
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) {
-                if (b < C::bcount(a)) {
-                    const int j = C::WR * a + c.wr;
-                    if (j < T && i <= j) {
-                        const double2 p = *reinterpret_cast<const double2*>(C::tile(j, i) + 2 * c.lane);
-                        accN[a] = fma(p.x, xb.x, accN[a]);
-                        accN[a] = fma(p.y, xb.y, accN[a]);
-                        if (i != j) {
-                            accT[b].x = fma(p.x, xg[a], accT[b].x);
-                            accT[b].y = fma(p.y, xg[a], accT[b].y);
-                        }
-                    }
+            for (int b = 0; b < a; ++b) {
+                const double2 p = lds2(trow + b * (C::W * 64));
+                const double2 xb = lds2(xc + b * (8 * C::W));
+                accN = fma(p.x, xb.x, accN);
+                accN = fma(p.y, xb.y, accN);
+                accT[b].x = fma(p.x, xg, accT[b].x);
+                accT[b].y = fma(p.y, xg, accT[b].y);
+            }
+            if (c.dv) {  // slot (a, a): a diagonal tile when wc == wr (N part only), else below the diagonal
+                const double2 p = lds2(trow + a * (C::W * 64));
+                const double2 xb = lds2(xc + a * (8 * C::W));
+                accN = fma(p.x, xb.x, accN);
+                accN = fma(p.y, xb.y, accN);
+                if (c.wc != c.wr) {
+                    accT[a].x = fma(p.x, xg, accT[a].x);
+                    accT[a].y = fma(p.y, xg, accT[a].y);
                 }
             }
+            accN = reduce_q(accN);
+            if (q == 0) C::part(c.wc)[8 * j + g] = accN;
         }
     }
 #pragma unroll
-    for (int a = 0; a < C::A; ++a) {
-        const int j = C::WR * a + c.wr;
-        const double v = reduce_q(accN[a]);
-        if (q == 0 && j < T) C::part(c.wc)[8 * j + g] = v;
-    }
-#pragma unroll
-    for (int b = 0; b < C::B; ++b) {
-        const int i = C::WC * b + c.wc;
+    for (int b = 0; b < C::A; ++b) {
+        const int i = C::W * b + c.wc;
         const double v0 = reduce_g(accT[b].x), v1 = reduce_g(accT[b].y);
-        if (g == 0 && i < T) *reinterpret_cast<double2*>(C::part(C::WC + c.wr) + 8 * i + 2 * q) = make_double2(v0, v1);
+        if (g == 0 && i < T) sts2(C::part(C::W + c.wr) + 8 * i + 2 * q, make_double2(v0, v1));
     }
 }
 
-// Solve H u = bs with the register tiles Y = L^-T of factor_invert:  u = Y (Y^T bs).  Tile slot (a, b) holds
-// Y_ij (row block i, column block j).  On return u[t] = sum_{p < WR} part(WC + p)[t].
+// Solve H u = bs with the register tiles Y = L^-T of factor_invert:  u = Y (Y^T bs).  Slot (a, b) holds Y_ij
+// (row block i, column block j).  On return u[t] = sum_{p < W} part(W + p)[t].
 template <class C>
 __device__ __forceinline__ void solve_phase(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
     const int T = c.T, g = c.g, q = c.q;
     {   // t = Y^T bs: T part (reduce over g), partial per wc
-        double2 acc[C::A];
+        const double* bc = bs + 8 * c.wc + g;
+        double bg[C::A];
 #pragma unroll
-        for (int a = 0; a < C::A; ++a) acc[a] = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int b = 0; b < C::B; ++b) {
-            const int i = C::WC * b + c.wc;
-            if (i < T) {
-                const double bg = bs[8 * i + g];
-#pragma unroll
-                for (int a = 0; a < C::A; ++a) {
-                    if (b < C::bcount(a)) {
-                        const int j = C::WR * a + c.wr;
-                        if (j < T && i <= j) {
-                            acc[a].x = fma(S[C::sidx(a, b)].x, bg, acc[a].x);
-                            acc[a].y = fma(S[C::sidx(a, b)].y, bg, acc[a].y);
-                        }
-                    }
-                }
-            }
-        }
+        for (int b = 0; b < C::A; ++b) bg[b] = bc[b * (8 * C::W)];   // NV-padded: always in range
 #pragma unroll
         for (int a = 0; a < C::A; ++a) {
-            const int j = C::WR * a + c.wr;
-            const double v0 = reduce_g(acc[a].x), v1 = reduce_g(acc[a].y);
-            if (g == 0 && j < T) *reinterpret_cast<double2*>(C::part(c.wc) + 8 * j + 2 * q) = make_double2(v0, v1);
+            const int j = C::W * a + c.wr;
+            if (j < T) {
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {   // out-of-triangle diagonal slots hold zeros
+                    acc.x = fma(S[C::sidx(a, b)].x, bg[b], acc.x);
+                    acc.y = fma(S[C::sidx(a, b)].y, bg[b], acc.y);
+                }
+                const double v0 = reduce_g(acc.x), v1 = reduce_g(acc.y);
+                if (g == 0) sts2(C::part(c.wc) + 8 * j + 2 * q, make_double2(v0, v1));
+            }
         }
     }
     __syncthreads();
     {   // u = Y t: N part (reduce over q), partial per wr
-        double2 tv[C::A];
+        double acc[C::A];
+#pragma unroll
+        for (int b = 0; b < C::A; ++b) acc[b] = 0.0;
+        const double* tr = C::part(0) + 8 * c.wr + 2 * q;
 #pragma unroll
         for (int a = 0; a < C::A; ++a) {
-            const int j = C::WR * a + c.wr;
-            tv[a] = make_double2(0.0, 0.0);
+            const int j = C::W * a + c.wr;
             if (j < T) {
+                double2 tv = lds2(tr + a * (8 * C::W));
 #pragma unroll
-                for (int p = 0; p < C::WC; ++p) {
-                    const double2 t = *reinterpret_cast<const double2*>(C::part(p) + 8 * j + 2 * q);
-                    tv[a].x += t.x;
-                    tv[a].y += t.y;
+                for (int p = 1; p < C::W; ++p) {
+                    const double2 t = lds2(tr + p * C::NV + a * (8 * C::W));
+                    tv.x += t.x;
+                    tv.y += t.y;
+                }
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    acc[b] = fma(S[C::sidx(a, b)].x, tv.x, acc[b]);
+                    acc[b] = fma(S[C::sidx(a, b)].y, tv.y, acc[b]);
                 }
             }
         }
 #pragma unroll
-        for (int b = 0; b < C::B; ++b) {
-            const int i = C::WC * b + c.wc;
-            double acc = 0.0;
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) {
-                if (b < C::bcount(a)) {
-                    const int j = C::WR * a + c.wr;
-                    if (j < T && i <= j) {
-                        acc = fma(S[C::sidx(a, b)].x, tv[a].x, acc);
-                        acc = fma(S[C::sidx(a, b)].y, tv[a].y, acc);
-                    }
-                }
-            }
-            acc = reduce_q(acc);
-            if (q == 0 && i < T) C::part(C::WC + c.wr)[8 * i + g] = acc;
+        for (int b = 0; b < C::A; ++b) {
+            const int i = C::W * b + c.wc;
+            const double v = reduce_q(acc[b]);
+            if (q == 0 && i < T) C::part(C::W + c.wr)[8 * i + g] = v;
         }
     }
     __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Cholesky C_kk = L L^T by rows (lane r = lane % 8
-// owns row r; the four lane groups of 8 compute it redundantly) fused with Gauss-Jordan on the identity, each
-// group carrying two columns of W = L^-1.  Publishes -W (row-major) to `binv`; returns Y_kk = W^T in accumulator
-// layout.  false on breakdown (non-positive or non-finite pivot), uniformly over the warp.
+// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Gauss-Jordan on M = [C_kk | I] (8 x 16, row stride
+// 20 in shared memory): for each column cc, row cc is scaled by 1 / sqrt(pivot) and eliminated from the rows
+// below, which leaves [L^T | L^-1] (C_kk = L L^T).  Lane (g, q) owns M[g][q + 4u], u < 4.  A rolled loop: this
+// runs on one warp while its block waits, so it is kept small enough to stay in the instruction cache.
+// Publishes -L^-1 (row-major) to `binv`; returns Y_kk = L^-T in accumulator layout.  false on breakdown
+// (non-positive or non-finite pivot), uniformly over the warp.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool diag_factor(const double2 s, double* scr, double* binv, double2& ykk, int lane) {
-    const int g = lane >> 2, q = lane & 3, r = lane & 7, rep = lane >> 3;
-    const int grp = lane & 24;
-    *reinterpret_cast<double2*>(scr + g * 10 + 2 * q) = make_double2(-s.x, -s.y);
+__device__ __forceinline__ bool diag_factor(const double2 s, double* M, double* binv, double2& ykk, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    sts2(M + g * 20 + 2 * q, make_double2(-s.x, -s.y));
+    sts2(M + g * 20 + 8 + 2 * q, make_double2(g == 2 * q ? 1.0 : 0.0, g == 2 * q + 1 ? 1.0 : 0.0));
     __syncwarp();
-    double a[8];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const double2 t = *reinterpret_cast<const double2*>(scr + r * 10 + 2 * m);
-        a[2 * m] = t.x;
-        a[2 * m + 1] = t.y;
-    }
-    double dg = scr[r * 10 + r];
-    double w0 = (r == 2 * rep) ? 1.0 : 0.0, w1 = (r == 2 * rep + 1) ? 1.0 : 0.0;
     bool ok = true;
-#pragma unroll
+    double* mine = M + g * 20 + q;
+#pragma unroll 1
     for (int cc = 0; cc < 8; ++cc) {
-        const double piv = __shfl_sync(kFull, dg, grp | cc);
+        const double* rowc = M + cc * 20;
+        const double piv = rowc[cc];
         ok = ok && (piv > 0.0) && (piv < INFINITY);
         const double rinv = rsqrt(piv);
-        const double lc = a[cc] * rinv;  // l[r][cc] for r >= cc
-        dg = fma(-lc, lc, dg);
+        const double lr = M[g * 20 + cc] * rinv;
+        double rc[4], mv[4];
 #pragma unroll
-        for (int m = cc + 1; m < 8; ++m) {
-            const double lm = __shfl_sync(kFull, lc, grp | m);
-            a[m] = fma(-lc, lm, a[m]);
+        for (int u = 0; u < 4; ++u) { rc[u] = rowc[q + 4 * u] * rinv; mv[u] = mine[4 * u]; }
+        __syncwarp();  // row cc and column cc have been read by everyone
+        if (g == cc) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mine[4 * u] = rc[u];
+        } else if (g > cc) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mine[4 * u] = fma(-lr, rc[u], mv[u]);
         }
-        const double wc0 = __shfl_sync(kFull, w0 * rinv, grp | cc);
-        const double wc1 = __shfl_sync(kFull, w1 * rinv, grp | cc);
-        w0 = (r == cc) ? wc0 : ((r > cc) ? fma(-lc, wc0, w0) : w0);
-        w1 = (r == cc) ? wc1 : ((r > cc) ? fma(-lc, wc1, w1) : w1);
+        __syncwarp();
     }
-    *reinterpret_cast<double2*>(binv + r * 8 + 2 * rep) = make_double2(-w0, -w1);
-    __syncwarp();
-    ykk = make_double2(-binv[(2 * q) * 8 + g], -binv[(2 * q + 1) * 8 + g]);
+    const double2 wv = lds2(M + g * 20 + 8 + 2 * q);
+    sts2(binv + 2 * lane, make_double2(-wv.x, -wv.y));
+    ykk = make_double2(M[(2 * q) * 20 + 8 + g], M[(2 * q + 1) * 20 + 8 + g]);
     return ok;
 }
 
@@ -506,92 +488,105 @@ __device__ __forceinline__ bool diag_factor(const double2 s, double* scr, double
 template <class C>
 __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
     const int T = c.T, g = c.g, q = c.q, lane = c.lane;
-    const double* dsq = C::vec(C::DSQ);
-    HDRT_FOR_SLOTS(C, a, b) {
-        const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
-        double2 v = make_double2(0.0, 0.0);
-        if (j < T && i <= j) {
-            v = *reinterpret_cast<const double2*>(C::tile(j, i) + 2 * lane);
-            if (i == j) {
-                const double d = dsq[8 * j + g];
-                if (g == 2 * q) v.x -= d;
-                if (g == 2 * q + 1) v.y -= d;
+    constexpr int W = C::W;
+    {
+        const double* dsq = C::vec(C::DSQ);
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) {
+            const int j = W * a + c.wr;
+#pragma unroll
+            for (int b = 0; b <= a; ++b) S[C::sidx(a, b)] = make_double2(0.0, 0.0);
+            if (j < T) {
+                const double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * lane;
+#pragma unroll
+                for (int b = 0; b < a; ++b) S[C::sidx(a, b)] = lds2(trow + b * (W * 64));
+                if (c.dv) {
+                    double2 v = lds2(trow + a * (W * 64));
+                    if (c.wc == c.wr) {
+                        const double d = dsq[8 * j + g];
+                        if (g == 2 * q) v.x -= d;
+                        if (g == 2 * q + 1) v.y -= d;
+                    }
+                    S[C::sidx(a, a)] = v;
+                }
             }
         }
-        S[C::sidx(a, b)] = v;
     }
+    double* panr = C::pan() + 64 * c.wr + 2 * lane;   // tile j = W a + wr: + 64 W a
+    double* panc = C::pan() + 64 * c.wc + 2 * lane;
+    double* trs = C::tr(threadIdx.x >> 5);
 #pragma unroll 1
     for (int k = 0; k < T; ++k) {
-        if ((k % C::WR) == c.wr && (k % C::WC) == c.wc) {  // owner of the diagonal tile
+        const int kw = k % W, kd = k / W;
+        const bool diag_owner = (kw == c.wr) && (kw == c.wc);
+        if (diag_owner) {
             double2 sk = make_double2(0.0, 0.0);
-            HDRT_FOR_SLOTS(C, a, b) {
-                if (C::WR * a + c.wr == k && C::WC * b + c.wc == k) sk = S[C::sidx(a, b)];
-            }
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) if (a == kd) sk = S[C::sidx(a, a)];
             double2 ykk;
             const bool ok = diag_factor(sk, C::scr(), C::binv(), ykk, lane);
-            HDRT_FOR_SLOTS(C, a, b) {
-                if (C::WR * a + c.wr == k && C::WC * b + c.wc == k) S[C::sidx(a, b)] = ykk;
-            }
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) if (a == kd) S[C::sidx(a, a)] = ykk;
             if (lane == 0) *c.flag = ok ? 1 : 0;
         }
         __syncthreads();  // (A) -L_kk^-1 published
         if (*c.flag == 0) return false;
-        const double2 bn = *reinterpret_cast<const double2*>(C::binv() + 2 * lane);
-        // finalise column k of the combined matrix [Y above the diagonal; L below] and publish it
-        HDRT_FOR_SLOTS(C, a, b) {
-            const int j = C::WR * a + c.wr, i = C::WC * b + c.wc;
-            if (j < T && i <= j) {
-                if (i == k && j > k) {         // L_jk = C_jk L_kk^-T; the slot restarts as the accumulator of -Y_kj
-                    double2 r2 = make_double2(0.0, 0.0);
-                    tile_mma(r2, S[C::sidx(a, b)], bn);
-                    *reinterpret_cast<double2*>(C::pan(j) + 2 * lane) = r2;
-                    S[C::sidx(a, b)] = make_double2(0.0, 0.0);
-                } else if (j == k && i < k) {  // Y_ik = (accumulated) L_kk^-T, final
-                    double2 r2 = make_double2(0.0, 0.0);
-                    tile_mma(r2, S[C::sidx(a, b)], bn);
-                    *reinterpret_cast<double2*>(C::pan(i) + 2 * lane) = r2;
-                    S[C::sidx(a, b)] = r2;
-                } else if (j == k && i == k) {
-                    *reinterpret_cast<double2*>(C::pan(k) + 2 * lane) = S[C::sidx(a, b)];
-                }
-            }
+        const double2 bn = lds2(C::binv() + 2 * lane);
+        if (diag_owner) {
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) if (a == kd) sts2(panr + a * (W * 64), S[C::sidx(a, a)]);
         }
-        __syncthreads();  // (B) column k published
-        if (k + 1 < T) {
-            double2 Fa[C::A];
+        if (kw == c.wc) {  // column k: L_jk = C_jk L_kk^-T for j > k; the slot restarts from zero
 #pragma unroll
-            for (int a = 0; a < C::A; ++a) {
-                const int j = C::WR * a + c.wr;
-                Fa[a] = make_double2(0.0, 0.0);
-                if (j < T && j > k) Fa[a] = *reinterpret_cast<const double2*>(C::pan(j) + 2 * lane);
-            }
+            for (int b = 0; b < C::A; ++b) {
+                if (b == kd) {
 #pragma unroll
-            for (int b = 0; b < C::B; ++b) {
-                const int i = C::WC * b + c.wc;
-                if (i < T) {
-                    const double2 Fb = *reinterpret_cast<const double2*>(C::pan(i) + 2 * lane);
-                    if (i <= k) {
-#pragma unroll
-                        for (int a = 0; a < C::A; ++a) {
-                            if (b < C::bcount(a)) {
-                                const int j = C::WR * a + c.wr;
-                                if (j < T && j > k && i <= j) tile_mma(S[C::sidx(a, b)], Fb, Fa[a]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < C::A; ++a) {
-                            if (b < C::bcount(a)) {
-                                const int j = C::WR * a + c.wr;
-                                if (j < T && j > k && i <= j) tile_mma(S[C::sidx(a, b)], Fa[a], Fb);
-                            }
+                    for (int a = b; a < C::A; ++a) {
+                        const int j = W * a + c.wr;
+                        if (j < T && (a > b || c.wr > c.wc)) {
+                            double2 r2 = make_double2(0.0, 0.0);
+                            tile_mma(r2, S[C::sidx(a, b)], bn);
+                            sts2(panr + a * (W * 64), r2);
+                            S[C::sidx(a, b)] = make_double2(0.0, 0.0);
                         }
                     }
                 }
             }
         }
+        if (kw == c.wr) {  // row k: (L^-T)_ik = tile^T L_kk^-T for i < k, final
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) {
+                if (a == kd) {
+#pragma unroll
+                    for (int b = 0; b <= a; ++b) {
+                        if (b < a || c.wc < c.wr) {
+                            sts2(trs + g * 10 + 2 * q, S[C::sidx(a, b)]);
+                            __syncwarp();
+                            const double2 tt = make_double2(trs[(2 * q) * 10 + g], trs[(2 * q + 1) * 10 + g]);
+                            __syncwarp();
+                            double2 r2 = make_double2(0.0, 0.0);
+                            tile_mma(r2, tt, bn);
+                            sts2(panc + b * (W * 64), r2);
+                            S[C::sidx(a, b)] = r2;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // (B) column k published
+        if (k + 1 < T) {
+#pragma unroll
+            for (int a = 0; a < C::A; ++a) {
+                const int j = W * a + c.wr;
+                if (j > k && j < T) {
+                    const double2 Fa = lds2(panr + a * (W * 64));
+#pragma unroll
+                    for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(panc + b * (W * 64)));
+                    if (c.dv) tile_mma(S[C::sidx(a, a)], Fa, lds2(panc + a * (W * 64)));
+                }
+            }
+        }
     }
-    (void)g; (void)q;
     return true;
 }
 
@@ -688,7 +683,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             if (act) bs[tid] = -qi - hi;
             __syncthreads();
             solve_phase<C>(c, S, bs);
-            xi = act ? sum_parts<C>(C::WC, C::WR, tid) : 0.0;
+            xi = act ? sum_parts<C>(C::W, C::W, tid) : 0.0;
             zi = -xi - hi;
             si = -zi;
             double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
@@ -716,7 +711,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
             if (act) bs[tid] = dxi - dinv * zs;
             __syncthreads();
             solve_phase<C>(c, S, bs);
-            dxi = act ? sum_parts<C>(C::WC, C::WR, tid) : 0.0;
+            dxi = act ? sum_parts<C>(C::W, C::W, tid) : 0.0;
             dzi = -dinv * dxi - zs;
             dsi = dsi - dzi;
             const double prod = dsi * dzi;
@@ -1114,11 +1109,13 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     c.T = (p.n_cols + 7) >> 3;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2; c.q = c.lane & 3;
-    c.wr = (threadIdx.x >> 5) / C::WC; c.wc = (threadIdx.x >> 5) % C::WC;
+    c.wr = (threadIdx.x >> 5) / C::W; c.wc = (threadIdx.x >> 5) % C::W;
+    c.dv = c.wc <= c.wr;
     c.flag = &s_flag;
-    const int npad = (p.n_rows + 1) & ~1;
+    const int npad = rows_pad(p.n_rows);
     c.w = g_smem + C::oRows;
     c.r2 = c.w + npad;
+    c.aux = c.r2 + npad;
     c.red_phase = 0;
     // zero the whole vector area once: padding entries (index >= n) of the column buffers must read as zero
     for (int i = threadIdx.x; i < kNumVec * C::NV; i += C::kThreads) g_smem[i] = 0.0;
