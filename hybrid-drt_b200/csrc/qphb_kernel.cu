@@ -28,6 +28,8 @@
 // and one more N-vector.  The Gram staging buffers alias the pan / partial area.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hdrt {
@@ -44,6 +46,23 @@ constexpr int kMaxIpm = 100;
 constexpr double kStep = 0.99;
 
 extern __shared__ __align__(16) double g_smem[];
+
+// Development aid (-DHDRT_PROFILE): per-phase clock64 totals of warp 0 of block 0, read back with hdrt_debug_profile.
+#ifdef HDRT_PROFILE
+__device__ unsigned long long g_prof[32];
+__shared__ unsigned long long s_prof[32];
+#define PROF_DECL long long _pt = clock64()
+#define PROF_ADD(slot)                                                        \
+    do {                                                                       \
+        if (threadIdx.x == 0) s_prof[slot] += (unsigned long long)(clock64() - _pt); \
+        _pt = clock64();                                                       \
+    } while (0)
+#define PROF_COUNT(slot) do { if (threadIdx.x == 0) s_prof[slot] += 1; } while (0)
+#else
+#define PROF_DECL
+#define PROF_ADD(slot)
+#define PROF_COUNT(slot)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // compile-time configuration: tile grid, register slots, shared-memory offsets (in doubles)
@@ -123,6 +142,16 @@ __device__ __forceinline__ void tile_mma(double2& d, const double2& x, const dou
         : "+d"(d.x), "+d"(d.y) : "d"(x.x), "d"(z.x));
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d.x), "+d"(d.y) : "d"(x.y), "d"(z.y));
+}
+
+// 1 / sqrt(x) for a positive finite x: hardware approximation (2^-22) + two Newton steps
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    y = fma(y, fma(-hx * y, y, 0.5), y);
+    return y;
 }
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -226,11 +255,12 @@ __device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
 }
 
 template <class C>
-__device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scalar, double l1_value, double* p_out,
+__device__ __noinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scalar, double l1_value, double* p_out,
                                            double* q_out) {
     const int tid = threadIdx.x;
     const int n = c.n, N = c.N, T = c.T;
     const int g = c.g, q = c.q, lane = c.lane;
+    PROF_DECL;
     double* w2 = c.r2;      // w^2, zero padded to a multiple of 8
     double* w2rv = c.aux;   // w^2 rv
     __syncthreads();        // previous users of the union area and of r2 are done
@@ -285,35 +315,42 @@ __device__ __forceinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_s
         __syncthreads();  // the buffer is free for the chunk after next
         buf ^= 1;
     }
-    // add the penalty, write -P tiles (padding rows / columns: identity) and the optional dense copy
+    PROF_ADD(5);
+    // -Gram tiles to shared memory, then one rolled pass over the lower-triangle tiles adds the penalty, sets the
+    // padding rows / columns to the identity and writes the optional dense copy
 #pragma unroll
     for (int a = 0; a < C::A; ++a) {
         const int j = C::W * a + c.wr;
         if (j < T) {
+            double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * lane;
 #pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const int i = C::W * b + c.wc;
-                if (b < a || c.dv) {
-                    const int r = 8 * j + g, c0 = 8 * i + 2 * q;
-                    double v[2] = {S[C::sidx(a, b)].x, S[C::sidx(a, b)].y};
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = c0 + e;
-                        if (r < n && cc < n) {
-                            v[e] += l2_entry<C>(c, f, r, cc);
-                            if (p_out && cc <= r) {
-                                p_out[(size_t)r * n + cc] = v[e];
-                                p_out[(size_t)cc * n + r] = v[e];
-                            }
-                        } else {
-                            v[e] = (r == cc) ? 1.0 : 0.0;
-                        }
-                    }
-                    sts2(C::tiles() + (j * (j + 1) / 2 + i) * 64 + 2 * lane, make_double2(-v[0], -v[1]));
-                }
-            }
+            for (int b = 0; b < a; ++b)
+                sts2(trow + b * (C::W * 64), make_double2(-S[C::sidx(a, b)].x, -S[C::sidx(a, b)].y));
+            if (c.dv) sts2(trow + a * (C::W * 64), make_double2(-S[C::sidx(a, a)].x, -S[C::sidx(a, a)].y));
         }
     }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = tid >> 5; r < 8 * T; r += C::kWarps) {
+        const int j = r >> 3;
+        double* trow = C::tiles() + (j * (j + 1) / 2) * 64 + (r & 7) * 8;
+#pragma unroll 1
+        for (int cc = lane; cc < 8 * (j + 1); cc += 32) {
+            double* e = trow + (cc >> 3) * 64 + (cc & 7);
+            double v;
+            if (r < n && cc < n) {
+                v = l2_entry<C>(c, f, r, cc) - *e;
+                if (p_out && cc <= r) {
+                    p_out[(size_t)r * n + cc] = v;
+                    p_out[(size_t)cc * n + r] = v;
+                }
+            } else {
+                v = (r == cc) ? 1.0 : 0.0;
+            }
+            *e = -v;
+        }
+    }
+    PROF_ADD(6);
 #pragma unroll
     for (int u = 0; u < QU; ++u) {
         const int col = (tid + C::kThreads * u) >> 2;
@@ -441,43 +478,53 @@ __device__ __forceinline__ void solve_phase(const Ctx& c, const double2 (&S)[C::
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Gauss-Jordan on M = [C_kk | I] (8 x 16, row stride
-// 20 in shared memory): for each column cc, row cc is scaled by 1 / sqrt(pivot) and eliminated from the rows
-// below, which leaves [L^T | L^-1] (C_kk = L L^T).  Lane (g, q) owns M[g][q + 4u], u < 4.  A rolled loop: this
-// runs on one warp while its block waits, so it is kept small enough to stay in the instruction cache.
-// Publishes -L^-1 (row-major) to `binv`; returns Y_kk = L^-T in accumulator layout.  false on breakdown
-// (non-positive or non-finite pivot), uniformly over the warp.
+// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Gaussian elimination on M = [C_kk | I] (8 x 16)
+// without row scaling: row g ends as [d_g Lt_g | Lt^-1_g] of C_kk = Lt D Lt^T (Lt unit lower); scaling row g by
+// d_g^-1/2 afterwards gives [L^T | L^-1] of the Cholesky factor.  Lane (g, q) keeps M[g][2q], M[g][2q + 1],
+// M[g][8 + 2q], M[g][9 + 2q] in registers -- the accumulator layout of both halves; row cc, its pivot and the
+// column-cc element of the own row travel by shuffles.  This runs on one warp while its block waits, and a lone
+// warp issues an instruction only every few cycles: the loop is rolled (it must stay in the instruction cache)
+// and carries as few instructions as possible (one reciprocal, one multiply, four FMAs, six shuffles).
+// Publishes -L^-1 (row-major = accumulator layout) to `binv`; returns Y_kk = L^-T in accumulator layout.  false
+// on breakdown (non-positive or non-finite pivot), uniformly over the warp.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool diag_factor(const double2 s, double* M, double* binv, double2& ykk, int lane) {
+__device__ __forceinline__ double fast_rcp(double x) {   // 1 / x, x positive and finite: 2^-22 seed + 2 Newton
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
+__device__ __forceinline__ bool diag_factor(const double2 s, double* binv, double2& ykk, int lane) {
     const int g = lane >> 2, q = lane & 3;
-    sts2(M + g * 20 + 2 * q, make_double2(-s.x, -s.y));
-    sts2(M + g * 20 + 8 + 2 * q, make_double2(g == 2 * q ? 1.0 : 0.0, g == 2 * q + 1 ? 1.0 : 0.0));
-    __syncwarp();
-    bool ok = true;
-    double* mine = M + g * 20 + q;
+    double m0 = -s.x, m1 = -s.y;
+    double m2 = (g == 2 * q) ? 1.0 : 0.0, m3 = (g == 2 * q + 1) ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int cc = 0; cc < 8; ++cc) {
-        const double* rowc = M + cc * 20;
-        const double piv = rowc[cc];
-        ok = ok && (piv > 0.0) && (piv < INFINITY);
-        const double rinv = rsqrt(piv);
-        const double lr = M[g * 20 + cc] * rinv;
-        double rc[4], mv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { rc[u] = rowc[q + 4 * u] * rinv; mv[u] = mine[4 * u]; }
-        __syncwarp();  // row cc and column cc have been read by everyone
-        if (g == cc) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) mine[4 * u] = rc[u];
-        } else if (g > cc) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) mine[4 * u] = fma(-lr, rc[u], mv[u]);
-        }
-        __syncwarp();
+    for (int cc = 0; cc < 7; ++cc) {
+        const int h = cc >> 1;
+        const double colv = (cc & 1) ? m1 : m0;                      // column cc of the own row, where q == h
+        const double agc = __shfl_sync(kFull, colv, 4 * g + h);      // M[g][cc]
+        const double piv = __shfl_sync(kFull, colv, 4 * cc + h);     // M[cc][cc]
+        const int src = 4 * cc + q;                                  // row cc
+        const double r0 = __shfl_sync(kFull, m0, src), r1 = __shfl_sync(kFull, m1, src);
+        const double r2 = __shfl_sync(kFull, m2, src), r3 = __shfl_sync(kFull, m3, src);
+        const double f = (g > cc) ? -agc * fast_rcp(piv) : 0.0;
+        m0 = fma(f, r0, m0);
+        m1 = fma(f, r1, m1);
+        m2 = fma(f, r2, m2);
+        m3 = fma(f, r3, m3);
     }
-    const double2 wv = lds2(M + g * 20 + 8 + 2 * q);
-    sts2(binv + 2 * lane, make_double2(-wv.x, -wv.y));
-    ykk = make_double2(M[(2 * q) * 20 + 8 + g], M[(2 * q + 1) * 20 + 8 + g]);
+    const double dg = __shfl_sync(kFull, (g & 1) ? m1 : m0, 4 * g + (g >> 1));   // d_g = M[g][g]
+    const bool ok = __all_sync(kFull, (dg > 0.0) && (dg < INFINITY));
+    const double rinv = fast_rsqrt(dg);
+    m2 *= rinv;
+    m3 *= rinv;
+    sts2(binv + 2 * lane, make_double2(-m2, -m3));
+    const int sx = 8 * q + (g >> 1);   // lane (2q, g / 2); lane (2q + 1, g / 2) is + 4
+    const double a2 = __shfl_sync(kFull, m2, sx), a3 = __shfl_sync(kFull, m3, sx);
+    const double b2 = __shfl_sync(kFull, m2, sx + 4), b3 = __shfl_sync(kFull, m3, sx + 4);
+    ykk = make_double2((g & 1) ? a3 : a2, (g & 1) ? b3 : b2);
     return ok;
 }
 
@@ -489,6 +536,7 @@ template <class C>
 __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
     const int T = c.T, g = c.g, q = c.q, lane = c.lane;
     constexpr int W = C::W;
+    PROF_DECL;
     {
         const double* dsq = C::vec(C::DSQ);
 #pragma unroll
@@ -515,21 +563,21 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
     double* panr = C::pan() + 64 * c.wr + 2 * lane;   // tile j = W a + wr: + 64 W a
     double* panc = C::pan() + 64 * c.wc + 2 * lane;
     double* trs = C::tr(threadIdx.x >> 5);
+    PROF_ADD(16);
+    // the diagonal tile of column 0
+    if (c.wr == 0 && c.wc == 0) {
+        double2 ykk;
+        const bool ok = diag_factor(S[0], C::binv(), ykk, lane);
+        S[0] = ykk;
+        if (lane == 0) *c.flag = ok ? 1 : 0;
+    }
 #pragma unroll 1
     for (int k = 0; k < T; ++k) {
         const int kw = k % W, kd = k / W;
         const bool diag_owner = (kw == c.wr) && (kw == c.wc);
-        if (diag_owner) {
-            double2 sk = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) if (a == kd) sk = S[C::sidx(a, a)];
-            double2 ykk;
-            const bool ok = diag_factor(sk, C::scr(), C::binv(), ykk, lane);
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) if (a == kd) S[C::sidx(a, a)] = ykk;
-            if (lane == 0) *c.flag = ok ? 1 : 0;
-        }
+        PROF_ADD(17);
         __syncthreads();  // (A) -L_kk^-1 published
+        PROF_ADD(18);
         if (*c.flag == 0) return false;
         const double2 bn = lds2(C::binv() + 2 * lane);
         if (diag_owner) {
@@ -553,19 +601,27 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                 }
             }
         }
-        if (kw == c.wr) {  // row k: (L^-T)_ik = tile^T L_kk^-T for i < k, final
+        if (kw == c.wr) {  // row k: (L^-T)_ik = tile^T L_kk^-T for i < k, final.  The transposes go through the
+                           // tiles' own pan slots (free until barrier B): dump all, read back transposed, multiply.
+            const double* pant = C::pan() + 64 * c.wc + g;
 #pragma unroll
             for (int a = 0; a < C::A; ++a) {
                 if (a == kd) {
+                    const bool dlow = c.wc < c.wr;   // slot (a, a) is left of the diagonal tile
+#pragma unroll
+                    for (int b = 0; b < a; ++b) sts2(panc + b * (W * 64), S[C::sidx(a, b)]);
+                    if (dlow) sts2(panc + a * (W * 64), S[C::sidx(a, a)]);
+                    __syncwarp();
+                    double2 tt[C::A];
+#pragma unroll
+                    for (int b = 0; b <= a; ++b)
+                        tt[b] = make_double2(pant[b * (W * 64) + (2 * q) * 8], pant[b * (W * 64) + (2 * q + 1) * 8]);
+                    __syncwarp();
 #pragma unroll
                     for (int b = 0; b <= a; ++b) {
-                        if (b < a || c.wc < c.wr) {
-                            sts2(trs + g * 10 + 2 * q, S[C::sidx(a, b)]);
-                            __syncwarp();
-                            const double2 tt = make_double2(trs[(2 * q) * 10 + g], trs[(2 * q + 1) * 10 + g]);
-                            __syncwarp();
+                        if (b < a || dlow) {
                             double2 r2 = make_double2(0.0, 0.0);
-                            tile_mma(r2, tt, bn);
+                            tile_mma(r2, tt[b], bn);
                             sts2(panc + b * (W * 64), r2);
                             S[C::sidx(a, b)] = r2;
                         }
@@ -573,8 +629,30 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                 }
             }
         }
+        PROF_ADD(19);
         __syncthreads();  // (B) column k published
+        PROF_ADD(20);
         if (k + 1 < T) {
+            // look-ahead: the owner of the next diagonal tile updates and factorises it before anything else
+            const int k1w = (k + 1) % W, k1d = (k + 1) / W;
+            const bool next_owner = (k1w == c.wr) && (k1w == c.wc);
+            if (next_owner) {
+                double2 sk = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int a = 0; a < C::A; ++a) {
+                    if (a == k1d) {
+                        tile_mma(S[C::sidx(a, a)], lds2(panr + a * (W * 64)), lds2(panc + a * (W * 64)));
+                        sk = S[C::sidx(a, a)];
+                    }
+                }
+                double2 ykk;
+                const bool ok = diag_factor(sk, C::binv(), ykk, lane);
+                PROF_COUNT(24);
+#pragma unroll
+                for (int a = 0; a < C::A; ++a) if (a == k1d) S[C::sidx(a, a)] = ykk;
+                if (lane == 0) *c.flag = ok ? 1 : 0;
+            }
+            PROF_ADD(17);
 #pragma unroll
             for (int a = 0; a < C::A; ++a) {
                 const int j = W * a + c.wr;
@@ -582,9 +660,10 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                     const double2 Fa = lds2(panr + a * (W * 64));
 #pragma unroll
                     for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(panc + b * (W * 64)));
-                    if (c.dv) tile_mma(S[C::sidx(a, a)], Fa, lds2(panc + a * (W * 64)));
+                    if (c.dv && !(next_owner && a == k1d)) tile_mma(S[C::sidx(a, a)], Fa, lds2(panc + a * (W * 64)));
                 }
             }
+            PROF_ADD(21);
         }
     }
     return true;
@@ -612,7 +691,7 @@ __device__ __forceinline__ double sum_parts(int first, int count, int t) {
 }
 
 template <class C>
-__device__ __forceinline__ QpOut qp_phase(Ctx& c) {
+__device__ __noinline__ QpOut qp_phase(Ctx& c) {
     const int tid = threadIdx.x;
     const int n = c.n;
     const bool act = tid < n;
@@ -631,6 +710,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
         resz0 = fmax(1.0, sqrt(t2[1]));
     }
     double2 S[C::NSLOT];
+    PROF_DECL;
     double xi = 0.0, si = 1.0, zi = 1.0, di = 1.0, dinv = 1.0, lam = 1.0;
     double rxi = 0.0, rzi = 0.0, gap = 0.0, pcost = 0.0;
     int iters;
@@ -673,7 +753,10 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
         }
         if (act) C::vec(C::DSQ)[tid] = dinv * dinv;
         __syncthreads();
-        if (!factor_invert<C>(c, S)) {
+        PROF_ADD(8);
+        const bool fact_ok = factor_invert<C>(c, S);
+        PROF_ADD(9);
+        if (!fact_ok) {
             out.status |= HDRT_ST_KKT_FAIL;
             if (iters <= 0) { out.fatal = true; xi = nan(""); }
             break;
@@ -729,6 +812,7 @@ __device__ __forceinline__ QpOut qp_phase(Ctx& c) {
                 sigma = sg * sg * sg;
             }
         }
+        PROF_ADD(10);
         xi += step * dxi;
         dsi = step * dsi + 1.0;
         dzi = step * dzi + 1.0;
@@ -755,7 +839,7 @@ struct BlockHyp {
 };
 
 template <class C>
-__device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, int len, double* rho, double* xmx,
+__device__ __noinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, int len, double* rho, double* xmx,
                                             bool first_iter) {
     const int tid = threadIdx.x;
     const int n = c.n, nn = c.n * c.n;
@@ -763,6 +847,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
     const int gi = start + tid;
     const double* xs = C::vec(C::XS);
     double* xh = C::vec(C::XH);
+    PROF_DECL;
     const double xi = act ? xs[gi] : 0.0;
     if (act) {
         const double ax = fabs(xi);
@@ -774,6 +859,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
     if (act) {
         const double inv2s0 = 1.0 / (2.0 * hp.sigma[0] * hp.sigma[0]);
         const double* __restrict__ pcol = c.pen + (start * n + gi);  // symmetric: read column-wise (coalesced)
+#pragma unroll 1
         for (int j = 0; j < len; ++j) {
             const int gj = start + j;
             const double xj = xs[gj];
@@ -792,6 +878,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
             }
         }
     }
+    PROF_ADD(13);
     block_reduce<C, 3, 0x7u>(mx, c);
     if (act) {
 #pragma unroll
@@ -822,6 +909,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
     double tr[3] = {0, 0, 0}, tx[3] = {0, 0, 0};
     if (act) {
         const double* __restrict__ pcol = c.pen + (start * n + gi);
+#pragma unroll 1
         for (int j = 0; j < len; ++j) {
             const int gj = start + j;
             const double xj = xs[gj];
@@ -833,6 +921,7 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
             }
         }
     }
+    PROF_ADD(14);
     double t6[6];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -857,35 +946,50 @@ __device__ __forceinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int star
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double var_floor, bool update_vz) {
+__device__ __noinline__ void weights_phase(Ctx& c, const double* est, double var_floor, bool update_vz) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, n = c.n, nc = c.nc;
     const double* xs = C::vec(C::XS);
-    for (int r = warp; r < N; r += C::kWarps) {
-        double acc = 0.0, accv = 0.0;
-        const double* __restrict__ src = c.rm + (size_t)r * n;
-        for (int col = lane; col < n; col += 32) {
-            const double xv = xs[col];
-            if (col == c.vz) {
-                acc += c.vzcol[r] * xv;
-            } else {
-                const double t = src[col] * xv;
-                acc += t;
-                if (col < c.vb_a || col >= c.vb_b) accv += t;
+    PROF_DECL;
+    // residuals: one warp per row
+    constexpr int RU = 1, CU = (C::NV + 31) / 32;
+    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+        double acc[RU], accv[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = rb + u * C::kWarps;
+            acc[u] = 0.0;
+            accv[u] = 0.0;
+            if (r < N) {
+                const double* __restrict__ src = c.rm + (size_t)r * n;
+#pragma unroll
+                for (int v = 0; v < CU; ++v) {
+                    const int col = lane + 32 * v;
+                    if (col < n) {
+                        const double t = ((col == c.vz) ? c.vzcol[r] : src[col]) * xs[col];
+                        acc[u] += t;
+                        if (col != c.vz && (col < c.vb_a || col >= c.vb_b)) accv[u] += t;
+                    }
+                }
             }
         }
-        acc = warp_sum(acc);
-        accv = warp_sum(accv);
-        if (lane == 0) {
-            const double resid = acc - c.rv[r];
-            c.r2[r] = resid * resid;
-            if (update_vz) {
-                const double sep = (r < nc) ? accv : -accv;
-                c.vzcol[r] = sep * c.vz_strength[r];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = rb + u * C::kWarps;
+            const double a = warp_sum(acc[u]);
+            const double av = update_vz ? warp_sum(accv[u]) : 0.0;
+            if (lane == 0 && r < N) {
+                const double resid = a - c.rv[r];
+                c.r2[r] = resid * resid;
+                if (update_vz) {
+                    const double sep = (r < nc) ? av : -av;
+                    c.vzcol[r] = sep * c.vz_strength[r];
+                }
             }
         }
     }
     __syncthreads();
+    PROF_ADD(11);
     double chrono_mean = 0.0;
     if (nc > 0 && c.vmm_chrono == nullptr) {
         double t1[1] = {0.0};
@@ -893,35 +997,47 @@ __device__ __forceinline__ void weights_phase(Ctx& c, const double* est, double 
         block_reduce<C, 1, 0u>(t1, c);
         chrono_mean = t1[0] / (double)nc;
     }
-    for (int r = warp; r < N; r += C::kWarps) {
-        double s_hat;
-        if (r < nc) {
-            if (c.vmm_chrono == nullptr) {
-                s_hat = chrono_mean;
-            } else {
-                double acc = 0.0;
-                for (int col = lane; col < nc; col += 32) acc += c.vmm_chrono[(size_t)r * nc + col] * c.r2[col];
-                s_hat = warp_sum(acc);
-            }
-        } else {
-            const int ne = N - nc;
+    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+        double sh[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = rb + u * C::kWarps;
             double acc = 0.0;
-            const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
-            for (int col = lane; col < ne; col += 32) acc += vr[col] * c.r2[nc + col];
-            s_hat = warp_sum(acc);
-        }
-        if (lane == 0) {
-            if (s_hat < var_floor) s_hat = var_floor;
-            double w = 1.0 / sqrt(s_hat);
-            if (est != nullptr) {
-                const double e = est[r];
-                const double frac = w / (w + e);
-                w = frac * w + (1.0 - frac) * e;
+            if (r < N) {
+                if (r < nc) {
+                    if (c.vmm_chrono != nullptr) {
+                        const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
+#pragma unroll 1
+                        for (int col = lane; col < nc; col += 32) acc += vr[col] * c.r2[col];
+                    }
+                } else {
+                    const int ne = N - nc;
+                    const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
+#pragma unroll 1
+                    for (int col = lane; col < ne; col += 32) acc += vr[col] * c.r2[nc + col];
+                }
             }
-            c.w[r] = fmax(w, 1e-10);
+            sh[u] = acc;
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = rb + u * C::kWarps;
+            double s_hat = warp_sum(sh[u]);
+            if (r < nc && c.vmm_chrono == nullptr) s_hat = chrono_mean;
+            if (lane == 0 && r < N) {
+                if (s_hat < var_floor) s_hat = var_floor;
+                double w = 1.0 / sqrt(s_hat);
+                if (est != nullptr) {
+                    const double e = est[r];
+                    const double frac = w / (w + e);
+                    w = frac * w + (1.0 - frac) * e;
+                }
+                c.w[r] = fmax(w, 1e-10);
+            }
         }
     }
     __syncthreads();
+    PROF_ADD(12);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -978,6 +1094,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     hp.use_gmat = false;
 
     int status = 0, n_ipm = 0;
+    PROF_DECL;
     L2Factors f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) f.use[k] = hy.derivative_weights[k] > 0.0;
@@ -1013,11 +1130,14 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             }
         }
         __syncthreads();
+        PROF_ADD(0);
         gram_phase<C>(c, f, init, hy.iw_l1_lambda_0, final_pq ? p.p_matrix + (size_t)b * n * n : nullptr,
                         (final_pq && p.q_vector) ? p.q_vector + (size_t)b * n : nullptr);
         if (final_pq) break;
 
+        PROF_ADD(1);
         QpOut qo = qp_phase<C>(c);
+        PROF_ADD(2);
         status |= qo.status;
         n_ipm += qo.iters;
         if (qo.fatal) { fatal = true; xi = qo.xi; break; }
@@ -1026,6 +1146,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (init) {
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
             weights_phase<C>(c, nullptr, var_floor, false);
+            PROF_ADD(4);
             for (int r = tid; r < N; r += C::kThreads) {
                 const double e = c.w[r];
                 est_g[r] = e;
@@ -1047,7 +1168,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         fun = qo.pcost;
         hyper_block<C>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
         if (c.dop_a >= 0) hyper_block<C>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
+        PROF_ADD(3);
         weights_phase<C>(c, est_g, var_floor, c.vz >= 0);
+        PROF_ADD(4);
         {   // convergence, qphb.py:597-603,969-970
             const bool act = tid < n;
             const double dx = xi - x_in;
@@ -1109,7 +1232,10 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     c.T = (p.n_cols + 7) >> 3;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2; c.q = c.lane & 3;
-    c.wr = (threadIdx.x >> 5) / C::W; c.wc = (threadIdx.x >> 5) % C::W;
+    // tile-grid role of this warp, rotated per block so that the heavy roles (diagonal owners) of the blocks
+    // sharing an SM land on different warp schedulers
+    const int role = ((threadIdx.x >> 5) + blockIdx.x % 3) % C::kWarps;
+    c.wr = role / C::W; c.wc = role % C::W;
     c.dv = c.wc <= c.wr;
     c.flag = &s_flag;
     const int npad = rows_pad(p.n_rows);
@@ -1117,6 +1243,9 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     c.r2 = c.w + npad;
     c.aux = c.r2 + npad;
     c.red_phase = 0;
+#ifdef HDRT_PROFILE
+    if (threadIdx.x < 32) s_prof[threadIdx.x] = 0;
+#endif
     // zero the whole vector area once: padding entries (index >= n) of the column buffers must read as zero
     for (int i = threadIdx.x; i < kNumVec * C::NV; i += C::kThreads) g_smem[i] = 0.0;
     __syncthreads();
@@ -1128,7 +1257,12 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
         __syncthreads();
         if (b >= p.batch) break;
         fit_one<C>(p, b, c);
+        PROF_COUNT(25);
     }
+#ifdef HDRT_PROFILE
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 32) g_prof[threadIdx.x] += s_prof[threadIdx.x];
+#endif
 }
 
 __global__ void fp64_probe_kernel(double* out, int iters) {
@@ -1158,6 +1292,7 @@ static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, 
     int occ = 0;
     HDRT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qphb_kernel<C>, C::kThreads, smem));
     if (occ < 1) { set_error("kernel cannot be resident (smem %zu)", smem); return HDRT_ERR_UNSUPPORTED; }
+    if (const char* e = getenv("HDRT_DEBUG_OCC")) { const int cap = atoi(e); if (cap > 0 && cap < occ) occ = cap; }  // dev knob
     int grid = h->sm_count * occ;
     if (grid > p.batch) grid = p.batch;
     HDRT_CUDA_CHECK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
@@ -1190,6 +1325,14 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (small_cfg(p.n_cols)) return launch_qphb<CfgS>(h, p, (size_t)smem, st);
     return launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }
+
+#ifdef HDRT_PROFILE
+extern "C" int hdrt_debug_profile(unsigned long long* out32, int reset) {
+    if (out32) cudaMemcpyFromSymbol(out32, g_prof, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host) {
     if (!h || !tflops_host) { set_error("null argument"); return HDRT_ERR_ARG; }

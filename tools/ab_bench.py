@@ -1,0 +1,39 @@
+"""Development aid: A/B the resident-input QPHB throughput of several builds of the library in one process.
+usage: python tools/ab_bench.py libA.so libB.so ...  (paths relative to hybrid-drt_b200/_lib)"""
+import ctypes as C
+import os
+import sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from hybdrt_b200 import engine as E, synth  # noqa: E402
+from hybdrt_b200.models import DRT  # noqa: E402
+B = 10000
+freq, z = synth.make_eis_batch(B, seed=0)
+libs = sys.argv[1:]
+res = {}
+for rep in range(2):
+    for name in libs:
+        E._lib = None
+        E._engines.clear()
+        E.LIB_PATH = os.path.join(ROOT, 'hybrid-drt_b200', '_lib', name)
+        drt = DRT()
+        r0 = drt.fit_eis_batch(freq, z)
+        plan = r0.plan
+        zs = z / r0.scales['coefficient_scale'][:, None]
+        eng = drt.engine
+        rv = eng.dev(np.concatenate([zs.real, zs.imag], axis=1))
+        hyp = drt._c_hypers(plan['opts'])
+        out = {}
+        def step():
+            eng.qphb_fit_batch(plan['rm'], rv, plan['pen'], plan['h'], plan['l1'], plan['n_special'], vmm_eis=plan['vmm_eis'], hypers=hyp, out=out)
+        step(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            step()
+        b.record(); torch.cuda.synchronize()
+        fps = 3 * B / (a.elapsed_time(b) * 1e-3)
+        res.setdefault(name, []).append(fps)
+        print(f'{name:36s} {fps:10.0f} fits/s   x checksum {float(out["x"].sum()):.12e}', flush=True)
