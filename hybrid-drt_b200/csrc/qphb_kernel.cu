@@ -215,24 +215,6 @@ struct L2Factors {
     bool use[3];    // derivative_weights[k] > 0
 };
 
-template <class C>
-__device__ __forceinline__ double l2_entry(const Ctx& c, const L2Factors& f, int i, int j) {
-    double acc = 0.0;
-    const bool drt = (i >= c.ns) && (j >= c.ns);
-    const bool dop = (c.dop_a >= 0) && (i >= c.dop_a) && (i < c.dop_b) && (j >= c.dop_a) && (j < c.dop_b);
-    const int nn = c.n * c.n;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (!f.use[k]) continue;
-        double m = c.pen[k * nn + i * c.n + j];
-        if (drt) m *= f.drt[k];
-        if (dop) m *= f.dop[k];
-        const double* us = C::vec(C::US0 + k);
-        acc += (us[i] * m) * us[j];
-    }
-    return acc;
-}
-
 // One chunk = 8 rows of rm, staged transposed: stage[col][rr] = rm[r0 + rr][col] (zero beyond N / n).  One warp
 // instruction copies a 4-column x 8-row block (lane = 4 rr + cl): 32-byte global segments, conflict-free stores.
 // The vz_offset column of a hybrid fit is read from its per-spectrum buffer.
@@ -255,8 +237,10 @@ __device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
 }
 
 template <class C>
-__device__ __noinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scalar, double l1_value, double* p_out,
-                                           double* q_out) {
+__device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l1_scalar, double l1_value, double* p_out,
+                                        double* q_out) {
+    Ctx c = cref;            // by value: the fields stay in registers instead of the caller's stack frame
+    const L2Factors f = fref;
     const int tid = threadIdx.x;
     const int n = c.n, N = c.N, T = c.T;
     const int g = c.g, q = c.q, lane = c.lane;
@@ -330,24 +314,54 @@ __device__ __noinline__ void gram_phase(Ctx& c, const L2Factors& f, bool l1_scal
         }
     }
     __syncthreads();
+    {
+        constexpr int CU = (C::NV + 31) / 32;
+        const int nn = n * n;
+        const bool dopb = c.dop_a >= 0;
 #pragma unroll 1
-    for (int r = tid >> 5; r < 8 * T; r += C::kWarps) {
-        const int j = r >> 3;
-        double* trow = C::tiles() + (j * (j + 1) / 2) * 64 + (r & 7) * 8;
-#pragma unroll 1
-        for (int cc = lane; cc < 8 * (j + 1); cc += 32) {
-            double* e = trow + (cc >> 3) * 64 + (cc & 7);
-            double v;
-            if (r < n && cc < n) {
-                v = l2_entry<C>(c, f, r, cc) - *e;
-                if (p_out && cc <= r) {
-                    p_out[(size_t)r * n + cc] = v;
-                    p_out[(size_t)cc * n + r] = v;
-                }
-            } else {
-                v = (r == cc) ? 1.0 : 0.0;
+        for (int r = tid >> 5; r < 8 * T; r += C::kWarps) {
+            const int j = r >> 3;
+            double* trow = C::tiles() + (j * (j + 1) / 2) * 64 + (r & 7) * 8;
+            const int rl = min(r, n - 1);
+            // all penalty loads of the row first (L2 hits with a long latency), clamped instead of branched
+            double pm[CU][3];
+#pragma unroll
+            for (int w = 0; w < CU; ++w) {
+                const int cl = min(lane + 32 * w, n - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pm[w][k] = f.use[k] ? c.pen[k * nn + rl * n + cl] : 0.0;
             }
-            *e = -v;
+#pragma unroll
+            for (int w = 0; w < CU; ++w) {
+                const int cc = lane + 32 * w;
+                if (cc < 8 * (j + 1)) {
+                    double* e = trow + (cc >> 3) * 64 + (cc & 7);
+                    double v;
+                    if (r < n && cc < n) {
+                        // qphb.calculate_qp_l2_matrix, qphb.py:53-120
+                        const bool drt = (r >= c.ns) && (cc >= c.ns);
+                        const bool dop = dopb && (r >= c.dop_a) && (r < c.dop_b) && (cc >= c.dop_a) && (cc < c.dop_b);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if (!f.use[k]) continue;
+                            double m = pm[w][k];
+                            if (drt) m *= f.drt[k];
+                            if (dop) m *= f.dop[k];
+                            const double* us = C::vec(C::US0 + k);
+                            acc += (us[r] * m) * us[cc];
+                        }
+                        v = acc - *e;
+                        if (p_out && cc <= r) {
+                            p_out[(size_t)r * n + cc] = v;
+                            p_out[(size_t)cc * n + r] = v;
+                        }
+                    } else {
+                        v = (r == cc) ? 1.0 : 0.0;
+                    }
+                    *e = -v;
+                }
+            }
         }
     }
     PROF_ADD(6);
@@ -691,7 +705,8 @@ __device__ __forceinline__ double sum_parts(int first, int count, int t) {
 }
 
 template <class C>
-__device__ __noinline__ QpOut qp_phase(Ctx& c) {
+__device__ __noinline__ QpOut qp_phase(Ctx& cref) {
+    Ctx c = cref;
     const int tid = threadIdx.x;
     const int n = c.n;
     const bool act = tid < n;
@@ -828,6 +843,7 @@ __device__ __noinline__ QpOut qp_phase(Ctx& c) {
     out.xi = xi;
     out.pcost = pcost;
     out.iters = iters < 0 ? 0 : iters;
+    cref.red_phase = c.red_phase;
     return out;
 }
 // ------------------------------------------------------------------------------------------------
@@ -839,8 +855,10 @@ struct BlockHyp {
 };
 
 template <class C>
-__device__ __noinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, int len, double* rho, double* xmx,
-                                            bool first_iter) {
+__device__ __noinline__ void hyper_block(Ctx& cref, const BlockHyp& hpref, int start, int len, double* rho, double* xmx,
+                                         bool first_iter) {
+    Ctx c = cref;
+    const BlockHyp hp = hpref;
     const int tid = threadIdx.x;
     const int n = c.n, nn = c.n * c.n;
     const bool act = tid < len;
@@ -859,21 +877,34 @@ __device__ __noinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, 
     if (act) {
         const double inv2s0 = 1.0 / (2.0 * hp.sigma[0] * hp.sigma[0]);
         const double* __restrict__ pcol = c.pen + (start * n + gi);  // symmetric: read column-wise (coalesced)
+        // rows in batches of four: the twelve loads (L2 hits, several hundred cycles each) are issued together
 #pragma unroll 1
-        for (int j = 0; j < len; ++j) {
-            const int gj = start + j;
-            const double xj = xs[gj];
-            const double m0 = pcol[j * n], m1 = pcol[nn + j * n], m2 = pcol[2 * nn + j * n];
-            double gam[3] = {(xi * m0) * xj, (xi * m1) * xj, (xi * m2) * xj};
-            if (hp.use_gmat) gam[0] += ((xhi * m1) * xh[gj]) * inv2s0;
+        for (int j0 = 0; j0 < len; j0 += 4) {
+            double mm[4][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (j == tid) {
-                    gd[k] = gam[k] + (hp.s_alpha[k] - 1.0) / hp.s_0[k];
-                } else {
-                    const double g = gam[k] * C::vec(C::US0 + k)[gj];
-                    bsum[k] += g;
-                    mx[k] = fmax(mx[k], fabs(g));
+            for (int u = 0; u < 4; ++u) {
+                const int jj = min(j0 + u, len - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) mm[u][k] = pcol[k * nn + jj * n];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j < len) {
+                    const int gj = start + j;
+                    const double xj = xs[gj];
+                    double gam[3] = {(xi * mm[u][0]) * xj, (xi * mm[u][1]) * xj, (xi * mm[u][2]) * xj};
+                    if (hp.use_gmat) gam[0] += ((xhi * mm[u][1]) * xh[gj]) * inv2s0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (j == tid) {
+                            gd[k] = gam[k] + (hp.s_alpha[k] - 1.0) / hp.s_0[k];
+                        } else {
+                            const double g = gam[k] * C::vec(C::US0 + k)[gj];
+                            bsum[k] += g;
+                            mx[k] = fmax(mx[k], fabs(g));
+                        }
+                    }
                 }
             }
         }
@@ -910,14 +941,26 @@ __device__ __noinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, 
     if (act) {
         const double* __restrict__ pcol = c.pen + (start * n + gi);
 #pragma unroll 1
-        for (int j = 0; j < len; ++j) {
-            const int gj = start + j;
-            const double xj = xs[gj];
+        for (int j0 = 0; j0 < len; j0 += 4) {
+            double mm[4][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double m = pcol[k * nn + j * n];
-                tr[k] += (xj * C::vec(C::US0 + k)[gj]) * m;
-                tx[k] += xj * m;
+            for (int u = 0; u < 4; ++u) {
+                const int jj = min(j0 + u, len - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) mm[u][k] = pcol[k * nn + jj * n];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j < len) {
+                    const int gj = start + j;
+                    const double xj = xs[gj];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        tr[k] += (xj * C::vec(C::US0 + k)[gj]) * mm[u][k];
+                        tx[k] += xj * mm[u][k];
+                    }
+                }
             }
         }
     }
@@ -940,49 +983,50 @@ __device__ __noinline__ void hyper_block(Ctx& c, const BlockHyp& hp, int start, 
 #pragma unroll
         for (int k = 0; k < 3; ++k) xmx[k] = t6[3 + k];
     }
+    cref.red_phase = c.red_phase;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __noinline__ void weights_phase(Ctx& c, const double* est, double var_floor, bool update_vz) {
+__device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double var_floor, bool update_vz) {
+    Ctx c = cref;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, n = c.n, nc = c.nc;
     const double* xs = C::vec(C::XS);
     PROF_DECL;
-    // residuals: one warp per row
-    constexpr int RU = 1, CU = (C::NV + 31) / 32;
+    // residuals: one warp per row, four rows per pass.  All loads of a pass (L2 hits, several hundred cycles
+    // each) are issued before the first use: row / column indices are clamped instead of branched around.
+    constexpr int RU = 4, CU = (C::NV + 31) / 32;
     for (int rb = warp; rb < N; rb += RU * C::kWarps) {
-        double acc[RU], accv[RU];
+        double v[RU][CU];
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-            const int r = rb + u * C::kWarps;
-            acc[u] = 0.0;
-            accv[u] = 0.0;
-            if (r < N) {
-                const double* __restrict__ src = c.rm + (size_t)r * n;
+            const double* __restrict__ src = c.rm + (size_t)min(rb + u * C::kWarps, N - 1) * n;
 #pragma unroll
-                for (int v = 0; v < CU; ++v) {
-                    const int col = lane + 32 * v;
-                    if (col < n) {
-                        const double t = ((col == c.vz) ? c.vzcol[r] : src[col]) * xs[col];
-                        acc[u] += t;
-                        if (col != c.vz && (col < c.vb_a || col >= c.vb_b)) accv[u] += t;
-                    }
-                }
-            }
+            for (int w = 0; w < CU; ++w) v[u][w] = src[min(lane + 32 * w, n - 1)];
         }
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
-            const int r = rb + u * C::kWarps;
-            const double a = warp_sum(acc[u]);
-            const double av = update_vz ? warp_sum(accv[u]) : 0.0;
-            if (lane == 0 && r < N) {
-                const double resid = a - c.rv[r];
+            const int r = min(rb + u * C::kWarps, N - 1);
+            double acc = 0.0, accv = 0.0;
+#pragma unroll
+            for (int w = 0; w < CU; ++w) {
+                const int col = lane + 32 * w;
+                if (col < n) {
+                    const double t = ((col == c.vz) ? c.vzcol[r] : v[u][w]) * xs[col];
+                    acc += t;
+                    if (col != c.vz && (col < c.vb_a || col >= c.vb_b)) accv += t;
+                }
+            }
+            acc = warp_sum(acc);
+            if (update_vz) accv = warp_sum(accv);
+            if (lane == 0 && rb + u * C::kWarps < N) {
+                const double resid = acc - c.rv[r];
                 c.r2[r] = resid * resid;
                 if (update_vz) {
-                    const double sep = (r < nc) ? av : -av;
+                    const double sep = (r < nc) ? accv : -accv;
                     c.vzcol[r] = sep * c.vz_strength[r];
                 }
             }
@@ -997,27 +1041,47 @@ __device__ __noinline__ void weights_phase(Ctx& c, const double* est, double var
         block_reduce<C, 1, 0u>(t1, c);
         chrono_mean = t1[0] / (double)nc;
     }
+    // variance estimate s_hat = vmm r2 (block diagonal: chrono rows x chrono columns, EIS rows x EIS columns)
     for (int rb = warp; rb < N; rb += RU * C::kWarps) {
         double sh[RU];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const int r = rb + u * C::kWarps;
-            double acc = 0.0;
-            if (r < N) {
-                if (r < nc) {
-                    if (c.vmm_chrono != nullptr) {
-                        const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
-#pragma unroll 1
-                        for (int col = lane; col < nc; col += 32) acc += vr[col] * c.r2[col];
-                    }
-                } else {
-                    const int ne = N - nc;
-                    const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
-#pragma unroll 1
-                    for (int col = lane; col < ne; col += 32) acc += vr[col] * c.r2[nc + col];
+        for (int u = 0; u < RU; ++u) sh[u] = 0.0;
+        const bool all_eis = rb >= nc;   // rows of a pass are ascending: every row of it is an EIS row
+        if (all_eis) {
+            const int ne = N - nc;
+            for (int c0 = 0; c0 < ne; c0 += 32 * CU) {
+                double v[RU][CU];
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const double* __restrict__ vr = c.vmm_eis + (size_t)(min(rb + u * C::kWarps, N - 1) - nc) * ne;
+#pragma unroll
+                    for (int w = 0; w < CU; ++w) v[u][w] = vr[min(c0 + lane + 32 * w, ne - 1)];
+                }
+#pragma unroll
+                for (int w = 0; w < CU; ++w) {
+                    const int col = c0 + lane + 32 * w;
+                    const double rr = (col < ne) ? c.r2[nc + col] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) sh[u] = fma(v[u][w], rr, sh[u]);
                 }
             }
-            sh[u] = acc;
+        } else {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int r = rb + u * C::kWarps;
+                if (r < N) {
+                    if (r < nc) {
+                        if (c.vmm_chrono != nullptr) {
+                            const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
+                            for (int col = lane; col < nc; col += 32) sh[u] = fma(vr[col], c.r2[col], sh[u]);
+                        }
+                    } else {
+                        const int ne = N - nc;
+                        const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
+                        for (int col = lane; col < ne; col += 32) sh[u] = fma(vr[col], c.r2[nc + col], sh[u]);
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
@@ -1038,6 +1102,7 @@ __device__ __noinline__ void weights_phase(Ctx& c, const double* est, double var
     }
     __syncthreads();
     PROF_ADD(12);
+    cref.red_phase = c.red_phase;
 }
 
 // ------------------------------------------------------------------------------------------------
