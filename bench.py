@@ -292,7 +292,7 @@ def run_gpu(args):
         prof = os.path.join(ROOT, 'profiles', 'qphb_traffic.json')
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+                traffic = json.load(open(prof)).get('dram_bytes_per_fit') * B   # ncu capture, scaled to this launch
             except Exception:
                 traffic = None
 
@@ -322,7 +322,7 @@ def run_gpu(args):
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / fp64_peak, 'traffic': traffic, 'kernel': 'qphb_kernel',
+                         'frac': achieved / fp64_peak, 'traffic': traffic, 'kernel': 'qphb_kernel (DMMA.8x8x4 + DFMA)',
                          'peak_source': 'measured in this run: register-resident DFMA loop on every SM '
                                         '(MEASURED_PEAKS.json has no FP64 entry)',
                          'flops_per_launch': flops},

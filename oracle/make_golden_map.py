@@ -1,0 +1,46 @@
+"""CPU ORACLE support (test infrastructure, not product code).
+
+Golden fixture for the mapping path: runs the UNMODIFIED reference ``hybdrt.mapping.DRTMD`` (on top of
+oracle/refshim.py) on a small synthetic map and stores what ``fit_all`` leaves behind.  Run in the authoring
+container only (the reference cannot travel):
+
+    python -m oracle.make_golden_map
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+refshim.install()
+warnings.filterwarnings('ignore')
+from hybdrt.mapping.drtmd import DRTMD  # noqa: E402  (the reference)
+from hybdrt_b200 import synth  # noqa: E402
+
+
+def main():
+    rows, cols = 2, 3
+    freq, z = synth.make_map_batch(rows, cols, seed=3)
+    supergrid = np.logspace(-8, 3, 111)
+    md = DRTMD(tau_supergrid=supergrid, psi_dim_names=['row', 'col'], print_progress=False)
+    psi = np.array([(r, c) for r in range(rows) for c in range(cols)], dtype=float)
+    for b in range(len(z)):
+        md.add_observation(psi[b], None, (freq, z[b]))
+    md.fit_all()
+    assert md.obs_fit_status.all()
+    out = dict(freq=freq, z=z, psi=psi, tau_supergrid=supergrid, obs_x=md.obs_x,
+               obs_tau_indices=np.array(md.obs_tau_indices), obs_drt_var=md.obs_drt_var, obs_llh=md.obs_llh,
+               obs_rss=md.obs_rss, tau_epsilon=md.tau_epsilon)
+    for key, val in md.obs_special.items():
+        out['special_' + key] = np.asarray(val)
+    path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_small.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()

@@ -326,3 +326,35 @@ def test_unsupported_options_raise():
     for kw in (dict(update_scale=True), dict(outlier_p=0.01), dict(penalty_type='discrete')):
         with pytest.raises(NotImplementedError):
             drt.fit_eis(c2['freq'], c2['z'][0], **kw)
+
+
+def test_mapping_drtmd_against_the_reference():
+    """hybdrt.mapping.DRTMD.fit_all (reference, one fit per observation) vs the batched dispatch."""
+    from hybdrt_b200.mapping import DRTMD
+    g = load_golden('drtmd_small.npz')
+    md = DRTMD(tau_supergrid=g['tau_supergrid'], psi_dim_names=['row', 'col'], print_progress=False)
+    assert abs(md.tau_epsilon - float(g['tau_epsilon'])) < 1e-12
+    for b in range(len(g['z'])):
+        md.add_observation(g['psi'][b], None, (g['freq'], g['z'][b]))
+    assert md.num_obs == 6 and not md.obs_fit_status.any()
+    md.fit_all()
+    assert md.obs_fit_status.all() and list(md.fitted_obs_index) == list(range(6))
+    assert np.array_equal(np.array(md.obs_tau_indices), g['obs_tau_indices'])
+    for b in range(6):
+        assert rel_err(md.obs_x[b], g['obs_x'][b]) < FIT_TOL
+    assert rel_err(md.obs_special['R_inf'], g['special_R_inf']) < FIT_TOL
+    assert rel_err(md.obs_special['inductance'], g['special_inductance']) < FIT_TOL
+    # batched == one at a time, and refit / incremental adds keep the containers consistent
+    md2 = DRTMD(tau_supergrid=g['tau_supergrid'], print_progress=False)
+    for b in range(3):
+        md2.add_observation(g['psi'][b], None, (g['freq'], g['z'][b]), fit=True)
+    md2.add_observations(g['psi'][3:], g['freq'], g['z'][3:])
+    assert md2.obs_fit_status.tolist() == [True] * 3 + [False] * 3
+    md2.fit_all()
+    assert np.allclose(md2.obs_x, md.obs_x, rtol=1e-12, atol=0) and md2.obs_special['R_inf'].shape == (6,)
+    # a second measurement grid goes into its own batch
+    md2.add_observation([9, 9], None, (g['freq'][::2], g['z'][0][::2]))
+    md2.fit_all()
+    assert md2.obs_fit_status.all() and md2.obs_tau_indices[6] is not None
+    with pytest.raises(ValueError):
+        md2.add_observation([0, 0], None, (g['freq'],))
