@@ -46,13 +46,25 @@ __device__ double warp_trapz(int kind, double arg, double eps, int quad_points) 
 }
 
 // numpy.interp(x, gx, gv) with edge clamping (numpy/_core/src/multiarray/compiled_base.c)
+// The index guess (the tables are uniform up to rounding) uses a precomputed inverse spacing; the two loops then
+// move it to exactly where numpy's binary search lands.
+struct InterpGrid {
+    double x0, xn, inv_dx;
+};
+__device__ __forceinline__ InterpGrid interp_grid(const double* __restrict__ gx, int npts) {
+    InterpGrid g;
+    g.x0 = __ldg(gx);
+    g.xn = __ldg(gx + npts - 1);
+    g.inv_dx = (double)(npts - 1) / (g.xn - g.x0);
+    return g;
+}
 __device__ __forceinline__ double interp_clamped(double x, const double* __restrict__ gx,
-                                                 const double* __restrict__ gv, int npts) {
+                                                 const double* __restrict__ gv, int npts, const InterpGrid& ig) {
     if (isnan(x)) return x;
-    const double x0 = __ldg(gx), xn = __ldg(gx + npts - 1);
+    const double x0 = ig.x0, xn = ig.xn;
     if (x > xn) return __ldg(gv + npts - 1);
     if (x < x0) return __ldg(gv);
-    int j = (int)((x - x0) / (xn - x0) * (double)(npts - 1));
+    int j = (int)((x - x0) * ig.inv_dx);
     j = max(0, min(npts - 1, j));
     while (j > 0 && __ldg(gx + j) > x) --j;
     while (j < npts - 1 && __ldg(gx + j + 1) <= x) ++j;
@@ -103,11 +115,12 @@ __global__ void impedance_interp_kernel(const double* __restrict__ freq, const d
         s_om[i] = freq[(size_t)g * nf + r0 + i] * 2.0 * 3.141592653589793;  // frequencies * 2 * np.pi
     __syncthreads();
     const size_t base = ((size_t)g * nf + r0) * nb;
+    const InterpGrid gre = interp_grid(re_x, npts), gim = interp_grid(im_x, npts);
     for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
         const int rr = idx / nb, m = idx - rr * nb;
         const double x = log(s_om[rr] * s_tau[m]);
-        a_re[base + idx] = interp_clamped(x, re_x, re_v, npts);
-        a_im[base + idx] = interp_clamped(x, im_x, im_v, npts);
+        a_re[base + idx] = interp_clamped(x, re_x, re_v, npts, gre);
+        a_im[base + idx] = interp_clamped(x, im_x, im_v, npts, gim);
     }
 }
 
@@ -152,6 +165,7 @@ __global__ void response_interp_kernel(const double* __restrict__ times, const d
     }
     __syncthreads();
     const size_t base = ((size_t)g * nt + r0) * nb;
+    const InterpGrid gtd = interp_grid(td_x, npts);
     for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
         const int rr = idx / nb, m = idx - rr * nb;
         const double t = s_t[rr];
@@ -159,7 +173,7 @@ __global__ void response_interp_kernel(const double* __restrict__ times, const d
         for (int k = 0; k < n_steps; ++k) {
             if (t > s_st[k]) {
                 const double x = log((t - s_st[k]) / s_tau[m]);
-                acc += __dmul_rn(interp_clamped(x, td_x, td_v, npts), s_sa[k]);
+                acc += __dmul_rn(interp_clamped(x, td_x, td_v, npts, gtd), s_sa[k]);
             }
         }
         rm[base + idx] = acc;
