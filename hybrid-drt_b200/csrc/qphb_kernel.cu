@@ -434,29 +434,34 @@ __device__ __forceinline__ void matvec_p(const Ctx& c, const double* xs) {
 
 // Solve H u = bs with the register tiles Y = L^-T of factor_invert:  u = Y (Y^T bs).  Slot (a, b) holds Y_ij
 // (row block i, column block j).  On return u[t] = sum_{p < W} part(W + p)[t].
+// part(wc)[8j + ..] <- this warp's contribution to Y^T bs ("T" part: reduce over g); sum over wc to finish
+template <class C>
+__device__ __forceinline__ void matvec_yt(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
+    const int T = c.T, g = c.g, q = c.q;
+    const double* bc = bs + 8 * c.wc + g;
+    double bg[C::A];
+#pragma unroll
+    for (int b = 0; b < C::A; ++b) bg[b] = bc[b * (8 * C::W)];   // NV-padded: always in range
+#pragma unroll
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::W * a + c.wr;
+        if (j < T) {
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {   // out-of-triangle diagonal slots hold zeros
+                acc.x = fma(S[C::sidx(a, b)].x, bg[b], acc.x);
+                acc.y = fma(S[C::sidx(a, b)].y, bg[b], acc.y);
+            }
+            const double v0 = reduce_g(acc.x), v1 = reduce_g(acc.y);
+            if (g == 0) sts2(C::part(c.wc) + 8 * j + 2 * q, make_double2(v0, v1));
+        }
+    }
+}
+
 template <class C>
 __device__ __forceinline__ void solve_phase(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
     const int T = c.T, g = c.g, q = c.q;
-    {   // t = Y^T bs: T part (reduce over g), partial per wc
-        const double* bc = bs + 8 * c.wc + g;
-        double bg[C::A];
-#pragma unroll
-        for (int b = 0; b < C::A; ++b) bg[b] = bc[b * (8 * C::W)];   // NV-padded: always in range
-#pragma unroll
-        for (int a = 0; a < C::A; ++a) {
-            const int j = C::W * a + c.wr;
-            if (j < T) {
-                double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int b = 0; b <= a; ++b) {   // out-of-triangle diagonal slots hold zeros
-                    acc.x = fma(S[C::sidx(a, b)].x, bg[b], acc.x);
-                    acc.y = fma(S[C::sidx(a, b)].y, bg[b], acc.y);
-                }
-                const double v0 = reduce_g(acc.x), v1 = reduce_g(acc.y);
-                if (g == 0) sts2(C::part(c.wc) + 8 * j + 2 * q, make_double2(v0, v1));
-            }
-        }
-    }
+    matvec_yt<C>(c, S, bs);
     __syncthreads();
     {   // u = Y t: N part (reduce over q), partial per wr
         double acc[C::A];
@@ -1106,6 +1111,45 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Post-fit diagnostics for the mapping path (DRT.estimate_distribution_cov, drt1d.py:3063-3151, with
+// estimate_param_cov :4116-4138): diag(B P^-1 B^T) for the rows b_t of the evaluation matrix B, in the scaled
+// space (the host multiplies by coefficient_scale^2).  P = L L^T is factorised and inverted by the same tile
+// sweep as the QP's KKT matrices (its negated tiles are in shared memory after the calculate_pq Gram pass);
+// then diag_t = |Y^T b_t|^2 with Y = L^-T.  Returns false if P is not positive definite (the reference warns
+// 'Singular P matrix' and reports no covariance).
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __noinline__ bool postfit_variance(Ctx& cref, const double* __restrict__ eval_mat, int n_eval, double* out) {
+    Ctx c = cref;
+    const int tid = threadIdx.x, n = c.n;
+    double* bs = C::vec(C::BS);
+    if (tid < C::NV) C::vec(C::DSQ)[tid] = 0.0;
+    __syncthreads();
+    double2 S[C::NSLOT];
+    const bool ok = factor_invert<C>(c, S);
+    if (ok) {
+#pragma unroll 1
+        for (int t = 0; t < n_eval; ++t) {
+            if (tid < n) bs[tid] = eval_mat[(size_t)t * n + tid];
+            __syncthreads();
+            matvec_yt<C>(c, S, bs);
+            __syncthreads();
+            double v[1] = {0.0};
+            if (tid < n) {
+                const double y = sum_parts<C>(0, C::W, tid);
+                v[0] = y * y;
+            }
+            block_reduce<C, 1, 0u>(v, c);
+            if (tid == 0) out[t] = v[0];
+        }
+    }
+    if (tid < C::NV) bs[tid] = 0.0;   // the padding entries of the solve right-hand side must read as zero
+    __syncthreads();
+    cref.red_phase = c.red_phase;
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
 // One spectrum.  The outer loop runs phase -1 (initialize_weights), 0..max_iter-1 (iterate_qphb) and,
 // when P/q are requested, one final Gram-only phase (calculate_pq) through the same code.
 template <class C>
@@ -1196,9 +1240,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
         __syncthreads();
         PROF_ADD(0);
-        gram_phase<C>(c, f, init, hy.iw_l1_lambda_0, final_pq ? p.p_matrix + (size_t)b * n * n : nullptr,
+        gram_phase<C>(c, f, init, hy.iw_l1_lambda_0, (final_pq && p.p_matrix) ? p.p_matrix + (size_t)b * n * n : nullptr,
                         (final_pq && p.q_vector) ? p.q_vector + (size_t)b * n : nullptr);
-        if (final_pq) break;
+        if (final_pq) {
+            if (p.dist_var && !postfit_variance<C>(c, p.eval_mat, p.n_eval, p.dist_var + (size_t)b * p.n_eval))
+                status |= HDRT_ST_COV_FAIL;
+            break;
+        }
 
         PROF_ADD(1);
         QpOut qo = qp_phase<C>(c);
@@ -1248,7 +1296,15 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (conv || it >= hy.max_iter) {
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
             if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = c.w[r];
-            if (p.p_matrix == nullptr) break;
+            if (p.resid_ss) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
+                double t2[2] = {0.0, 0.0};
+                for (int r = tid; r < N; r += C::kThreads) {
+                    if (r < c.nc) t2[0] += c.r2[r]; else t2[1] += c.r2[r];
+                }
+                block_reduce<C, 2, 0u>(t2, c);
+                if (tid == 0) { p.resid_ss[2 * (size_t)b] = t2[0]; p.resid_ss[2 * (size_t)b + 1] = t2[1]; }
+            }
+            if (p.p_matrix == nullptr && p.dist_var == nullptr) break;
             final_pq = true;
         }
     }
@@ -1382,6 +1438,7 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (p.n_chrono < p.n_rows && !p.vmm_eis) { set_error("vmm_eis required when EIS rows exist"); return HDRT_ERR_ARG; }
     if (p.vz_index >= 0 && (!p.vz_col || !p.vz_strength)) { set_error("vz_col and vz_strength required with vz_index"); return HDRT_ERR_ARG; }
     if (p.dop_start >= 0 && (p.dop_end <= p.dop_start || p.dop_end > p.n_special)) { set_error("invalid DOP range"); return HDRT_ERR_ARG; }
+    if (p.dist_var && (!p.eval_mat || p.n_eval <= 0)) { set_error("dist_var needs eval_mat and n_eval > 0"); return HDRT_ERR_ARG; }
     if (p.n_cols > kMaxCols) { set_error("n_cols %d > %d unsupported", p.n_cols, kMaxCols); return HDRT_ERR_UNSUPPORTED; }
     const long long smem = hdrt_qphb_smem_bytes(p.n_rows, p.n_cols);
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_lib', 'libhybdrt_b200.so')
 
 MODE_INTERP, MODE_TRAPZ = 0, 1
-ST_CONVERGED, ST_MAXITER, ST_QP_MAXITERS, ST_KKT_FAIL, ST_NAN = 1, 2, 4, 8, 16
+ST_CONVERGED, ST_MAXITER, ST_QP_MAXITERS, ST_KKT_FAIL, ST_NAN, ST_COV_FAIL = 1, 2, 4, 8, 16, 32
 
 _D3 = C.c_double * 3
 
@@ -53,6 +53,7 @@ class Problem(C.Structure):
         ('s_vectors', _P), ('rho', _P), ('dop_rho', _P), ('xmx_norms', _P), ('dop_xmx_norms', _P),
         ('fun', _P), ('vz_col', _P), ('p_matrix', _P), ('q_vector', _P),
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
+        ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P),
     ]
 
 
@@ -256,7 +257,7 @@ class Engine:
 
     def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
                        dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
-                       hypers=None, want_pq=False, out=None):
+                       hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False):
         """Launch the batched QPHB solver.  All inputs are device float64 tensors.
 
         rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
@@ -311,6 +312,12 @@ class Engine:
         if want_pq:
             p.p_matrix = _ptr(buf('p_matrix', b, n, n))
             p.q_vector = _ptr(buf('q_vector', b, n))
+        if eval_mat is not None:       # post-fit diagnostics of the mapping path
+            assert eval_mat.is_cuda and eval_mat.dtype == torch.float64 and eval_mat.is_contiguous() and eval_mat.shape[1] == n
+            p.eval_mat, p.n_eval = _ptr(eval_mat), int(eval_mat.shape[0])
+            p.dist_var = _ptr(buf('dist_var', b, eval_mat.shape[0]))
+        if want_resid:
+            p.resid_ss = _ptr(buf('resid_ss', b, 2))
         p.n_outer = _ptr(buf('n_outer', b, dtype=torch.int32))
         p.n_ipm = _ptr(buf('n_ipm', b, dtype=torch.int32))
         p.status = _ptr(buf('status', b, dtype=torch.int32))

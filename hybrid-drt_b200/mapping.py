@@ -10,9 +10,12 @@ flags) is then filled for the whole group with array operations.
 With ``shard=True`` under ``torchrun`` every rank fits an interleaved slice of each group and the results are
 gathered on all ranks (sharding.gather_results); no collective runs during the fits.
 
+The post-fit diagnostics the reference computes after every fit (drtmd.py:256-279: ``obs_drt_var`` =
+diag of ``estimate_distribution_cov`` on the tau supergrid with ``extend_var``, ``obs_llh``, ``obs_rss`` with uniform
+weights, normalised) come out of the same kernel launch (``diag_tau``).
+
 Not mirrored (outside SURVEY.md section 8): file readers, resolve / filter / badness scoring, prediction
-helpers, PFRT.  The post-fit diagnostics ``obs_drt_var`` / ``obs_llh`` / ``obs_rss`` (section 8f, N1) are left at
-zero.
+helpers, PFRT.
 """
 import time
 
@@ -29,7 +32,10 @@ class DRTMD:
                  fit_inductance=True, fit_ohmic=True, fit_capacitance=False, fixed_basis_nu=None, fit_dop=False,
                  normalize_dop=True, nu_basis_type='gaussian', nu_epsilon=None, time_precision=10,
                  input_signal_precision=10, frequency_precision=10, fit_kw=None, fit_type='drt',
-                 print_diagnostics=False, print_progress=True, warn=False, device=0):
+                 print_diagnostics=False, print_progress=True, warn=False, llh_kw=None, rss_kw=None, device=0):
+        for kw_dict in (llh_kw, rss_kw):
+            if kw_dict and (kw_dict.get('normalize', True) is not True or kw_dict.get('weights', 'uniform') != 'uniform'):
+                raise NotImplementedError('hybdrt_b200: llh_kw / rss_kw other than the DRTMD defaults')
         if fit_type != 'drt':
             raise NotImplementedError("hybdrt_b200: fit_type other than 'drt' (PFRT) is outside the accelerated path")
         self.tau_supergrid = np.asarray(tau_supergrid, dtype=float)
@@ -126,10 +132,38 @@ class DRTMD:
             self.fit_observation(self._n - 1)
 
     def add_observations(self, psi, eis_frequencies, z):
-        """Bulk form of add_observation for EIS maps on a shared frequency grid: psi [B, d], z [B, Nf]."""
-        psi = np.asarray(psi, dtype=float).reshape(len(z), -1)
-        for b in range(len(z)):
-            self.add_observation(psi[b], None, (eis_frequencies, z[b]))
+        """Bulk form of add_observation for EIS maps on a shared frequency grid: psi [B, d], z [B, Nf].  The
+        containers grow once (add_observation re-allocates them per call, as the reference does)."""
+        z = np.asarray(z)
+        nb = len(z)
+        psi = np.asarray(psi, dtype=float).reshape(nb, -1)
+        if self.obs_psi is None:
+            self.obs_psi = np.zeros((0, psi.shape[1]))
+        if psi.shape[1] != self.obs_psi.shape[1]:
+            raise ValueError(f'psi must have length {self.obs_psi.shape[1]}')
+        f = np.asarray(eis_frequencies, dtype=float)
+        nt = len(self.tau_supergrid)
+        self.obs_psi = np.vstack([self.obs_psi, psi])
+        self.obs_data.extend((None, (f, z[b])) for b in range(nb))
+        self.obs_group_id.extend([None] * nb)
+        self.obs_data_badness = np.concatenate([self.obs_data_badness, np.zeros(nb)])
+        self.obs_ignore_flag = np.concatenate([self.obs_ignore_flag, np.zeros(nb, dtype=bool)])
+        self._n += nb
+        self.obs_fit_attr.extend([None] * nb)
+        self.obs_fit_errors.extend([None] * nb)
+        self.obs_tau_indices.extend([None] * nb)
+        self.obs_fit_status = np.concatenate([self.obs_fit_status, np.zeros(nb, dtype=bool)])
+        self.obs_fit_badness = np.concatenate([self.obs_fit_badness, np.zeros(nb)])
+        self.obs_x = np.vstack([self.obs_x, np.zeros((nb, nt))])
+        self.obs_drt_var = np.vstack([self.obs_drt_var, np.zeros((nb, nt))])
+        self.obs_llh = np.concatenate([self.obs_llh, np.zeros(nb)])
+        self.obs_rss = np.concatenate([self.obs_rss, np.zeros(nb)])
+        self.obs_outer_iterations = np.concatenate([self.obs_outer_iterations, np.zeros(nb, dtype=int)])
+        self.obs_status = np.concatenate([self.obs_status, np.zeros(nb, dtype=int)])
+        if self.obs_special is not None:
+            for key in list(self.obs_special):
+                pad = np.zeros((nb,) + self.obs_special[key].shape[1:])
+                self.obs_special[key] = np.concatenate([self.obs_special[key], pad], axis=0)
 
     def get_obs_data(self, obs_index):
         chrono_data, eis_data = self.obs_data[obs_index]
@@ -148,6 +182,17 @@ class DRTMD:
             key += [f.shape, f.tobytes()]
         return tuple(key)
 
+    def _group(self, obs_index):
+        """Observations by measurement grid.  Arrays shared by identity (bulk adds) are hashed once."""
+        groups, by_id = {}, {}
+        for idx in obs_index:
+            chrono, eis = self.get_obs_data(idx)
+            ident = (id(chrono[0]), id(chrono[1]), id(eis[0]))
+            if ident not in by_id:
+                by_id[ident] = self._grid_key(chrono, eis)
+            groups.setdefault(by_id[ident], []).append(idx)
+        return groups
+
     def fit_observation(self, obs_index, ignore_errors=False):
         self.fit_observations([obs_index], ignore_errors=ignore_errors, _quiet=True)
 
@@ -157,11 +202,7 @@ class DRTMD:
         if verbose:
             print(f'Found {len(obs_index)} observations to fit')
         start = time.time()
-        groups = {}
-        for idx in obs_index:
-            chrono, eis = self.get_obs_data(idx)
-            groups.setdefault(self._grid_key(chrono, eis), []).append(idx)
-        for members in groups.values():
+        for members in self._group(obs_index).values():
             self._fit_group(np.asarray(members), ignore_errors, shard)
         if verbose and obs_index:
             el = time.time() - start
@@ -194,17 +235,20 @@ class DRTMD:
             zz = z if (z is None or len(z)) else np.ones((1, z.shape[1]), dtype=complex)
             vv = v if (v is None or len(v)) else np.ones((1, v.shape[1]))
             if chrono0[0] is None:
-                res = drt.fit_eis_batch(eis0[0], zz, **self.fit_kw)
+                res = drt.fit_eis_batch(eis0[0], zz, diag_tau=self.tau_supergrid, **self.fit_kw)
             elif eis0[0] is None:
-                res = drt.fit_chrono_batch(chrono0[0], chrono0[1], vv, **self.fit_kw)
+                res = drt.fit_chrono_batch(chrono0[0], chrono0[1], vv, diag_tau=self.tau_supergrid, **self.fit_kw)
             else:
-                res = drt.fit_hybrid_batch(chrono0[0], chrono0[1], vv, eis0[0], zz, **self.fit_kw)
+                res = drt.fit_hybrid_batch(chrono0[0], chrono0[1], vv, eis0[0], zz, diag_tau=self.tau_supergrid,
+                                           **self.fit_kw)
         fp = res.fit_parameters()
         host = res.host(['status', 'n_outer'])
         left = nearest_index(self.tau_supergrid, drt.basis_tau[0])
         right = nearest_index(self.tau_supergrid, drt.basis_tau[-1]) + 1
         nloc = len(local)
-        out = {'x': fp['x'][:nloc], 'status': host['status'][:nloc], 'n_outer': host['n_outer'][:nloc]}
+        out = {'x': fp['x'][:nloc], 'status': host['status'][:nloc], 'n_outer': host['n_outer'][:nloc],
+               'drt_var': res.distribution_var(extend_var=True)[:nloc], 'llh': res.evaluate_llh()[:nloc],
+               'rss': res.evaluate_rss()[:nloc]}
         sp_keys = list(drt.special_qp_params.keys())
         for key in sp_keys:
             out['sp_' + key] = np.asarray(fp[key])[:nloc]
@@ -226,6 +270,9 @@ class DRTMD:
         self.obs_x[good, left:right] = out['x'][~bad]
         for key in sp_keys:
             self.obs_special[key][good] = out['sp_' + key][~bad]
+        self.obs_drt_var[good] = out['drt_var'][~bad]
+        self.obs_llh[good] = out['llh'][~bad]
+        self.obs_rss[good] = out['rss'][~bad]
         self.obs_fit_status[good] = True
         self.obs_outer_iterations[members] = out['n_outer']
         self.obs_status[members] = out['status']

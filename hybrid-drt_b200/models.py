@@ -240,6 +240,55 @@ class BatchFit:
         out['z_sigma_tot'] = (sig[:, nc:nc + nf] + 1j * sig[:, nc + nf:]) * cs if nf else None
         return out
 
+    # ---- post-fit diagnostics of the mapping path (drtmd.py:256-279); need diag_tau at fit time
+    def _uniform_weights(self):
+        """weights='uniform': the mean estimated weight of each domain (drt1d.py:4433-4447)."""
+        ew = self.host(['est_weights'])['est_weights']
+        nc = self.plan['n_chrono']
+        wc = ew[:, :nc].mean(axis=1) if nc else np.zeros(len(ew))
+        we = ew[:, nc:].mean(axis=1) if ew.shape[1] > nc else np.zeros(len(ew))
+        return wc, we
+
+    def evaluate_rss(self, normalize=True):
+        """DRT.evaluate_rss(weights='uniform') (drt1d.py:4433-4459, qphb.evaluate_rss :1347-1352)."""
+        ss = self.host(['resid_ss'])['resid_ss']
+        wc, we = self._uniform_weights()
+        rss = wc ** 2 * ss[:, 0] + we ** 2 * ss[:, 1]
+        return rss / self.plan['n_rows'] if normalize else rss
+
+    def evaluate_llh(self, normalize=True, alpha_0=2, beta_0=1):
+        """DRT.evaluate_llh(weights='uniform', marginalize_weights=True) (drt1d.py:4461-4496, qphb.py:1355-1377)."""
+        from scipy.special import loggamma
+        n_rows, nc = self.plan['n_rows'], self.plan['n_chrono']
+        wc, we = self._uniform_weights()
+        rss = self.evaluate_rss(normalize=False)
+        alpha_n = alpha_0 - 1 + n_rows / 2
+        beta_n = beta_0 + 0.5 * rss
+        llh = alpha_0 * np.log(beta_0) - alpha_n * np.log(beta_n) + loggamma(alpha_n) - loggamma(alpha_0)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            llh = llh + (nc * np.log(wc) if nc else 0.0) + ((n_rows - nc) * np.log(we) if n_rows > nc else 0.0)
+        return llh / n_rows if normalize else llh
+
+    def distribution_var(self, extend_var=True):
+        """diag of DRT.estimate_distribution_cov(tau=diag_tau) (drt1d.py:3063-3151) for the whole batch; NaN rows
+        where the final P was not positive definite (reference: None + 'Singular P matrix' warning)."""
+        pl = self.plan
+        h = self.host(['dist_var', 'status'])
+        var = h['dist_var'] * self.scales['coefficient_scale'][:, None] ** 2
+        var[(h['status'] & _engine.ST_COV_FAIL) != 0] = np.nan
+        if extend_var:
+            tau = pl['diag_tau']
+            lo, hi = np.inf, -np.inf
+            if pl['frequencies'] is not None:
+                lo, hi = 1 / (2 * np.pi * np.max(pl['frequencies'])), 1 / (2 * np.pi * np.min(pl['frequencies']))
+            if pl['times'] is not None:
+                td = time_since_step(pl['times'], pl['step_times'])
+                lo, hi = min(lo, np.min(td)), max(hi, np.max(td))
+            li, ri = nearest_index(tau, lo) + 1, nearest_index(tau, hi)
+            var[:, :li] = np.maximum(var[:, :li], var[:, li:li + 1])
+            var[:, ri:] = np.maximum(var[:, ri:], var[:, ri:ri + 1])
+        return var
+
     def predict_z(self, frequencies=None):
         """DRT.predict_z at the fit frequencies (drt1d.py:3500-3542) for the whole batch."""
         pl = self.plan
@@ -438,7 +487,7 @@ class DRT:
         plan = dict(data_type=data_type, special_qp_params=sp, n_special=ns, n=n, n_rows=n_rows, n_chrono=nc,
                     n_freq=nf, frequencies=frequencies, times=times, basis_tau=tau,
                     inductance_scale=kw['inductance_scale'], capacitance_scale=kw['capacitance_scale'],
-                    weight_factor=kw['weight_factor'], hypers=hyp)
+                    weight_factor=kw['weight_factor'], hypers=hyp, step_times=step_times)
         self.inductance_scale, self.capacitance_scale = kw['inductance_scale'], kw['capacitance_scale']
 
         # DOP scale vector, drt1d.py:5767-5788
@@ -625,10 +674,21 @@ class DRT:
         ch.eis_weight_factor = float(kw['eis_weight_factor'])
         return ch
 
+    def _eval_matrix(self, plan, tau_eval):
+        """basis.construct_func_eval_matrix (basis.py:488-514, order 0, gaussian) on ``tau_eval``, embedded in the
+        full coefficient vector (zero columns for the special parameters).  None when no diagnostics are wanted."""
+        if tau_eval is None:
+            return None
+        d = np.log(np.asarray(tau_eval, dtype=float))[:, None] - np.log(plan['basis_tau'])[None, :]
+        em = np.zeros((d.shape[0], plan['n']))
+        em[:, plan['n_special']:] = np.exp(-(self.tau_epsilon * d) ** 2)
+        return self.engine.dev(em)
+
     # ------------------------------------------------------------------------------------------------
     # the batched fit core
     # ------------------------------------------------------------------------------------------------
-    def _fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, want_pq=False, step_times=None,
+    def _fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, want_pq=False, diag_tau=None,
+                        step_times=None,
                         step_sizes=None, nonneg=True, neg_allowed_tau_range=None, series_neg=False,
                         scale_data=True, update_scale=False, solve_rp=False,
                         offset_steps=True, step_offset_size=None, discard_first_n=None,
@@ -740,7 +800,9 @@ class DRT:
                                  vmm_eis=plan['vmm_eis'], vmm_chrono=None, n_chrono=nc, dop_range=dop_range,
                                  vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
                                  hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
-                                 want_pq=want_pq)
+                                 want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
+                                 want_resid=diag_tau is not None)
+        plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         if nf:
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
             if self.fit_dop:
@@ -761,6 +823,8 @@ class DRT:
                                     neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data,
                                     update_scale=update_scale, eis_error_structure=error_structure,
                                     eis_vmm_epsilon=vmm_epsilon, eis_reim_cor=vmm_reim_cor, **kwargs)
+    # every *_batch entry accepts diag_tau=<tau grid>: the kernel then also returns what DRTMD.fit_observation
+    # computes after each fit (distribution variance on that grid, residual sums for llh / rss)
 
     def fit_chrono_batch(self, times, i_signal, v_signal, step_times=None, step_sizes=None, nonneg=True,
                          error_structure='uniform', vmm_epsilon=4, **kwargs):

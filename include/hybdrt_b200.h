@@ -34,6 +34,7 @@ extern "C" {
 #define HDRT_ST_QP_MAXITERS 4 /* some QP hit the interior-point iteration cap (cvxopt 'unknown')  */
 #define HDRT_ST_KKT_FAIL 8    /* Cholesky breakdown inside a QP (cvxopt: singular KKT matrix)     */
 #define HDRT_ST_NAN 16        /* non-finite coefficients                                          */
+#define HDRT_ST_COV_FAIL 32   /* final P not positive definite: no covariance (reference: 'Singular P matrix') */
 
 typedef struct hdrt_handle hdrt_handle;
 
@@ -160,6 +161,13 @@ typedef struct hdrt_qphb_problem {
     int* n_outer;          /* [1]   outer iterations executed                              */
     int* n_ipm;            /* [1]   interior-point iterations summed over all QPs          */
     int* status;           /* [1]   HDRT_ST_* bits                                         */
+
+    /* optional post-fit diagnostics of the mapping path (drtmd.py:256-279) */
+    const double* eval_mat; /* [n_eval][n] rows of the distribution-evaluation matrix (basis.construct_func_eval_matrix,
+                               zero in the special columns), shared by the batch; needed iff dist_var != NULL       */
+    int n_eval;
+    double* dist_var;      /* [n_eval] diag(B P^-1 B^T) in the scaled space (drt1d.py:3063-3151, :4116-4138)         */
+    double* resid_ss;      /* [2]   sum of squared residuals of the final x: chrono rows, EIS rows (qphb.py:1347)   */
 } hdrt_qphb_problem;
 
 /* Fills `hyp` with the reference defaults (qphb.py:208-255 eff_hp=True, drt1d.py:102-137). */

@@ -344,6 +344,10 @@ def test_mapping_drtmd_against_the_reference():
         assert rel_err(md.obs_x[b], g['obs_x'][b]) < FIT_TOL
     assert rel_err(md.obs_special['R_inf'], g['special_R_inf']) < FIT_TOL
     assert rel_err(md.obs_special['inductance'], g['special_inductance']) < FIT_TOL
+    # post-fit diagnostics (drtmd.py:256-279): distribution variance on the supergrid, llh, rss
+    for b in range(6):
+        assert rel_err(md.obs_drt_var[b], g['obs_drt_var'][b]) < 1e-5
+    assert rel_err(md.obs_rss, g['obs_rss']) < FIT_TOL and rel_err(md.obs_llh, g['obs_llh']) < FIT_TOL
     # batched == one at a time, and refit / incremental adds keep the containers consistent
     md2 = DRTMD(tau_supergrid=g['tau_supergrid'], print_progress=False)
     for b in range(3):
