@@ -79,6 +79,7 @@ struct Cfg {
     static constexpr int NTILE = TMAX * (TMAX + 1) / 2;
     static constexpr int NPART = 2 * W;
     static constexpr int kChunk = 8;                  // rows of rm per Gram step (two DMMA k-steps)
+    static constexpr int kStages = 4;                 // cp.async ring depth of the Gram (lives in the tile area)
     // offsets
     static constexpr int oRed = kNumVec * NV;
     static constexpr int oRbuf = oRed + 2 * kRedSlots * kWarps;
@@ -88,8 +89,8 @@ struct Cfg {
     static constexpr int oScr = oBinv + 64;                    //          diagonal-tile scratch (160)
     static constexpr int oTr = oScr + 160;                     //          per-warp transpose scratch (80 each)
     static constexpr int oPan = oTr + 80 * kWarps;             //          TMAX tiles: column k
-    static constexpr int oStage = oUnion;                      // Gram view: 2 x NV x 8 (transposed chunks)
-    static constexpr int oTiles = cmax(oPan + TMAX * 64, oStage + 2 * NV * kChunk);
+    static constexpr int oTiles = oPan + TMAX * 64;            // NTILE x 64 negated P tiles; Gram staging ring
+    static_assert(kStages * NV * kChunk <= NTILE * 64, "staging ring must fit in the tile area");
     static constexpr int oRows = oTiles + NTILE * 64;          // w[N], r2[N], aux[N]
     enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH, SPARE };
     static __device__ __forceinline__ double* vec(int k) { return g_smem + k * NV; }
@@ -100,8 +101,13 @@ struct Cfg {
     static __device__ __forceinline__ double* scr() { return g_smem + oScr; }
     static __device__ __forceinline__ double* tr(int warp) { return g_smem + oTr + 80 * warp; }
     static __device__ __forceinline__ double* pan() { return g_smem + oPan; }
-    static __device__ __forceinline__ double* stage() { return g_smem + oStage; }
     static __device__ __forceinline__ double* tiles() { return g_smem + oTiles; }
+    // per-row vectors w[N], r2[N], aux[N] (each padded to a multiple of 8): derived from g_smem so that the
+    // compiler emits shared-memory loads, not generic ones
+    static __device__ __forceinline__ int* flag() { return reinterpret_cast<int*>(g_smem + oRbuf + 8); }   // factorisation status
+    static __device__ __forceinline__ double* roww() { return g_smem + oRows; }
+    static __device__ __forceinline__ double* rowr2(int N) { return g_smem + oRows + ((N + 7) & ~7); }
+    static __device__ __forceinline__ double* rowaux(int N) { return g_smem + oRows + 2 * ((N + 7) & ~7); }
     __host__ __device__ static constexpr int sidx(int a, int b) { return a * (a + 1) / 2 + b; }
 };
 
@@ -131,8 +137,6 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
-    double *w, *r2, *aux;
-    int* flag;      // shared: factorisation status of the current tile column
     int red_phase;
 };
 
@@ -223,7 +227,7 @@ __device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
     const int warp = threadIdx.x >> 5, cl = c.lane & 3, rr = c.lane >> 2;
     const bool rok = r0 + rr < c.N;
     const double* srow = c.rm + (size_t)(r0 + rr) * c.n;
-    double* drow = C::stage() + buf * C::NV * C::kChunk + rr;
+    double* drow = C::tiles() + buf * C::NV * C::kChunk + rr;
 #pragma unroll
     for (int u = 0; u < (C::NV / 4 + C::kWarps - 1) / C::kWarps; ++u) {
         const int col = 4 * (warp + C::kWarps * u) + cl;
@@ -245,13 +249,20 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
     const int n = c.n, N = c.N, T = c.T;
     const int g = c.g, q = c.q, lane = c.lane;
     PROF_DECL;
-    double* w2 = c.r2;      // w^2, zero padded to a multiple of 8
-    double* w2rv = c.aux;   // w^2 rv
-    __syncthreads();        // previous users of the union area and of r2 are done
-    stage_chunk<C>(c, 0, 0);
+    double* w2 = C::rowr2(c.N);      // w^2, zero padded to a multiple of 8
+    double* w2rv = C::rowaux(c.N);   // w^2 rv
+    __syncthreads();        // previous users of the tile area and of r2 are done
+    // rm chunks travel through a ring of kStages buffers inside the (still unused) tile area: the copies are L2
+    // hits with a latency of a few chunks' worth of DMMA work
+    constexpr int NS = C::kStages;
+    const int nchunks = (N + C::kChunk - 1) / C::kChunk;
+#pragma unroll
+    for (int st = 0; st < NS - 1; ++st) {
+        if (st < nchunks) stage_chunk<C>(c, st * C::kChunk, st); else cp_async_commit();
+    }
     for (int r = tid; r < rows_pad(N); r += C::kThreads) {
         double ww = 0.0, wv = 0.0;
-        if (r < N) { ww = c.w[r] * c.w[r]; wv = ww * c.rv[r]; }
+        if (r < N) { ww = C::roww()[r] * C::roww()[r]; wv = ww * c.rv[r]; }
         w2[r] = ww;
         w2rv[r] = wv;
     }
@@ -262,13 +273,13 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
     double2 S[C::NSLOT];
 #pragma unroll
     for (int e = 0; e < C::NSLOT; ++e) S[e] = make_double2(0.0, 0.0);
-    int buf = 0;
-    for (int r0 = 0; r0 < N; r0 += C::kChunk) {
-        const bool more = r0 + C::kChunk < N;
-        if (more) stage_chunk<C>(c, r0 + C::kChunk, buf ^ 1);
-        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int r0 = ci * C::kChunk, buf = ci % NS;
+        cp_async_wait<NS - 2>();   // chunk ci has landed (this thread's copies); the barrier publishes it
         __syncthreads();
-        const double* base = C::stage() + buf * C::NV * C::kChunk;
+        if (ci + NS - 1 < nchunks) stage_chunk<C>(c, (ci + NS - 1) * C::kChunk, (ci + NS - 1) % NS);   // refill the
+        else cp_async_commit();                                            // buffer everyone left last iteration
+        const double* base = C::tiles() + buf * C::NV * C::kChunk;
         // fragment of tile column X: .x = rm[r0 + 2q][8X + g], .y = rm[r0 + 2q + 1][8X + g]
         const double* frow = base + (8 * c.wr + g) * C::kChunk + 2 * q;
         const double* fcol = base + (8 * c.wc + g) * C::kChunk + 2 * q;
@@ -296,9 +307,8 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
                 }
             }
         }
-        __syncthreads();  // the buffer is free for the chunk after next
-        buf ^= 1;
     }
+    __syncthreads();   // every warp is done with the ring before the tiles overwrite it
     PROF_ADD(5);
     // -Gram tiles to shared memory, then one rolled pass over the lower-triangle tiles adds the penalty, sets the
     // padding rows / columns to the identity and writes the optional dense copy
@@ -588,7 +598,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
         double2 ykk;
         const bool ok = diag_factor(S[0], C::binv(), ykk, lane);
         S[0] = ykk;
-        if (lane == 0) *c.flag = ok ? 1 : 0;
+        if (lane == 0) *C::flag() = ok ? 1 : 0;
     }
 #pragma unroll 1
     for (int k = 0; k < T; ++k) {
@@ -597,7 +607,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
         PROF_ADD(17);
         __syncthreads();  // (A) -L_kk^-1 published
         PROF_ADD(18);
-        if (*c.flag == 0) return false;
+        if (*C::flag() == 0) return false;
         const double2 bn = lds2(C::binv() + 2 * lane);
         if (diag_owner) {
 #pragma unroll
@@ -669,7 +679,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                 PROF_COUNT(24);
 #pragma unroll
                 for (int a = 0; a < C::A; ++a) if (a == k1d) S[C::sidx(a, a)] = ykk;
-                if (lane == 0) *c.flag = ok ? 1 : 0;
+                if (lane == 0) *C::flag() = ok ? 1 : 0;
             }
             PROF_ADD(17);
 #pragma unroll
@@ -1029,7 +1039,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
             if (update_vz) accv = warp_sum(accv);
             if (lane == 0 && rb + u * C::kWarps < N) {
                 const double resid = acc - c.rv[r];
-                c.r2[r] = resid * resid;
+                C::rowr2(c.N)[r] = resid * resid;
                 if (update_vz) {
                     const double sep = (r < nc) ? accv : -accv;
                     c.vzcol[r] = sep * c.vz_strength[r];
@@ -1042,7 +1052,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     double chrono_mean = 0.0;
     if (nc > 0 && c.vmm_chrono == nullptr) {
         double t1[1] = {0.0};
-        for (int r = tid; r < nc; r += C::kThreads) t1[0] += c.r2[r];
+        for (int r = tid; r < nc; r += C::kThreads) t1[0] += C::rowr2(c.N)[r];
         block_reduce<C, 1, 0u>(t1, c);
         chrono_mean = t1[0] / (double)nc;
     }
@@ -1065,7 +1075,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
 #pragma unroll
                 for (int w = 0; w < CU; ++w) {
                     const int col = c0 + lane + 32 * w;
-                    const double rr = (col < ne) ? c.r2[nc + col] : 0.0;
+                    const double rr = (col < ne) ? C::rowr2(c.N)[nc + col] : 0.0;
 #pragma unroll
                     for (int u = 0; u < RU; ++u) sh[u] = fma(v[u][w], rr, sh[u]);
                 }
@@ -1078,12 +1088,12 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
                     if (r < nc) {
                         if (c.vmm_chrono != nullptr) {
                             const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
-                            for (int col = lane; col < nc; col += 32) sh[u] = fma(vr[col], c.r2[col], sh[u]);
+                            for (int col = lane; col < nc; col += 32) sh[u] = fma(vr[col], C::rowr2(c.N)[col], sh[u]);
                         }
                     } else {
                         const int ne = N - nc;
                         const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
-                        for (int col = lane; col < ne; col += 32) sh[u] = fma(vr[col], c.r2[nc + col], sh[u]);
+                        for (int col = lane; col < ne; col += 32) sh[u] = fma(vr[col], C::rowr2(c.N)[nc + col], sh[u]);
                     }
                 }
             }
@@ -1101,7 +1111,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
                     const double frac = w / (w + e);
                     w = frac * w + (1.0 - frac) * e;
                 }
-                c.w[r] = fmax(w, 1e-10);
+                C::roww()[r] = fmax(w, 1e-10);
             }
         }
     }
@@ -1186,7 +1196,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         for (int k = 0; k < 3; ++k) { C::vec(C::SV0 + k)[tid] = hy.s_0[k]; C::vec(C::US0 + k)[tid] = sqrt(hy.s_0[k]); }
     }
     for (int r = tid; r < N; r += C::kThreads) {
-        c.w[r] = 1.0;
+        C::roww()[r] = 1.0;
         if (c.vz >= 0) c.vzcol[r] = 0.0;
     }
     __syncthreads();
@@ -1218,7 +1228,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         // weights entering the Gram: 1 (init) / weight factors (drt1d.py:881-892) / scaled weights (:991-1008)
         if (!init) {
             for (int r = tid; r < N; r += C::kThreads) {
-                double w = c.w[r];
+                double w = C::roww()[r];
                 if (final_pq) {
                     w *= hy.weight_factor;
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
@@ -1226,7 +1236,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
                     if (it > 0) w = w * hy.weight_factor;
                 }
-                c.w[r] = w;
+                C::roww()[r] = w;
             }
         }
         {
@@ -1261,7 +1271,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             weights_phase<C>(c, nullptr, var_floor, false);
             PROF_ADD(4);
             for (int r = tid; r < N; r += C::kThreads) {
-                const double e = c.w[r];
+                const double e = C::roww()[r];
                 est_g[r] = e;
                 double wi = e;
                 if (hy.has_iw_prior) {  // qphb.solve_init_weight_scale, qphb.py:1471-1479
@@ -1270,7 +1280,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                     wi = 1.0 / sqrt(s_hat);
                 }
                 if (p.init_weights) p.init_weights[(size_t)b * N + r] = wi;
-                c.w[r] = wi;
+                C::roww()[r] = wi;
             }
             __syncthreads();
             it = 0;
@@ -1295,11 +1305,11 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         ++it;
         if (conv || it >= hy.max_iter) {
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
-            if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = c.w[r];
+            if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = C::roww()[r];
             if (p.resid_ss) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
                 double t2[2] = {0.0, 0.0};
                 for (int r = tid; r < N; r += C::kThreads) {
-                    if (r < c.nc) t2[0] += c.r2[r]; else t2[1] += c.r2[r];
+                    if (r < c.nc) t2[0] += C::rowr2(c.N)[r]; else t2[1] += C::rowr2(c.N)[r];
                 }
                 block_reduce<C, 2, 0u>(t2, c);
                 if (tid == 0) { p.resid_ss[2 * (size_t)b] = t2[0]; p.resid_ss[2 * (size_t)b + 1] = t2[1]; }
@@ -1337,7 +1347,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (p.n_ipm) p.n_ipm[b] = n_ipm;
         if (p.status) p.status[b] = status;
     }
-    if (fatal && p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = c.w[r];
+    if (fatal && p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = C::roww()[r];
     __syncthreads();
 }
 
@@ -1345,7 +1355,6 @@ template <class C>
 __global__ void __launch_bounds__(C::kThreads, C::MINB)
 qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     __shared__ int s_work;
-    __shared__ int s_flag;
     Ctx c;
     c.N = p.n_rows; c.n = p.n_cols; c.ns = p.n_special; c.nc = p.n_chrono;
     c.dop_a = p.dop_start; c.dop_b = p.dop_end; c.vz = p.vz_index; c.vb_a = p.vb_start; c.vb_b = p.vb_end;
@@ -1358,11 +1367,6 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     const int role = ((threadIdx.x >> 5) + blockIdx.x % 3) % C::kWarps;
     c.wr = role / C::W; c.wc = role % C::W;
     c.dv = c.wc <= c.wr;
-    c.flag = &s_flag;
-    const int npad = rows_pad(p.n_rows);
-    c.w = g_smem + C::oRows;
-    c.r2 = c.w + npad;
-    c.aux = c.r2 + npad;
     c.red_phase = 0;
 #ifdef HDRT_PROFILE
     if (threadIdx.x < 32) s_prof[threadIdx.x] = 0;
