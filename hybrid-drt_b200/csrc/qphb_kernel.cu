@@ -24,8 +24,8 @@
 //             memory ("pan"), and every tile (j, i) with j > k gets  tile += pan_j pan_i^T.
 //   Solves    u = Y (Y^T b) with Y = L^-T straight from the register tiles (DFMA + shuffle reductions).
 // Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the negated P tiles of the current QP
-// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N]
-// and one more N-vector.  The Gram staging buffers alias the pan / partial area.
+// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N].
+// The Gram staging ring lives in the tile area (the tiles are written after the last chunk).
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
 #include <stdlib.h>
@@ -36,7 +36,7 @@ namespace hdrt {
 
 constexpr int kMaxCols = 160;
 constexpr int kRedSlots = 8;
-constexpr int kNumVec = 12;
+constexpr int kNumVec = 11;
 
 // cvxopt coneqp defaults (cvxopt 1.3 coneprog.py; the reference only sets show_progress, qphb.py:25)
 constexpr double kAbsTol = 1e-7;
@@ -86,28 +86,23 @@ struct Cfg {
     static constexpr int oUnion = oRbuf + 16;
     static constexpr int oPart = oUnion;                       // QP view: NPART x NV matvec partials
     static constexpr int oBinv = oPart + NPART * NV;           //          -L_kk^-1 (64)
-    static constexpr int oScr = oBinv + 64;                    //          diagonal-tile scratch (160)
-    static constexpr int oTr = oScr + 160;                     //          per-warp transpose scratch (80 each)
-    static constexpr int oPan = oTr + 80 * kWarps;             //          TMAX tiles: column k
+    static constexpr int oPan = oBinv + 64;                    //          TMAX tiles: column k
     static constexpr int oTiles = oPan + TMAX * 64;            // NTILE x 64 negated P tiles; Gram staging ring
     static_assert(kStages * NV * kChunk <= NTILE * 64, "staging ring must fit in the tile area");
     static constexpr int oRows = oTiles + NTILE * 64;          // w[N], r2[N], aux[N]
-    enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH, SPARE };
+    enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH };
     static __device__ __forceinline__ double* vec(int k) { return g_smem + k * NV; }
     static __device__ __forceinline__ double* red() { return g_smem + oRed; }
     static __device__ __forceinline__ double* rbuf() { return g_smem + oRbuf; }
     static __device__ __forceinline__ double* part(int p) { return g_smem + oPart + p * NV; }
     static __device__ __forceinline__ double* binv() { return g_smem + oBinv; }
-    static __device__ __forceinline__ double* scr() { return g_smem + oScr; }
-    static __device__ __forceinline__ double* tr(int warp) { return g_smem + oTr + 80 * warp; }
     static __device__ __forceinline__ double* pan() { return g_smem + oPan; }
     static __device__ __forceinline__ double* tiles() { return g_smem + oTiles; }
-    // per-row vectors w[N], r2[N], aux[N] (each padded to a multiple of 8): derived from g_smem so that the
+    // per-row vectors w[N], r2[N] (each padded to a multiple of 8): derived from g_smem so that the
     // compiler emits shared-memory loads, not generic ones
     static __device__ __forceinline__ int* flag() { return reinterpret_cast<int*>(g_smem + oRbuf + 8); }   // factorisation status
     static __device__ __forceinline__ double* roww() { return g_smem + oRows; }
     static __device__ __forceinline__ double* rowr2(int N) { return g_smem + oRows + ((N + 7) & ~7); }
-    static __device__ __forceinline__ double* rowaux(int N) { return g_smem + oRows + 2 * ((N + 7) & ~7); }
     __host__ __device__ static constexpr int sidx(int a, int b) { return a * (a + 1) / 2 + b; }
 };
 
@@ -117,7 +112,7 @@ using CfgL = Cfg<20, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, 
 __host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>
 __host__ __device__ inline long long smem_doubles_cfg(int N) {
-    return (long long)C::oRows + 3LL * rows_pad(N) + 2;
+    return (long long)C::oRows + 2LL * rows_pad(N) + 2;
 }
 __host__ __device__ inline bool small_cfg(int n) { return n <= CfgS::NV; }
 __host__ __device__ inline long long smem_doubles(int N, int n) {
@@ -250,7 +245,6 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
     const int g = c.g, q = c.q, lane = c.lane;
     PROF_DECL;
     double* w2 = C::rowr2(c.N);      // w^2, zero padded to a multiple of 8
-    double* w2rv = C::rowaux(c.N);   // w^2 rv
     __syncthreads();        // previous users of the tile area and of r2 are done
     // rm chunks travel through a ring of kStages buffers inside the (still unused) tile area: the copies are L2
     // hits with a latency of a few chunks' worth of DMMA work
@@ -261,10 +255,7 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
         if (st < nchunks) stage_chunk<C>(c, st * C::kChunk, st); else cp_async_commit();
     }
     for (int r = tid; r < rows_pad(N); r += C::kThreads) {
-        double ww = 0.0, wv = 0.0;
-        if (r < N) { ww = C::roww()[r] * C::roww()[r]; wv = ww * c.rv[r]; }
-        w2[r] = ww;
-        w2rv[r] = wv;
+        w2[r] = (r < N) ? C::roww()[r] * C::roww()[r] : 0.0;
     }
     constexpr int QU = (4 * C::NV + C::kThreads - 1) / C::kThreads;  // q: lane group of 4 per column
     double qacc[QU];
@@ -296,7 +287,9 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
             }
         }
         {
-            const double2 wv = lds2(w2rv + r0 + 2 * (tid & 3));
+            const int rq = r0 + 2 * (tid & 3);       // q = -rm^T (w^2 rv): rv straight from global (issued early)
+            const double2 w2q = lds2(w2 + rq);
+            const double2 wv = make_double2(rq < N ? w2q.x * c.rv[rq] : 0.0, rq + 1 < N ? w2q.y * c.rv[rq + 1] : 0.0);
 #pragma unroll
             for (int u = 0; u < QU; ++u) {
                 const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
@@ -591,7 +584,6 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
     }
     double* panr = C::pan() + 64 * c.wr + 2 * lane;   // tile j = W a + wr: + 64 W a
     double* panc = C::pan() + 64 * c.wc + 2 * lane;
-    double* trs = C::tr(threadIdx.x >> 5);
     PROF_ADD(16);
     // the diagonal tile of column 0
     if (c.wr == 0 && c.wc == 0) {
