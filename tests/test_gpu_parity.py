@@ -362,3 +362,33 @@ def test_mapping_drtmd_against_the_reference():
     assert md2.obs_fit_status.all() and md2.obs_tau_indices[6] is not None
     with pytest.raises(ValueError):
         md2.add_observation([0, 0], None, (g['freq'],))
+
+
+def test_full_size_c2_batch_properties():
+    """BASELINE config C2 at its full size (10,000 spectra) through the public API: size-independent properties,
+    plus the oracle on a few members of the big batch."""
+    from hybdrt_b200 import synth
+    from hybdrt_b200.models import DRT
+    from oracle import drt_oracle as orc
+    freq, z = synth.make_eis_batch(10000, seed=0)
+    drt = DRT()
+    res = drt.fit_eis_batch(freq, z)
+    h = res.host(['x', 'status', 'n_outer', 'n_ipm', 'weights'])
+    st = h['status']
+    assert np.all((st & 3) != 0) and np.all((st & 3) != 3) and not np.any(st & (8 | 16))
+    # interior-point iterates: the bound holds to the solver's feasibility tolerance (cvxopt feastol 1e-7, relative)
+    assert np.all(np.isfinite(h['x'])) and h['x'].min() > -1e-5 and np.all(h['weights'] > 0)
+    assert 2 <= h['n_outer'].min() and h['n_outer'].max() <= 50
+    idx = np.random.default_rng(1).permutation(10000)[:24]
+    sub = drt.fit_eis_batch(freq, z[idx]).host(['x', 'n_ipm'])
+    assert np.array_equal(sub['x'], h['x'][idx]) and np.array_equal(sub['n_ipm'], h['n_ipm'][idx])   # batch independent
+    fp = res.fit_parameters()
+    zp = res.predict_z()
+    rel = np.linalg.norm(zp - z, axis=1) / np.linalg.norm(z, axis=1)
+    assert np.median(rel) < 3e-2 and rel.max() < 0.2        # every spectrum is fitted to about its noise level (0.5 % of Rp)
+    prep = orc.EisPrep(freq)
+    for b in idx[:3]:
+        ref = prep.fit(z[b])
+        assert int(h['n_outer'][b]) == ref['n_outer']
+        assert rel_err(h['x'][b], ref['x']) < FIT_TOL
+        assert abs(fp['R_inf'][b] - ref['params']['R_inf']) < FIT_TOL * abs(ref['params']['R_inf'])
