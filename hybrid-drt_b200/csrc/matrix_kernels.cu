@@ -98,29 +98,129 @@ __global__ void lookup_kernel(double eps, int grid_points, int quad_points, doub
 }
 
 // ---- impedance matrix (mat1d.py:212-374) ---------------------------------------------------------
-// grid.x = n_grids, grid.y = row tiles.  freq/tau staged in shared memory.
-__global__ void impedance_interp_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int nf,
-                                        int nb, const double* __restrict__ re_x, const double* __restrict__ re_v,
-                                        const double* __restrict__ im_x, const double* __restrict__ im_v,
-                                        int npts, double* __restrict__ a_re, double* __restrict__ a_im,
-                                        int rows_per_cta) {
+// Generic path (lookup tables too large for shared memory): grid.x = n_grids, grid.y = row tiles, tables read
+// through the read-only path.
+__global__ void impedance_interp_global_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int nf,
+                                               int nb, const double* __restrict__ re_x, const double* __restrict__ re_v,
+                                               const double* __restrict__ im_x, const double* __restrict__ im_v,
+                                               int npts, double* __restrict__ a_re, double* __restrict__ a_im,
+                                               int rows_per_cta) {
     extern __shared__ double sm[];
     double* s_tau = sm;
     double* s_om = sm + nb;
     const int g = blockIdx.x;
     const int r0 = blockIdx.y * rows_per_cta;
     const int rows = min(rows_per_cta, nf - r0);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_tau[i] = tau[(size_t)g * nb + i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_tau[i] = log(tau[(size_t)g * nb + i]);
     for (int i = threadIdx.x; i < rows; i += blockDim.x)
-        s_om[i] = freq[(size_t)g * nf + r0 + i] * 2.0 * 3.141592653589793;  // frequencies * 2 * np.pi
+        s_om[i] = log(freq[(size_t)g * nf + r0 + i] * 2.0 * 3.141592653589793);  // frequencies * 2 * np.pi
     __syncthreads();
     const size_t base = ((size_t)g * nf + r0) * nb;
     const InterpGrid gre = interp_grid(re_x, npts), gim = interp_grid(im_x, npts);
     for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
         const int rr = idx / nb, m = idx - rr * nb;
-        const double x = log(s_om[rr] * s_tau[m]);
+        const double x = s_om[rr] + s_tau[m];
         a_re[base + idx] = interp_clamped(x, re_x, re_v, npts, gre);
         a_im[base + idx] = interp_clamped(x, im_x, im_v, npts, gim);
+    }
+}
+
+// Production path: persistent CTAs (two per SM) keep both lookup tables in shared memory together with the
+// interval slopes (computed once per CTA with the same division numpy.interp does per evaluation), so an entry
+// costs ln(omega_n) + ln(tau_m) (logs once per row / column of the work item), one index guess and a handful of
+// shared-memory loads -- no log, no division: the kernel is bound by the HBM writes.  ln(omega tau) is formed as
+// ln(omega) + ln(tau); the reference itself evaluates entries either way (full evaluation, or first row / column
+// + Toeplitz fill, mat1d.py:341-372), the two differ at the 1e-16 level.
+// A work item is `rows_per_item` rows of one grid; stores are 16-byte, streaming (the output is not re-read).
+struct SmemTable {
+    const double* x;
+    const double* v;
+    const double* s;
+    double x0, xn, inv_dx, v0, vn;
+};
+__device__ __forceinline__ double interp_smem(double x, const SmemTable& t, int npts) {
+    if (isnan(x)) return x;
+    if (x > t.xn) return t.vn;
+    if (x < t.x0) return t.v0;
+    int j = (int)((x - t.x0) * t.inv_dx);
+    j = max(0, min(npts - 1, j));
+    while (j > 0 && t.x[j] > x) --j;
+    while (j < npts - 1 && t.x[j + 1] <= x) ++j;
+    if (j == npts - 1) return t.vn;
+    return __dadd_rn(__dmul_rn(t.s[j], x - t.x[j]), t.v[j]);
+}
+
+constexpr int kIThreads = 512;
+
+__global__ void __launch_bounds__(kIThreads, 2)
+impedance_interp_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int n_grids, int nf, int nb,
+                        const double* __restrict__ re_x, const double* __restrict__ re_v,
+                        const double* __restrict__ im_x, const double* __restrict__ im_v, int npts,
+                        double* __restrict__ a_re, double* __restrict__ a_im, int rows_per_item, int tiles_per_grid) {
+    extern __shared__ __align__(16) double sm[];
+    double* t_rx = sm;
+    double* t_rv = t_rx + npts;
+    double* t_rs = t_rv + npts;
+    double* t_ix = t_rs + npts;
+    double* t_iv = t_ix + npts;
+    double* t_is = t_iv + npts;
+    double* s_vec = t_is + npts;                      // two buffers of [nb ln tau | rows_per_item ln omega]
+    const int vlen = nb + rows_per_item;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < npts; i += kIThreads) {
+        t_rx[i] = __ldg(re_x + i); t_rv[i] = __ldg(re_v + i);
+        t_ix[i] = __ldg(im_x + i); t_iv[i] = __ldg(im_v + i);
+    }
+    __syncthreads();
+    for (int i = tid; i < npts - 1; i += kIThreads) {
+        t_rs[i] = (t_rv[i + 1] - t_rv[i]) / (t_rx[i + 1] - t_rx[i]);
+        t_is[i] = (t_iv[i + 1] - t_iv[i]) / (t_ix[i + 1] - t_ix[i]);
+    }
+    SmemTable tr, ti;
+    tr.x = t_rx; tr.v = t_rv; tr.s = t_rs; tr.x0 = t_rx[0]; tr.xn = t_rx[npts - 1]; tr.v0 = t_rv[0]; tr.vn = t_rv[npts - 1];
+    ti.x = t_ix; ti.v = t_iv; ti.s = t_is; ti.x0 = t_ix[0]; ti.xn = t_ix[npts - 1]; ti.v0 = t_iv[0]; ti.vn = t_iv[npts - 1];
+    tr.inv_dx = (double)(npts - 1) / (tr.xn - tr.x0);
+    ti.inv_dx = (double)(npts - 1) / (ti.xn - ti.x0);
+    const long long items = (long long)n_grids * tiles_per_grid;
+    int buf = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
+        const int g = (int)(item / tiles_per_grid);
+        const int r0 = (int)(item - (long long)g * tiles_per_grid) * rows_per_item;
+        const int rows = min(rows_per_item, nf - r0);
+        double* s_lt = s_vec + buf * vlen;
+        double* s_lw = s_lt + nb;
+        for (int i = tid; i < nb + rows; i += kIThreads) {
+            if (i < nb) s_lt[i] = log(tau[(size_t)g * nb + i]);
+            else s_lw[i - nb] = log(freq[(size_t)g * nf + r0 + (i - nb)] * 2.0 * 3.141592653589793);  // 2 pi f
+        }
+        __syncthreads();   // also orders the slope table on the first pass; the other buffer is free by now
+        const size_t base = ((size_t)g * nf + r0) * nb;
+        const int cnt = rows * nb;
+        const int head = (int)(base & 1);               // element offset to the first 16-byte aligned pair
+        if (tid == 0 && head) {
+            const double x = s_lw[0] + s_lt[0];
+            a_re[base] = interp_smem(x, tr, npts);
+            a_im[base] = interp_smem(x, ti, npts);
+        }
+        const int npairs = (cnt - head) >> 1;
+        for (int p = tid; p < npairs; p += kIThreads) {
+            const int idx = head + 2 * p;
+            const int rr = idx / nb, m = idx - rr * nb;
+            const bool wrap = (m + 1 == nb);
+            const double xa = s_lw[rr] + s_lt[m];
+            const double xb = wrap ? s_lw[rr + 1] + s_lt[0] : s_lw[rr] + s_lt[m + 1];
+            const double2 vr = make_double2(interp_smem(xa, tr, npts), interp_smem(xb, tr, npts));
+            const double2 vi = make_double2(interp_smem(xa, ti, npts), interp_smem(xb, ti, npts));
+            __stcs(reinterpret_cast<double2*>(a_re + base + idx), vr);
+            __stcs(reinterpret_cast<double2*>(a_im + base + idx), vi);
+        }
+        if (tid == kIThreads - 1 && ((cnt - head) & 1)) {
+            const int idx = cnt - 1;
+            const int rr = idx / nb, m = idx - rr * nb;
+            const double x = s_lw[rr] + s_lt[m];
+            a_re[base + idx] = interp_smem(x, tr, npts);
+            a_im[base + idx] = interp_smem(x, ti, npts);
+        }
     }
 }
 
@@ -257,6 +357,75 @@ __global__ void eis_vmm_kernel(const double* __restrict__ freq, int n_grids, int
     }
 }
 
+// ---- chrono variance-estimation matrix (mat1d.py:455-490, utils/chrono.py:5-39) ----------------------
+// error_structure=None: Gaussian RBF in transformed time (log time since the last step, segments laid end to
+// end), no correlation between steps, rows normalised.  One CTA per (grid, block of rows); every CTA rebuilds
+// the transformed-time vector of its grid in shared memory (n_t logs against rows x n_t exps of real work).
+constexpr int kVRows = 32;   // rows per CTA, four per warp
+
+__global__ void chrono_vmm_kernel(const double* __restrict__ times, const double* __restrict__ step_times, int nt,
+                                  int n_steps, double vmm_eps, int uniform, double* __restrict__ vmm) {
+    extern __shared__ __align__(16) double sm[];
+    double* s_tt = sm;                                       // [nt] transformed times
+    double* s_off = sm + nt;                                 // [n_steps] segment offsets
+    int* s_seg = reinterpret_cast<int*>(s_off + n_steps);    // [nt] segment index (0 = before the first step)
+    __shared__ double s_red[kMThreads / 32];
+    const int g = blockIdx.x, r0 = blockIdx.y * kVRows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* t = times + (size_t)g * nt;
+    const double* st = step_times + (size_t)g * n_steps;
+    double* out = vmm + (size_t)g * nt * nt;
+    if (uniform) {
+        for (int rr = warp; rr < kVRows && r0 + rr < nt; rr += kMThreads / 32)
+            for (int j = lane; j < nt; j += 32) out[(size_t)(r0 + rr) * nt + j] = 1.0 / (double)nt;
+        return;
+    }
+    // t_sample = min(diff(times))
+    double mn = INFINITY;
+    for (int i = tid; i + 1 < nt; i += kMThreads) mn = fmin(mn, t[i + 1] - t[i]);
+    mn = -warp_max(-mn);
+    if (lane == 0) s_red[warp] = mn;
+    __syncthreads();
+    double t_sample = s_red[0];
+    for (int w = 1; w < kMThreads / 32; ++w) t_sample = fmin(t_sample, s_red[w]);
+    const double trans_base = log(t_sample / 4.0);
+    if (tid == 0) {                                          // trans_offsets = [0, cumsum(log(diff(start_times)) - base)]
+        double acc = 0.0;
+        s_off[0] = 0.0;
+        for (int k = 1; k < n_steps; ++k) {
+            acc += log(st[k] - st[k - 1]) - trans_base;
+            s_off[k] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nt; i += kMThreads) {
+        const double ti = t[i];
+        int k = -1;
+        for (int m = 0; m < n_steps; ++m) if (ti >= st[m]) k = m;   // start_times are ascending
+        double tt;
+        if (k < 0) {
+            tt = ti - st[0];                                 // before the first step: linear
+        } else {
+            const double td = fmax(ti - st[k], t_sample / 2.0);
+            tt = s_off[k] + log(td) - trans_base;
+        }
+        s_tt[i] = tt;
+        s_seg[i] = k + 1;
+    }
+    __syncthreads();
+    for (int rr = warp; rr < kVRows; rr += kMThreads / 32) {
+        const int r = r0 + rr;
+        if (r >= nt) break;
+        const double tr = s_tt[r];
+        const int sr = s_seg[r];
+        double sum = 0.0;
+        for (int j = lane; j < nt; j += 32) sum += (s_seg[j] == sr) ? rbf(tr - s_tt[j], vmm_eps) : 0.0;
+        sum = warp_sum(sum);
+        for (int j = lane; j < nt; j += 32)
+            out[(size_t)r * nt + j] = ((s_seg[j] == sr) ? rbf(tr - s_tt[j], vmm_eps) : 0.0) / sum;
+    }
+}
+
 // ---- DOP impedance columns (phasance.py:19-37,61-80,108-118) --------------------------------------
 struct cplx { double re, im; };
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
@@ -356,13 +525,31 @@ extern "C" int hdrt_build_impedance(int mode, const double* freq, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == HDRT_MODE_INTERP) {
         if (!re_x || !re_v || !im_x || !im_v || grid_points < 2) { set_error("interp mode needs lookup tables"); return HDRT_ERR_ARG; }
-        // aim for >= 4 waves of 148 SMs; each CTA writes rows_per_cta * nb * 16 bytes
-        int rows_per_cta = nf;
-        while (rows_per_cta > 8 && (long long)n_grids * ((nf + rows_per_cta - 1) / rows_per_cta) < 148 * 8) rows_per_cta = (rows_per_cta + 1) / 2;
-        dim3 grid(n_grids, (nf + rows_per_cta - 1) / rows_per_cta);
-        const size_t smem = sizeof(double) * (nb + rows_per_cta);
-        impedance_interp_kernel<<<grid, kMThreads, smem, st>>>(freq, tau, nf, nb, re_x, re_v, im_x, im_v, grid_points,
-                                                               a_re, a_im, rows_per_cta);
+        int dev = 0, sms = 148;
+        HDRT_CUDA_CHECK(cudaGetDevice(&dev));
+        HDRT_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int ctas = 2 * sms;
+        // work items: whole grids when there are enough of them, otherwise row tiles (>= 4 rows) so that every
+        // CTA of the persistent grid has work
+        int rows_per_item = nf;
+        while (rows_per_item > 4 && (long long)n_grids * ((nf + rows_per_item - 1) / rows_per_item) < ctas) rows_per_item = (rows_per_item + 1) / 2;
+        const int tiles = (nf + rows_per_item - 1) / rows_per_item;
+        const size_t smem = sizeof(double) * (6 * (size_t)grid_points + 2 * (size_t)(nb + rows_per_item));
+        if (smem <= 110 * 1024) {
+            HDRT_CUDA_CHECK(cudaFuncSetAttribute(impedance_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long items = (long long)n_grids * tiles;
+            const int grid = (int)(items < ctas ? items : ctas);
+            impedance_interp_kernel<<<grid, kIThreads, smem, st>>>(freq, tau, n_grids, nf, nb, re_x, re_v, im_x, im_v,
+                                                                   grid_points, a_re, a_im, rows_per_item, tiles);
+        } else {
+            int rows_per_cta = nf;
+            while (rows_per_cta > 8 && (long long)n_grids * ((nf + rows_per_cta - 1) / rows_per_cta) < 148 * 8) rows_per_cta = (rows_per_cta + 1) / 2;
+            dim3 grid(n_grids, (nf + rows_per_cta - 1) / rows_per_cta);
+            const size_t smem_g = sizeof(double) * (nb + rows_per_cta);
+            if (smem_g > 48 * 1024) { set_error("grid too large for the staging buffer"); return HDRT_ERR_UNSUPPORTED; }
+            impedance_interp_global_kernel<<<grid, kMThreads, smem_g, st>>>(freq, tau, nf, nb, re_x, re_v, im_x, im_v,
+                                                                            grid_points, a_re, a_im, rows_per_cta);
+        }
     } else if (mode == HDRT_MODE_TRAPZ) {
         if (quad_points < 2) { set_error("quad_points < 2"); return HDRT_ERR_ARG; }
         const long long total = (long long)n_grids * nf * nb;
@@ -425,6 +612,22 @@ extern "C" int hdrt_build_eis_vmm(const double* freq, int n_grids, int nf, doubl
     const long long rows = (long long)n_grids * 2 * nf;
     eis_vmm_kernel<<<grid_for(rows * 32, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(freq, n_grids, nf, vmm_eps,
                                                                                          reim_cor, uniform, vmm);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_chrono_vmm(const double* times, const double* step_times, int n_grids, int nt, int n_steps,
+                                     double vmm_eps, int uniform, double* vmm, void* stream) {
+    if (!times || !step_times || !vmm || n_grids < 0 || nt < 2 || n_steps <= 0) {
+        set_error("hdrt_build_chrono_vmm: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    if (n_grids == 0) return HDRT_OK;
+    const size_t smem = sizeof(double) * ((size_t)nt + n_steps) + sizeof(int) * (size_t)nt;
+    if (smem > 200 * 1024) { set_error("hdrt_build_chrono_vmm: %d samples do not fit the staging buffer", nt); return HDRT_ERR_UNSUPPORTED; }
+    HDRT_CUDA_CHECK(cudaFuncSetAttribute(chrono_vmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_grids, (nt + kVRows - 1) / kVRows);
+    chrono_vmm_kernel<<<grid, kMThreads, smem, (cudaStream_t)stream>>>(times, step_times, nt, n_steps, vmm_eps, uniform, vmm);
     HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }

@@ -103,6 +103,7 @@ struct Cfg {
     static __device__ __forceinline__ int* flag() { return reinterpret_cast<int*>(g_smem + oRbuf + 8); }   // factorisation status
     static __device__ __forceinline__ double* roww() { return g_smem + oRows; }
     static __device__ __forceinline__ double* rowr2(int N) { return g_smem + oRows + ((N + 7) & ~7); }
+    static __device__ __forceinline__ double* rowu(int N) { return g_smem + oRows + 2 * ((N + 7) & ~7); }   // outlier fits only
     __host__ __device__ static constexpr int sidx(int a, int b) { return a * (a + 1) / 2 + b; }
 };
 
@@ -111,12 +112,13 @@ using CfgL = Cfg<20, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, 
 
 __host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>
-__host__ __device__ inline long long smem_doubles_cfg(int N) {
-    return (long long)C::oRows + 2LL * rows_pad(N) + 2;
+__host__ __device__ inline long long smem_doubles_cfg(int N, int row_vectors) {
+    return (long long)C::oRows + (long long)row_vectors * rows_pad(N) + 2;
 }
 __host__ __device__ inline bool small_cfg(int n) { return n <= CfgS::NV; }
-__host__ __device__ inline long long smem_doubles(int N, int n) {
-    return small_cfg(n) ? smem_doubles_cfg<CfgS>(N) : smem_doubles_cfg<CfgL>(N);
+// row_vectors: 2 (w, r^2) or 3 (+ T^1/2 r^2 of the outlier error structure)
+__host__ __device__ inline long long smem_doubles(int N, int n, int row_vectors = 2) {
+    return small_cfg(n) ? smem_doubles_cfg<CfgS>(N, row_vectors) : smem_doubles_cfg<CfgL>(N, row_vectors);
 }
 
 struct Ctx {
@@ -132,6 +134,8 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
+    double* t_out;  // global, per spectrum: outlier_t (only with outlier_p)
+    double outlier_p;  // < 0: no outlier error structure
     int red_phase;
 };
 
@@ -994,10 +998,82 @@ __device__ __noinline__ void hyper_block(Ctx& cref, const BlockHyp& hpref, int s
 }
 
 // ------------------------------------------------------------------------------------------------
+// Rows rb + u kWarps (u < 4) of vmm @ uin for one warp; uin is a per-row vector in shared memory.  vmm is block
+// diagonal: chrono rows x chrono columns (dense, or NULL = uniform: the caller substitutes the mean), EIS rows x
+// EIS columns.  The sums are warp-reduced (valid in every lane).
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void vmm_rows(const Ctx& c, const double* uin, int rb, double (&sh)[4]) {
+    constexpr int RU = 4, CU = (C::NV + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int N = c.N, nc = c.nc;
+#pragma unroll
+    for (int u = 0; u < RU; ++u) sh[u] = 0.0;
+    const bool all_eis = rb >= nc;   // rows of a pass are ascending: every row of it is an EIS row
+    if (all_eis) {
+        const int ne = N - nc;
+        for (int c0 = 0; c0 < ne; c0 += 32 * CU) {
+            double v[RU][CU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const double* __restrict__ vr = c.vmm_eis + (size_t)(min(rb + u * C::kWarps, N - 1) - nc) * ne;
+#pragma unroll
+                for (int w = 0; w < CU; ++w) v[u][w] = vr[min(c0 + lane + 32 * w, ne - 1)];
+            }
+#pragma unroll
+            for (int w = 0; w < CU; ++w) {
+                const int col = c0 + lane + 32 * w;
+                const double rr = (col < ne) ? uin[nc + col] : 0.0;
+#pragma unroll
+                for (int u = 0; u < RU; ++u) sh[u] = fma(v[u][w], rr, sh[u]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = rb + u * C::kWarps;
+            if (r < N) {
+                if (r < nc) {
+                    if (c.vmm_chrono != nullptr) {
+                        // dense chrono block (flexible error structure): rows are long (n_chrono columns); four
+                        // independent loads in flight per lane
+                        const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        int col = lane;
+                        for (; col + 96 < nc; col += 128) {
+                            const double v0 = vr[col], v1 = vr[col + 32], v2 = vr[col + 64], v3 = vr[col + 96];
+                            a0 = fma(v0, uin[col], a0);
+                            a1 = fma(v1, uin[col + 32], a1);
+                            a2 = fma(v2, uin[col + 64], a2);
+                            a3 = fma(v3, uin[col + 96], a3);
+                        }
+                        for (; col < nc; col += 32) a0 = fma(vr[col], uin[col], a0);
+                        sh[u] = (a0 + a1) + (a2 + a3);
+                    }
+                } else {
+                    const int ne = N - nc;
+                    const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
+                    for (int col = lane; col < ne; col += 32) sh[u] = fma(vr[col], uin[nc + col], sh[u]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) sh[u] = warp_sum(sh[u]);
+}
+
+// diag(vmm)[r] (qphb.py:1646: the first initialisation pass with outliers excludes the point itself)
+__device__ __forceinline__ double vmm_diag_at(const Ctx& c, int r) {
+    if (r < c.nc) return c.vmm_chrono ? c.vmm_chrono[(size_t)r * c.nc + r] : 1.0 / (double)c.nc;
+    const int ne = c.N - c.nc;
+    return c.vmm_eis[(size_t)(r - c.nc) * ne + (r - c.nc)];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double var_floor, bool update_vz) {
+__device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double var_floor, bool update_vz, bool base) {
     Ctx c = cref;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, n = c.n, nc = c.nc;
@@ -1041,61 +1117,66 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     }
     __syncthreads();
     PROF_ADD(11);
-    double chrono_mean = 0.0;
-    if (nc > 0 && c.vmm_chrono == nullptr) {
-        double t1[1] = {0.0};
-        for (int r = tid; r < nc; r += C::kThreads) t1[0] += C::rowr2(c.N)[r];
-        block_reduce<C, 1, 0u>(t1, c);
-        chrono_mean = t1[0] / (double)nc;
-    }
-    // variance estimate s_hat = vmm r2 (block diagonal: chrono rows x chrono columns, EIS rows x EIS columns)
-    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
-        double sh[RU];
-#pragma unroll
-        for (int u = 0; u < RU; ++u) sh[u] = 0.0;
-        const bool all_eis = rb >= nc;   // rows of a pass are ascending: every row of it is an EIS row
-        if (all_eis) {
-            const int ne = N - nc;
-            for (int c0 = 0; c0 < ne; c0 += 32 * CU) {
-                double v[RU][CU];
-#pragma unroll
-                for (int u = 0; u < RU; ++u) {
-                    const double* __restrict__ vr = c.vmm_eis + (size_t)(min(rb + u * C::kWarps, N - 1) - nc) * ne;
-#pragma unroll
-                    for (int w = 0; w < CU; ++w) v[u][w] = vr[min(c0 + lane + 32 * w, ne - 1)];
-                }
-#pragma unroll
-                for (int w = 0; w < CU; ++w) {
-                    const int col = c0 + lane + 32 * w;
-                    const double rr = (col < ne) ? C::rowr2(c.N)[nc + col] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < RU; ++u) sh[u] = fma(v[u][w], rr, sh[u]);
-                }
-            }
-        } else {
+    const bool uniform_chrono = nc > 0 && c.vmm_chrono == nullptr;
+    const bool outl = c.outlier_p >= 0.0;
+    const double* uin = C::rowr2(c.N);
+    if (outl) {
+        // qphb.solve_outlier_t (qphb.py:1497-1519): s_bar = vmm r^2, t = 1 - P(outlier | r); the averaging matrix
+        // then becomes T^1/2 vmm T^1/2 + (I - T) (qphb.outlier_tvt :1522-1538), applied below without forming it
+        const double p = c.outlier_p;
+        double mean1 = 0.0;
+        if (uniform_chrono) {
+            double t1[1] = {0.0};
+            for (int r = tid; r < nc; r += C::kThreads) t1[0] += uin[r];
+            block_reduce<C, 1, 0u>(t1, c);
+            mean1 = t1[0] / (double)nc;
+        }
+        for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+            double sh[RU];
+            vmm_rows<C>(c, uin, rb, sh);
 #pragma unroll
             for (int u = 0; u < RU; ++u) {
                 const int r = rb + u * C::kWarps;
-                if (r < N) {
-                    if (r < nc) {
-                        if (c.vmm_chrono != nullptr) {
-                            const double* __restrict__ vr = c.vmm_chrono + (size_t)r * nc;
-                            for (int col = lane; col < nc; col += 32) sh[u] = fma(vr[col], C::rowr2(c.N)[col], sh[u]);
-                        }
-                    } else {
-                        const int ne = N - nc;
-                        const double* __restrict__ vr = c.vmm_eis + (size_t)(r - nc) * ne;
-                        for (int col = lane; col < ne; col += 32) sh[u] = fma(vr[col], C::rowr2(c.N)[nc + col], sh[u]);
-                    }
+                if (lane == 0 && r < N) {
+                    const double r2 = uin[r];
+                    double s_bar = (r < nc && uniform_chrono) ? mean1 : sh[u];
+                    if (base) { const double d = vmm_diag_at(c, r); s_bar = (s_bar - d * r2) / (1.0 - d); }
+                    const double sd = sqrt(s_bar), ar = sqrt(r2);
+                    const double k2pi = 2.5066282746310002;   // sqrt(2 pi)
+                    const double pdf_in = 1.0 / (sd * k2pi) * exp(-0.5 * r2 / (sd * sd));
+                    const double pdf_out = 1.0 / (ar * k2pi) * exp(-0.5 * r2 / (ar * ar));
+                    double t = 1.0 - p * pdf_out / ((1.0 - p) * pdf_in + p * pdf_out);
+                    if (sd > ar) t = 1.0;
+                    c.t_out[r] = t;
+                    C::rowu(c.N)[r] = sqrt(t) * r2;
                 }
             }
         }
+        __syncthreads();
+        uin = C::rowu(c.N);
+    }
+    double chrono_mean = 0.0;
+    if (uniform_chrono) {
+        double t1[1] = {0.0};
+        for (int r = tid; r < nc; r += C::kThreads) t1[0] += uin[r];
+        block_reduce<C, 1, 0u>(t1, c);
+        chrono_mean = t1[0] / (double)nc;
+    }
+    // variance estimate s_hat = vmm_eff r2 (block diagonal: chrono rows x chrono columns, EIS rows x EIS columns)
+    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+        double sh[RU];
+        vmm_rows<C>(c, uin, rb, sh);
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
             const int r = rb + u * C::kWarps;
-            double s_hat = warp_sum(sh[u]);
-            if (r < nc && c.vmm_chrono == nullptr) s_hat = chrono_mean;
+            double s_hat = sh[u];
+            if (r < nc && uniform_chrono) s_hat = chrono_mean;
             if (lane == 0 && r < N) {
+                if (base) { const double d = vmm_diag_at(c, r); s_hat = (s_hat - d * uin[r]) / (1.0 - d); }
+                if (outl) {
+                    const double t = c.t_out[r];
+                    s_hat = sqrt(t) * s_hat + (1.0 - t) * C::rowr2(c.N)[r];
+                }
                 if (s_hat < var_floor) s_hat = var_floor;
                 double w = 1.0 / sqrt(s_hat);
                 if (est != nullptr) {
@@ -1165,6 +1246,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     c.vmm_chrono = p.vmm_chrono ? p.vmm_chrono + (size_t)b * p.vmm_chrono_stride : nullptr;
     c.pen = p.pen + (size_t)b * p.pen_stride;
     c.vzcol = p.vz_col ? p.vz_col + (size_t)b * N : nullptr;
+    const bool outl = hy.has_outlier_p != 0;
+    c.outlier_p = outl ? hy.outlier_p : -1.0;
+    c.t_out = outl ? p.outlier_t + (size_t)b * N : nullptr;
     double* est_g = p.est_weights + (size_t)b * N;
 
     // var floor = var(y) * 1e-7 (qphb.py:1560-1561)
@@ -1211,7 +1295,8 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     for (int k = 0; k < 3; ++k) f.use[k] = hy.derivative_weights[k] > 0.0;
     double xi = 1e-6;  // drt1d.py:612
     double fun = 0.0;
-    int it = -1;       // -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681)
+    int it = outl ? -2 : -1;   // -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p the
+                               // initialisation runs twice (-2, -1), the second time weighted by the first estimate
     bool conv = false, fatal = false, final_pq = false;
 #pragma unroll 1
     while (true) {
@@ -1260,8 +1345,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         __syncthreads();
         if (init) {
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
-            weights_phase<C>(c, nullptr, var_floor, false);
+            weights_phase<C>(c, nullptr, var_floor, false, outl);
             PROF_ADD(4);
+            if (it == -2) { it = -1; continue; }   // qphb.py:1634-1655: second pass with w = est_weights
             for (int r = tid; r < N; r += C::kThreads) {
                 const double e = C::roww()[r];
                 est_g[r] = e;
@@ -1284,7 +1370,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         hyper_block<C>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
         if (c.dop_a >= 0) hyper_block<C>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
         PROF_ADD(3);
-        weights_phase<C>(c, est_g, var_floor, c.vz >= 0);
+        weights_phase<C>(c, est_g, var_floor, c.vz >= 0, false);
         PROF_ADD(4);
         {   // convergence, qphb.py:597-603,969-970
             const bool act = tid < n;
@@ -1396,6 +1482,13 @@ __global__ void fp64_probe_kernel(double* out, int iters) {
 
 using namespace hdrt;
 
+static long long qphb_smem_bytes(int n_rows, int n_cols, int row_vectors) {
+    if (n_rows <= 0 || n_cols <= 0 || n_cols > kMaxCols) return -1;
+    const long long bytes = smem_doubles(n_rows, n_cols, row_vectors) * 8;
+    if (bytes > 227 * 1024) return -1;
+    return bytes;
+}
+
 extern "C" long long hdrt_qphb_smem_bytes(int n_rows, int n_cols) {
     if (n_rows <= 0 || n_cols <= 0 || n_cols > kMaxCols) return -1;
     const long long bytes = smem_doubles(n_rows, n_cols) * 8;
@@ -1436,7 +1529,11 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (p.dop_start >= 0 && (p.dop_end <= p.dop_start || p.dop_end > p.n_special)) { set_error("invalid DOP range"); return HDRT_ERR_ARG; }
     if (p.dist_var && (!p.eval_mat || p.n_eval <= 0)) { set_error("dist_var needs eval_mat and n_eval > 0"); return HDRT_ERR_ARG; }
     if (p.n_cols > kMaxCols) { set_error("n_cols %d > %d unsupported", p.n_cols, kMaxCols); return HDRT_ERR_UNSUPPORTED; }
-    const long long smem = hdrt_qphb_smem_bytes(p.n_rows, p.n_cols);
+    if (p.hyp.has_outlier_p && (!p.outlier_t || !(p.hyp.outlier_p > 0.0) || !(p.hyp.outlier_p < 1.0))) {
+        set_error("outlier_p must lie in (0, 1) and needs the outlier_t buffer");
+        return HDRT_ERR_ARG;
+    }
+    const long long smem = qphb_smem_bytes(p.n_rows, p.n_cols, p.hyp.has_outlier_p ? 3 : 2);
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));

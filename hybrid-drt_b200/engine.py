@@ -31,6 +31,7 @@ class Hypers(C.Structure):
         ('xtol', C.c_double), ('weight_factor', C.c_double),
         ('chrono_weight_factor', C.c_double), ('eis_weight_factor', C.c_double),
         ('has_iw_prior', C.c_int), ('max_iter', C.c_int),
+        ('outlier_p', C.c_double), ('has_outlier_p', C.c_int), ('reserved_', C.c_int),
     ]
 
 
@@ -53,7 +54,7 @@ class Problem(C.Structure):
         ('s_vectors', _P), ('rho', _P), ('dop_rho', _P), ('xmx_norms', _P), ('dop_xmx_norms', _P),
         ('fun', _P), ('vz_col', _P), ('p_matrix', _P), ('q_vector', _P),
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
-        ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P),
+        ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P),
     ]
 
 
@@ -85,6 +86,7 @@ def load_library():
                                         _P, _P, C.c_int, C.c_int, _P, _P]
     lib.hdrt_build_penalty.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P]
     lib.hdrt_build_eis_vmm.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]
+    lib.hdrt_build_chrono_vmm.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P]
     lib.hdrt_build_dop_z.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
     lib.hdrt_default_hypers.argtypes = [C.POINTER(Hypers)]
     lib.hdrt_default_hypers.restype = None
@@ -98,7 +100,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     'hdrt_version', 'hdrt_last_error', 'hdrt_create', 'hdrt_destroy', 'hdrt_sm_count', 'hdrt_build_lookup',
-    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_dop_z',
+    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z',
     'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64',
 ]
 
@@ -240,6 +242,17 @@ class Engine:
         self.launches += 1
         return vmm
 
+    def build_chrono_vmm(self, times, step_times, vmm_eps=4, uniform=False):
+        """mat1d.construct_chrono_var_matrix. times [G,nt], step_times [G,ns] -> [G,nt,nt]."""
+        times = self.dev(times).reshape(-1, np.shape(times)[-1])
+        st = self.dev(step_times).reshape(-1, np.shape(step_times)[-1])
+        g, nt = times.shape
+        vmm = self.empty(g, nt, nt)
+        self._check(self.lib.hdrt_build_chrono_vmm(_ptr(times), _ptr(st), g, nt, st.shape[1], float(vmm_eps),
+                                                   int(bool(uniform)), _ptr(vmm), self._stream()))
+        self.launches += 1
+        return vmm
+
     def build_dop_z(self, freq, nu, nu_eps):
         """phasance.construct_phasor_z_matrix (gaussian). freq [G,nf], nu [n_nu] -> complex128 [G,nf,n_nu]."""
         freq = self.dev(freq).reshape(-1, np.shape(freq)[-1])
@@ -318,6 +331,8 @@ class Engine:
             p.dist_var = _ptr(buf('dist_var', b, eval_mat.shape[0]))
         if want_resid:
             p.resid_ss = _ptr(buf('resid_ss', b, 2))
+        if hyp.has_outlier_p:
+            p.outlier_t = _ptr(buf('outlier_t', b, n_rows))
         p.n_outer = _ptr(buf('n_outer', b, dtype=torch.int32))
         p.n_ipm = _ptr(buf('n_ipm', b, dtype=torch.int32))
         p.status = _ptr(buf('status', b, dtype=torch.int32))

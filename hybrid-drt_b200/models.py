@@ -592,8 +592,12 @@ class DRT:
         plan['rm'] = rm
 
         # ---- variance-estimation matrices, drt1d.py:614-636
+        plan['vmm_chrono'] = None             # 'uniform': rank one (ones / Nt), never materialised
         if times is not None and kw['chrono_error_structure'] != 'uniform':
-            _not_supported("chrono_error_structure other than 'uniform'")
+            if kw['chrono_error_structure'] is not None:
+                raise ValueError(f"Invalid error structure {kw['chrono_error_structure']}")
+            plan['vmm_chrono'] = eng.build_chrono_vmm(times[None], self.step_times[None],
+                                                      kw['chrono_vmm_epsilon'])[0]
         if frequencies is not None:
             es = kw['eis_error_structure']
             if es not in (None, 'uniform'):
@@ -672,6 +676,8 @@ class DRT:
         ch.weight_factor = float(kw['weight_factor'])
         ch.chrono_weight_factor = float(kw['chrono_weight_factor'])
         ch.eis_weight_factor = float(kw['eis_weight_factor'])
+        if hyp.get('outlier_p') is not None:                     # qphb.py:232; error structure qphb.py:1497-1538
+            ch.has_outlier_p, ch.outlier_p = 1, float(hyp['outlier_p'])
         return ch
 
     def _eval_matrix(self, plan, tau_eval):
@@ -708,8 +714,7 @@ class DRT:
         # options outside the hot path (same keyword names as drt1d.py:102-137)
         for flag, name in ((series_neg, 'series_neg'), (update_scale, 'update_scale'), (solve_rp, 'solve_rp'),
                            (downsample, 'downsample'), (subtract_background, 'subtract_background'),
-                           (remove_extremes, 'remove_extremes'), (remove_outliers, 'remove_outliers'),
-                           (return_outlier_index, 'return_outlier_index'),
+                           (remove_extremes, 'remove_extremes'),
                            (init_weights_separately, 'init_weights_separately'),
                            (discard_first_n is not None, 'discard_first_n'), (peak_locations is not None,
                                                                             'peak_locations'),
@@ -727,8 +732,11 @@ class DRT:
             if key not in hypers:
                 raise ValueError(f'Invalid keyword argument {key}')
         hypers.update(kw)
-        if hypers['outlier_p'] is not None:
-            _not_supported('outlier_p')
+        if remove_outliers:
+            _not_supported('remove_outliers in a batched call (the flagged points differ per spectrum; '
+                           'use the single-spectrum fit_* methods or group the spectra yourself)')
+        if return_outlier_index:             # drt1d.py:817-835: stop after initialize_weights
+            max_iter = 0
         if (eis_weight_factor is None) != (chrono_weight_factor is None):
             warnings.warn('Both eis_weight_factor and chrono_weight_factor must be provided. '
                           'If only one is provided, it will be ignored.')
@@ -743,6 +751,7 @@ class DRT:
                     capacitance_penalty=capacitance_penalty, inductance_scale=inductance_scale,
                     capacitance_scale=capacitance_scale, chrono_error_structure=chrono_error_structure,
                     eis_error_structure=eis_error_structure, eis_vmm_epsilon=eis_vmm_epsilon,
+                    chrono_vmm_epsilon=chrono_vmm_epsilon,
                     eis_reim_cor=eis_reim_cor, iw_l1_lambda_0=iw_l1_lambda_0, iw_l2_lambda_0=iw_l2_lambda_0,
                     vz_offset=vz_offset, vz_offset_scale=vz_offset_scale, vz_offset_eps=vz_offset_eps,
                     eis_weight_factor=eis_weight_factor, chrono_weight_factor=chrono_weight_factor,
@@ -797,7 +806,7 @@ class DRT:
         vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
         vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
         raw = eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
-                                 vmm_eis=plan['vmm_eis'], vmm_chrono=None, n_chrono=nc, dop_range=dop_range,
+                                 vmm_eis=plan['vmm_eis'], vmm_chrono=plan['vmm_chrono'], n_chrono=nc, dop_range=dop_range,
                                  vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
                                  hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
                                  want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
@@ -842,11 +851,60 @@ class DRT:
     # ------------------------------------------------------------------------------------------------
     # reference single-spectrum API (drt1d.py:1197-1268)
     # ------------------------------------------------------------------------------------------------
-    def _qphb_fit_core(self, times, i_signal, v_signal, frequencies, z, **kw):
+    def _qphb_fit_core(self, times, i_signal, v_signal, frequencies, z, remove_outliers=False, outlier_thresh=0.75,
+                       **kw):
+        """Single-spectrum entry (drt1d.py:102-1104) = a batch of one, plus the remove_outliers two-pass flow
+        (drt1d.py:217-303) on the host."""
+        if times is not None:
+            times, i_signal, v_signal = np.array(times), np.array(i_signal), np.array(v_signal)
+        if frequencies is not None:
+            frequencies, z = np.array(frequencies), np.array(z)
+        self.eis_outlier_index = self.eis_outliers = None
+        self.chrono_outlier_index = self.chrono_outliers = None
+        if remove_outliers:
+            if 'outlier_p' not in kw:
+                raise ValueError('If remove_outliers is True, the prior probability of outlier presence, outlier_p, '
+                                 'must be specified. A good starting value might be 0.01-0.05')
+            chrono_idx, eis_idx = self._outlier_index(times, i_signal, v_signal, frequencies, z, outlier_thresh, kw)
+            self.eis_outlier_index, self.chrono_outlier_index = eis_idx, chrono_idx
+            kw = dict(kw)
+            if kw.get('step_times') is None and times is not None:
+                kw['step_times'] = self.step_times          # step times determined before the outlier removal
+            if times is not None and np.sum(chrono_idx) > 0:
+                if self.warn:
+                    warnings.warn('Found outliers in chrono data at the following '
+                                  f'indices: {np.where(chrono_idx)[0].tolist()}. '
+                                  'These data points will be removed before fitting')
+                self.chrono_outliers = (times[chrono_idx], i_signal[chrono_idx], v_signal[chrono_idx])
+                times, i_signal, v_signal = times[~chrono_idx], i_signal[~chrono_idx], v_signal[~chrono_idx]
+            if frequencies is not None and np.sum(eis_idx) > 0:
+                if self.warn:
+                    warnings.warn('Found outliers in EIS data at the following '
+                                  f'indices: {np.where(eis_idx)[0].tolist()}. '
+                                  'These data points will be removed before fitting')
+                self.eis_outliers = (frequencies[eis_idx], z[eis_idx])
+                frequencies, z = frequencies[~eis_idx], z[~eis_idx]
+            kw['outlier_p'] = None                           # drt1d.py:297-298
         v_b = None if v_signal is None else np.asarray(v_signal, dtype=float)[None, :]
         z_b = None if z is None else np.asarray(z)[None, :]
         res = self._fit_core_batch(times, i_signal, v_b, frequencies, z_b, want_pq=True, **kw)
         self._store_single(res)
+
+    def _outlier_index(self, times, i_signal, v_signal, frequencies, z, outlier_thresh, kw):
+        """First pass of remove_outliers: (chrono_outlier_index, eis_outlier_index) from the outlier_t of the
+        weight initialisation (drt1d.py:817-835)."""
+        v_b = None if v_signal is None else np.asarray(v_signal, dtype=float)[None, :]
+        z_b = None if z is None else np.asarray(z)[None, :]
+        res = self._fit_core_batch(times, i_signal, v_b, frequencies, z_b, return_outlier_index=True, **kw)
+        t = res.host(['outlier_t'])['outlier_t'][0]
+        idx = (1 - t) > outlier_thresh
+        nc = res.plan['n_chrono']
+        chrono_idx = idx[:nc] if nc else None
+        eis_idx = None
+        if res.plan['n_freq']:
+            nf = res.plan['n_freq']
+            eis_idx = idx[nc:nc + nf] | idx[nc + nf:]        # bad real OR imag value
+        return chrono_idx, eis_idx
 
     def fit_eis(self, frequencies, z, nonneg=True, neg_allowed_tau_range=None, scale_data=True, update_scale=False,
                 error_structure=None, vmm_epsilon=0.25, vmm_reim_cor=0.25, **kwargs):
@@ -941,6 +999,7 @@ class DRT:
             'chrono_weight_factor': opts['chrono_weight_factor'], 'eis_weight_factor': opts['eis_weight_factor'],
             'vz_strength_vec': pl.get('vz_strength_host', 1),
             'n_outer': int(h['n_outer'][0]), 'n_ipm': int(h['n_ipm'][0]), 'status': st,
+            'outlier_t': h['outlier_t'][0] if 'outlier_t' in h else np.ones(pl['n_rows']),
         }
         self.qphb_history = None    # per-iteration history is not exported by the batched kernel
 

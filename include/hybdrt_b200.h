@@ -79,6 +79,12 @@ int hdrt_build_penalty(const double* grid, int n_grids, int nb, double eps, int 
 int hdrt_build_eis_vmm(const double* freq, int n_grids, int nf, double vmm_eps, double reim_cor, int uniform,
                        double* vmm, void* stream);
 
+/* mat1d.construct_chrono_var_matrix (mat1d.py:455-490) with utils.chrono.get_time_transforms (chrono.py:5-39).
+ * times [n_grids][nt] (ascending), step_times [n_grids][n_steps] -> vmm [n_grids][nt][nt].  uniform != 0 is
+ * error_structure='uniform' (every entry 1/nt; the solver never needs it materialised: pass vmm_chrono = NULL). */
+int hdrt_build_chrono_vmm(const double* times, const double* step_times, int n_grids, int nt, int n_steps,
+                          double vmm_eps, int uniform, double* vmm, void* stream);
+
 /* phasance.construct_phasor_z_matrix, gaussian basis, normalize=False (phasance.py:19-37,61-80,108-118).
  * freq [n_grids][nf], nu [n_nu] -> interleaved complex128 zm [n_grids][nf][n_nu][2]. */
 int hdrt_build_dop_z(const double* freq, const double* nu, int n_grids, int nf, int n_nu, double nu_eps, double* zm,
@@ -114,6 +120,9 @@ typedef struct hdrt_hypers {
     double eis_weight_factor;
     int has_iw_prior;
     int max_iter; /* drt1d.py:135 */
+    double outlier_p;  /* prior probability of a point being an outlier (qphb.py:232, :1497-1538); read iff has_outlier_p */
+    int has_outlier_p; /* 0 = hypers['outlier_p'] is None */
+    int reserved_;
 } hdrt_hypers;
 
 typedef struct hdrt_qphb_problem {
@@ -168,6 +177,8 @@ typedef struct hdrt_qphb_problem {
     int n_eval;
     double* dist_var;      /* [n_eval] diag(B P^-1 B^T) in the scaled space (drt1d.py:3063-3151, :4116-4138)         */
     double* resid_ss;      /* [2]   sum of squared residuals of the final x: chrono rows, EIS rows (qphb.py:1347)   */
+    double* outlier_t;     /* [N]   1 - outlier probability of the last weight update (qphb.py:1497-1519); required
+                                    iff hyp.has_outlier_p                                                            */
 } hdrt_qphb_problem;
 
 /* Fills `hyp` with the reference defaults (qphb.py:208-255 eff_hp=True, drt1d.py:102-137). */

@@ -143,6 +143,36 @@ def eis_vmm(freq, vmm_eps=0.25, reim_cor=0.25, structure=None):
     return vmm / vmm.sum(axis=1)[:, None]
 
 
+def time_transform(times, step_times):
+    """utils.chrono.get_time_transforms forward transform, chrono.py:5-39: linear before the first step, then
+    log(time since the step) per segment, segments laid end to end."""
+    times = np.asarray(times, dtype=float)
+    start = np.asarray(step_times, dtype=float)
+    t_sample = np.min(np.diff(times))
+    base = np.log(t_sample / 4)
+    offsets = np.concatenate([[0], np.cumsum(np.log(start[1:] - start[:-1]) - base)])
+    tt = np.zeros_like(times)
+    seg = np.zeros(times.size, dtype=int)
+    pre = times < start[0]
+    tt[pre] = times[pre] - start[0]
+    for i, s0 in enumerate(start):
+        s1 = np.inf if i == len(start) - 1 else start[i + 1]
+        idx = (times >= s0) & (times < s1)
+        tt[idx] = offsets[i] + np.log(np.maximum(times[idx] - s0, t_sample / 2)) - base
+        seg[idx] = i + 1
+    return tt, seg
+
+
+def chrono_vmm(times, step_times, vmm_eps=4.0, structure=None):
+    """mat1d.construct_chrono_var_matrix, mat1d.py:455-490."""
+    nt = len(times)
+    if structure == 'uniform':
+        return np.ones((nt, nt)) / nt
+    tt, seg = time_transform(times, step_times)
+    vmm = rbf(tt[:, None] - tt[None, :], vmm_eps) * (seg[:, None] == seg[None, :])
+    return vmm / vmm.sum(axis=1)[:, None]
+
+
 def dop_z_matrix(freq, nu, nu_eps):
     """phasance.construct_phasor_z_matrix (gaussian, normalize=False), phasance.py:19-37,61-80,108-118."""
     omega = 2 * np.pi * np.asarray(freq, dtype=float)
@@ -269,17 +299,60 @@ def apply_vmm(vmm, r2):
     return vmm @ r2
 
 
-def estimate_weights(x, y, vmm, rm, est_weights=None):
-    """qphb.estimate_weights without the outlier branch, qphb.py:1545-1594."""
+def vmm_diag(vmm, n):
+    """diag(vmm) for the dense or structured form."""
+    if isinstance(vmm, dict):
+        nc = vmm['n_chrono']
+        d = np.empty(n)
+        if nc:
+            d[:nc] = np.diag(vmm['chrono']) if vmm.get('chrono') is not None else 1.0 / nc
+        if vmm.get('eis') is not None:
+            d[nc:] = np.diag(vmm['eis'])
+        return d
+    return np.diag(vmm).copy()
+
+
+def apply_vmm_base(vmm, u):
+    """(vmm - diag(vmm)) / (1 - diag(vmm))[:, None] @ u: the self-excluding averaging matrix of the first
+    initialisation pass with outliers, qphb.py:1644-1649."""
+    d = vmm_diag(vmm, u.size)
+    return (apply_vmm(vmm, u) - d * u) / (1 - d)
+
+
+def outlier_t_vector(s_bar, resid, outlier_p):
+    """qphb.solve_outlier_t, qphb.py:1497-1519 (pdf_normal: utils/stats.py:11-12)."""
+    with np.errstate(invalid='ignore', divide='ignore'):
+        sd = np.sqrt(s_bar)
+        pdf_in = 1 / (sd * np.sqrt(2 * np.pi)) * np.exp(-0.5 * resid ** 2 / sd ** 2)
+        ar = np.abs(resid)
+        pdf_out = 1 / (ar * np.sqrt(2 * np.pi)) * np.exp(-0.5 * resid ** 2 / ar ** 2)
+        t = 1 - outlier_p * pdf_out / ((1 - outlier_p) * pdf_in + outlier_p * pdf_out)
+    t[sd > ar] = 1
+    return t
+
+
+def estimate_weights(x, y, vmm, rm, est_weights=None, outlier_p=None, base=False, return_t=False):
+    """qphb.estimate_weights, qphb.py:1545-1594.  With outlier_p the averaging matrix becomes
+    T^1/2 vmm T^1/2 + (I - T) (qphb.outlier_tvt :1522-1538), applied here without forming it;
+    base=True uses the self-excluding matrix of the first initialisation pass (:1644-1649)."""
     resid = rm @ x - y
-    s_hat = apply_vmm(vmm, resid ** 2)
+    r2 = resid ** 2
+    mv = apply_vmm_base if base else apply_vmm
+    if outlier_p is not None:
+        t = outlier_t_vector(mv(vmm, r2), resid, outlier_p)
+        sq = t ** 0.5
+        s_hat = sq * mv(vmm, sq * r2) + (1 - t) * r2
+    else:
+        t = np.ones(len(y))
+        s_hat = mv(vmm, r2)
     floor = np.var(y) * 1e-7
     s_hat = np.where(s_hat < floor, floor, s_hat)
     w = s_hat ** -0.5
     if est_weights is not None:
         frac = w / (w + est_weights)
         w = frac * w + (1 - frac) * est_weights
-    return np.maximum(w, 1e-10)
+    w = np.maximum(w, 1e-10)
+    return (w, t) if return_t else w
 
 
 def converged(x_in, x_out, atol, rtol):
@@ -338,9 +411,19 @@ def qphb_fit(prob, hypers=None, record_history=False):
 
     # initialize_weights, qphb.py:1609-1681 with iw hypers of drt1d.py:640-645
     l2_iw = l2_matrix(pen, s_vec, rho, dop_rho, hyp, ns, dop_range, l2_lambda_0=prob.get('iw_l2', 1e-4))
-    res = qp(rm, rv, l2_iw, prob.get('iw_l1', 1e-4))
-    x_overfit = res['x']
-    est_w = estimate_weights(x_overfit, rv, vmm, rm)
+    outlier_p = hyp.get('outlier_p')
+    if outlier_p is not None:                                                    # qphb.py:1629-1655
+        est_w = np.ones(rm.shape[0])
+        for _ in range(2):
+            res = qp(est_w[:, None] * rm, est_w * rv, l2_iw, prob.get('iw_l1', 1e-4))
+            x_overfit = res['x']
+            est_w, outlier_t = estimate_weights(x_overfit, rv, vmm, rm, outlier_p=outlier_p, base=True,
+                                                return_t=True)
+    else:
+        res = qp(rm, rv, l2_iw, prob.get('iw_l1', 1e-4))
+        x_overfit = res['x']
+        est_w, outlier_t = estimate_weights(x_overfit, rv, vmm, rm, return_t=True)
+    init_outlier_t = outlier_t
     if hyp['iw_alpha'] is not None:                                              # qphb.py:1471-1479
         bq = 0.5 - hyp['iw_alpha'] + 1
         s_hat = (-bq + np.sqrt(bq ** 2 + 2 * hyp['iw_beta'] * est_w ** -2.0)) / (2 * hyp['iw_beta'])
@@ -400,7 +483,7 @@ def qphb_fit(prob, hypers=None, record_history=False):
                 ra = hyp['dop_rho_alpha'][k]
                 dop_rho[k] = update_rho(m, xp, s_new, ra, ra / hyp['dop_rho_0'][k], dop_xmx[k])
 
-        w = estimate_weights(x, rv, vmm, rm, est_w)                              # qphb.py:938
+        w, outlier_t = estimate_weights(x, rv, vmm, rm, est_w, outlier_p=outlier_p, return_t=True)   # qphb.py:938
         conv = converged(x_in, x, np.mean(x_in) * 1e-3, xtol)                    # qphb.py:969-970
         if record_history:
             history.append(dict(x=x.copy(), s=np.array(s_vec), rho=rho.copy(), w=w.copy(),
@@ -429,7 +512,8 @@ def qphb_fit(prob, hypers=None, record_history=False):
         x=x, fun=res['primal objective'], weights=w_scaled, true_weights=w_true,
         est_weights=est_w, init_weights=init_w, x_overfit=x_overfit,
         s_vectors=np.array(s_vec), rho=rho, dop_rho=dop_rho, xmx_norms=xmx, dop_xmx_norms=dop_xmx,
-        n_outer=it, converged=conv, ipm_iters=np.array(ipm_log),
+        n_outer=it, converged=conv, ipm_iters=np.array(ipm_log), outlier_t=outlier_t,
+        init_outlier_t=init_outlier_t,
         p_matrix=l2 + wrm.T @ wrm, q_vector=-wrm.T @ (w_scaled * rv) + l1, rm_final=rm,
     )
     if record_history:

@@ -317,13 +317,86 @@ def test_model_hybrid_and_chrono():
         assert rel_err(res.predict_z()[b], hf['z_pred'][b]) < FIT_TOL
 
 
+def test_outlier_error_structure_and_removal(eng, orc, lookup_golden):
+    """outlier_p (qphb.py:1497-1538, two-pass initialisation :1629-1655) and remove_outliers (drt1d.py:217-303)
+    against the unmodified reference; the kernel alone against the oracle on the same problems."""
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200 import engine as E
+    g = load_golden('outlier_eis.npz')
+    prep = orc.EisPrep(g['freq'], tables=lookup_golden)
+    hyp = E.default_hypers()
+    hyp.has_outlier_p, hyp.outlier_p = 1, float(g['outlier_p'])
+    rvs = np.array([prep.problem(zz)[0]['rv'] for zz in g['z']])
+    out = _eis_launch(eng, prep, rvs, hypers=hyp)
+    for b in range(len(g['z'])):
+        ref = prep.fit(g['z'][b], hypers=dict(outlier_p=float(g['outlier_p'])))
+        assert int(out['n_outer'][b]) == ref['n_outer'] == int(g['n_outer'][b])
+        assert int(out['n_ipm'][b]) == int(g['qp_log_total'][b])
+        assert rel_err(out['x'][b], ref['x']) < FIT_TOL
+        assert rel_err(out['outlier_t'][b], ref['outlier_t']) < FIT_TOL
+        assert rel_err(out['est_weights'][b], g['est_weights'][b]) < FIT_TOL
+        assert rel_err(out['x_overfit'][b], g['x_overfit_eis'][b]) < FIT_TOL
+    drt = DRT()
+    res = drt.fit_eis_batch(g['freq'], g['z'], outlier_p=float(g['outlier_p']))
+    h = res.host()
+    for b in range(len(g['z'])):
+        assert rel_err(h['x'][b], g['cvx_x'][b]) < FIT_TOL
+        assert rel_err(h['outlier_t'][b], g['outlier_t'][b]) < FIT_TOL
+        assert rel_err(res.predict_z()[b], g['z_pred'][b]) < FIT_TOL
+    drt.warn = False
+    for b in range(len(g['z'])):
+        drt.fit_eis(g['freq'], g['z'][b], outlier_p=float(g['outlier_p']), remove_outliers=True)
+        assert np.array_equal(np.asarray(drt.eis_outlier_index), g['ro_index'][b])
+        assert drt.qphb_params['n_outer'] == int(g['ro_n_outer'][b])
+        assert rel_err(drt.fit_parameters['x'], g['ro_x'][b]) < FIT_TOL
+        assert rel_err(drt.predict_z(g['freq']), g['ro_z_pred'][b]) < FIT_TOL
+    with pytest.raises(ValueError):
+        drt.fit_eis(g['freq'], g['z'][0], remove_outliers=True)
+    with pytest.raises(E.EngineError):
+        hyp.outlier_p = 1.5
+        _eis_launch(eng, prep, rvs, hypers=hyp)
+
+
+def test_flexible_chrono_error_structure(eng, orc):
+    """chrono_error_structure=None (mat1d.py:455-490): the matrix builder, then fit_chrono / fit_hybrid with the
+    dense chrono block, then the tutorial's flags (flexible chrono errors + outlier_p) against the reference."""
+    from hybdrt_b200.models import DRT
+    g = load_golden('chrono_flex.npz')
+    v2 = _np(eng.build_chrono_vmm(g['t2'][None], g['st2'][None], 4.0)[0])
+    assert rel_err(v2[::8], g['vmm_two_step_rows']) < MAT_TOL
+    assert rel_err(v2, orc.chrono_vmm(g['t2'], g['st2'], 4.0)) < MAT_TOL
+    assert np.allclose(v2.sum(axis=1), 1.0, atol=1e-13)
+    vu = _np(eng.build_chrono_vmm(g['t2'][None], g['st2'][None], 4.0, uniform=True)[0])
+    assert np.array_equal(vu, np.full_like(vu, 1.0 / len(g['t2'])))
+    v1 = _np(eng.build_chrono_vmm(g['times'][None], g['step_times'][None], 4.0)[0])
+    assert rel_err(v1[::8], g['vmm_chrono_rows']) < MAT_TOL
+    drt = DRT()
+    drt.fit_chrono(g['times'], g['i_signal'], g['v_signal'][1], error_structure=None)
+    assert drt.qphb_params['n_outer'] == int(g['chrono_n_outer']) and drt.qphb_params['n_ipm'] == int(g['chrono_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['chrono_cvx_x']) < FIT_TOL
+    assert rel_err(drt.qphb_params['est_weights'], g['chrono_est_weights']) < FIT_TOL
+    assert rel_err(drt.predict_response(), g['chrono_v_pred']) < FIT_TOL
+    drt.fit_hybrid(g['times'], g['i_signal'], g['v_signal'][0], g['freq'], g['z'][0], chrono_error_structure=None)
+    assert drt.qphb_params['n_outer'] == int(g['hybrid_n_outer']) and drt.qphb_params['n_ipm'] == int(g['hybrid_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['hybrid_cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['freq']), g['hybrid_z_pred']) < FIT_TOL
+    drt.fit_hybrid(g['times'], g['i_signal'], g['tut_v_signal'], g['freq'], g['z'][0], chrono_error_structure=None,
+                   outlier_p=0.01)
+    assert drt.qphb_params['n_outer'] == int(g['tut_n_outer']) and drt.qphb_params['n_ipm'] == int(g['tut_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['tut_cvx_x']) < FIT_TOL
+    assert rel_err(drt.qphb_params['outlier_t'], g['tut_outlier_t']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['freq']), g['tut_z_pred']) < FIT_TOL
+    with pytest.raises(ValueError):
+        drt.fit_chrono(g['times'], g['i_signal'], g['v_signal'][1], error_structure='nonsense')
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')
     with pytest.raises(NotImplementedError):
         DRT(tau_basis_type='Cole-Cole')
     drt = DRT()
-    for kw in (dict(update_scale=True), dict(outlier_p=0.01), dict(penalty_type='discrete')):
+    for kw in (dict(update_scale=True), dict(penalty_type='discrete')):
         with pytest.raises(NotImplementedError):
             drt.fit_eis(c2['freq'], c2['z'][0], **kw)
 

@@ -158,6 +158,41 @@ def test_chrono_matches_reference(tables):
     assert rel_err(res['x'], cs['cvx_x']) < 1e-8
 
 
+def test_outlier_error_structure_matches_reference(tables):
+    """outlier_p: Bernoulli-mixture t vector, T^1/2 vmm T^1/2 + (I - T), two-pass initialisation."""
+    g = load_golden('outlier_eis.npz')
+    prep = orc.EisPrep(g['freq'], tables=tables)
+    for b in range(g['z'].shape[0]):
+        res = prep.fit(g['z'][b], hypers=dict(outlier_p=float(g['outlier_p'])))
+        assert res['n_outer'] == int(g['n_outer'][b])
+        assert int(res['ipm_iters'].sum()) == int(g['qp_log_total'][b])
+        assert rel_err(res['x'], g['cvx_x'][b]) < 1e-9
+        assert rel_err(res['est_weights'], g['est_weights'][b]) < 1e-9
+        assert rel_err(res['outlier_t'], g['outlier_t'][b]) < 1e-9
+        flagged = (1 - res['init_outlier_t']) > 0.75                  # drt1d.py:820
+        nf = g['freq'].size
+        assert np.array_equal(flagged[:nf] | flagged[nf:], g['ro_index'][b])
+
+
+def test_flexible_chrono_error_structure_matches_reference(tables):
+    g = load_golden('chrono_flex.npz')
+    assert rel_err(orc.chrono_vmm(g['t2'], g['st2'], 4.0)[::8], g['vmm_two_step_rows']) < 1e-13
+    vmm = orc.chrono_vmm(g['times'], g['step_times'], 4.0)
+    assert rel_err(vmm[::8], g['vmm_chrono_rows']) < 1e-13
+    cs = load_golden('chrono_small.npz')                              # same trace: rm / rv are shared
+    rm = cs['rm']
+    n_rows, n = rm.shape
+    pen = _layout_pen(cs['basis_tau'], float(tables['eps']), [1e-6, 1e-6, 1e-6])
+    h = np.zeros(n)
+    h[0] = 1000
+    prob = dict(rm=rm, rv=cs['rv'], vmm=dict(n_chrono=n_rows, chrono=vmm, eis=None), pen=pen, h=h,
+                l1=np.zeros(n), n_special=3, n_chrono=n_rows)
+    res = orc.qphb_fit(prob)
+    assert res['n_outer'] == int(g['chrono_n_outer'])
+    assert int(res['ipm_iters'].sum()) == int(g['chrono_ipm'])
+    assert rel_err(res['x'], g['chrono_cvx_x']) < 1e-8
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
