@@ -137,17 +137,25 @@ struct SmemTable {
     const double* v;
     const double* s;
     double x0, xn, inv_dx, v0, vn;
+    bool uniform;   // every knot within 1e-9 of a spacing of the uniform grid: the index guess can be trusted
 };
+// Exact numpy.interp semantics (same interval as numpy's binary search, slope * (x - x_j) + v_j, edge values
+// outside the span).  Common path: no loop and no branch -- the interval index comes from the uniform-grid guess,
+// which is provably right when x is further than 1e-6 of a spacing from a knot; otherwise (or for a non-uniform
+// table) the two loops move the index to where the binary search lands.
 __device__ __forceinline__ double interp_smem(double x, const SmemTable& t, int npts) {
-    if (isnan(x)) return x;
-    if (x > t.xn) return t.vn;
-    if (x < t.x0) return t.v0;
-    int j = (int)((x - t.x0) * t.inv_dx);
-    j = max(0, min(npts - 1, j));
-    while (j > 0 && t.x[j] > x) --j;
-    while (j < npts - 1 && t.x[j + 1] <= x) ++j;
-    if (j == npts - 1) return t.vn;
-    return __dadd_rn(__dmul_rn(t.s[j], x - t.x[j]), t.v[j]);
+    const double pos = (x - t.x0) * t.inv_dx;
+    const int jr = __double2int_rd(pos);          // floor, saturating; NaN -> 0
+    const double frac = pos - (double)jr;         // in [0, 1) also for x outside the span (|pos| < 2^31)
+    int j = max(0, min(jr, npts - 2));
+    if (!(frac > 1e-6 && frac < 1.0 - 1e-6 && t.uniform)) {   // rare: x at a knot, NaN, or an odd table
+        while (j > 0 && t.x[j] > x) --j;
+        while (j < npts - 2 && t.x[j + 1] <= x) ++j;
+    }
+    double r = __dadd_rn(__dmul_rn(t.s[j], x - t.x[j]), t.v[j]);   // NaN x gives NaN
+    r = (x >= t.xn) ? t.vn : r;
+    r = (x < t.x0) ? t.v0 : r;
+    return r;
 }
 
 constexpr int kIThreads = 512;
@@ -176,11 +184,22 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
         t_rs[i] = (t_rv[i + 1] - t_rv[i]) / (t_rx[i + 1] - t_rx[i]);
         t_is[i] = (t_iv[i + 1] - t_iv[i]) / (t_ix[i + 1] - t_ix[i]);
     }
+    __shared__ int s_nonuniform[2];
+    if (tid < 2) s_nonuniform[tid] = 0;
     SmemTable tr, ti;
     tr.x = t_rx; tr.v = t_rv; tr.s = t_rs; tr.x0 = t_rx[0]; tr.xn = t_rx[npts - 1]; tr.v0 = t_rv[0]; tr.vn = t_rv[npts - 1];
     ti.x = t_ix; ti.v = t_iv; ti.s = t_is; ti.x0 = t_ix[0]; ti.xn = t_ix[npts - 1]; ti.v0 = t_iv[0]; ti.vn = t_iv[npts - 1];
     tr.inv_dx = (double)(npts - 1) / (tr.xn - tr.x0);
     ti.inv_dx = (double)(npts - 1) / (ti.xn - ti.x0);
+    __syncthreads();
+    for (int i = tid; i < npts; i += kIThreads) {
+        if (fabs((t_rx[i] - tr.x0) * tr.inv_dx - (double)i) > 1e-9) s_nonuniform[0] = 1;
+        if (fabs((t_ix[i] - ti.x0) * ti.inv_dx - (double)i) > 1e-9) s_nonuniform[1] = 1;
+    }
+    __syncthreads();
+    tr.uniform = s_nonuniform[0] == 0;
+    ti.uniform = s_nonuniform[1] == 0;
+    const int pstep_r = (2 * kIThreads) / nb, pstep_m = (2 * kIThreads) % nb;   // index advance per pair-loop trip
     const long long items = (long long)n_grids * tiles_per_grid;
     int buf = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
@@ -203,9 +222,10 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
             a_im[base] = interp_smem(x, ti, npts);
         }
         const int npairs = (cnt - head) >> 1;
-        for (int p = tid; p < npairs; p += kIThreads) {
+        int rr = (head + 2 * tid) / nb, m = (head + 2 * tid) - rr * nb;
+        for (int p = tid; p < npairs; p += kIThreads, rr += pstep_r, m += pstep_m) {
+            if (m >= nb) { m -= nb; ++rr; }
             const int idx = head + 2 * p;
-            const int rr = idx / nb, m = idx - rr * nb;
             const bool wrap = (m + 1 == nb);
             const double xa = s_lw[rr] + s_lt[m];
             const double xb = wrap ? s_lw[rr + 1] + s_lt[0] : s_lw[rr] + s_lt[m + 1];

@@ -362,6 +362,44 @@ def converged(x_in, x_out, atol, rtol):
         return bool(np.max(np.abs(d / (x_in + 1e-15))) <= rtol or np.max(np.abs(d)) <= atol)
 
 
+def update_hypers(x, s_vec, rho, dop_rho, pen, hyp, ns, dop_range, xmx, dop_xmx):
+    """The s / rho updates of one qphb.iterate_qphb call (qphb.py:722-933) for the DRT block and the DOP block."""
+    kk = len(hyp['derivative_weights'])
+    s_vec = [s.copy() for s in s_vec]
+    rho = rho.copy()
+    xd = x[ns:]
+    for k, dw in enumerate(hyp['derivative_weights']):                       # qphb.py:722-803
+        if dw <= 0:
+            continue
+        m = pen[k][ns:, ns:]
+        alpha = hyp['s_alpha'][k]
+        beta = (alpha - 1) / hyp['s_0'][k]
+        if k == 0:
+            xh = np.sign(xd) * np.abs(xd) ** 0.5
+            g = xh[:, None] * pen[1][ns:, ns:] * xh[None, :]
+        else:
+            g = 0
+        s_new = update_s(m, xd, s_vec[k][ns:], 1.0, alpha, beta, g, hyp['sigma_ds'][k])
+        s_vec[k][ns:] = s_new
+        ra = hyp['rho_alpha'][k]
+        rho[k] = update_rho(m, xd, s_new, ra, ra / hyp['rho_0'][k], xmx[k])
+    if dop_range is not None:                                                # qphb.py:822-933
+        a, b = dop_range
+        dop_rho = dop_rho.copy()
+        xp = x[a:b]
+        for k, dw in enumerate(hyp['dop_derivative_weights']):
+            if dw <= 0:
+                continue
+            m = pen[k][a:b, a:b]
+            alpha = hyp['dop_s_alpha'][k]
+            beta = (alpha - 1) / hyp['dop_s_0'][k]
+            s_new = update_s(m, xp, s_vec[k][a:b], 1.0, alpha, beta, 0, hyp['dop_sigma_ds'][k])
+            s_vec[k][a:b] = s_new
+            ra = hyp['dop_rho_alpha'][k]
+            dop_rho[k] = update_rho(m, xp, s_new, ra, ra / hyp['dop_rho_0'][k], dop_xmx[k])
+    return s_vec, rho, dop_rho
+
+
 def qphb_fit(prob, hypers=None, record_history=False):
     """The loop of DRT._qphb_fit_core, drt1d.py:556-1008, on prepared matrices.
 
@@ -450,45 +488,14 @@ def qphb_fit(prob, hypers=None, record_history=False):
         res = qp(wrm, wrv, l2, l1)
         x = res['x']
 
-        s_vec = [s.copy() for s in s_vec]
-        rho = rho.copy()
-        xd = x[ns:]
-        for k, dw in enumerate(hyp['derivative_weights']):                       # qphb.py:722-803
-            if dw <= 0:
-                continue
-            m = pen[k][ns:, ns:]
-            alpha = hyp['s_alpha'][k]
-            beta = (alpha - 1) / hyp['s_0'][k]
-            if k == 0:
-                xh = np.sign(xd) * np.abs(xd) ** 0.5
-                g = xh[:, None] * pen[1][ns:, ns:] * xh[None, :]
-            else:
-                g = 0
-            s_new = update_s(m, xd, s_vec[k][ns:], 1.0, alpha, beta, g, hyp['sigma_ds'][k])
-            s_vec[k][ns:] = s_new
-            ra = hyp['rho_alpha'][k]
-            rho[k] = update_rho(m, xd, s_new, ra, ra / hyp['rho_0'][k], xmx[k])
-        if dop_range is not None:                                                # qphb.py:822-933
-            a, b = dop_range
-            dop_rho = dop_rho.copy()
-            xp = x[a:b]
-            for k, dw in enumerate(hyp['dop_derivative_weights']):
-                if dw <= 0:
-                    continue
-                m = pen[k][a:b, a:b]
-                alpha = hyp['dop_s_alpha'][k]
-                beta = (alpha - 1) / hyp['dop_s_0'][k]
-                s_new = update_s(m, xp, s_vec[k][a:b], 1.0, alpha, beta, 0, hyp['dop_sigma_ds'][k])
-                s_vec[k][a:b] = s_new
-                ra = hyp['dop_rho_alpha'][k]
-                dop_rho[k] = update_rho(m, xp, s_new, ra, ra / hyp['dop_rho_0'][k], dop_xmx[k])
-
+        s_vec, rho, dop_rho = update_hypers(x, s_vec, rho, dop_rho, pen, hyp, ns, dop_range, xmx, dop_xmx)
         w, outlier_t = estimate_weights(x, rv, vmm, rm, est_w, outlier_p=outlier_p, return_t=True)   # qphb.py:938
         conv = converged(x_in, x, np.mean(x_in) * 1e-3, xtol)                    # qphb.py:969-970
         if record_history:
             history.append(dict(x=x.copy(), s=np.array(s_vec), rho=rho.copy(), w=w.copy(),
                                 fun=res['primal objective'], ipm=res['iterations']))
         if it == 0:                                                              # drt1d.py:946-962
+            xd = x[ns:]
             xmx = np.array([xd @ pen[k][ns:, ns:] @ xd for k in range(kk)])
             if dop_range is not None:
                 a, b = dop_range
@@ -519,6 +526,114 @@ def qphb_fit(prob, hypers=None, record_history=False):
     if record_history:
         out['history'] = history
     return out
+
+
+def qphb_continue(prob, state, hypers, max_iter=10, min_iter=2):
+    """DRT._continue_from_init, drt1d.py:1270-1365: iterate_qphb warm-started from ``state`` (x, s_vectors, rho,
+    dop_rho, weights, est_weights, xmx_norms, dop_xmx_norms, rm with the current vz_offset column) under modified
+    hyper-parameters.  The weights are multiplied by the weight factors on every pass, xmx norms stay fixed, and
+    convergence only ends the loop from pass ``min_iter`` on."""
+    hyp = dict(DEFAULT_HYPERS)
+    hyp.update(hypers)
+    rm = np.array(state['rm'], dtype=float)
+    rv = np.asarray(prob['rv'], dtype=float)
+    vmm, h, l1 = prob['vmm'], np.asarray(prob['h'], dtype=float), np.asarray(prob['l1'], dtype=float)
+    pen = [np.asarray(m, dtype=float) for m in prob['pen']]
+    ns, dop_range = int(prob['n_special']), prob.get('dop_range')
+    nc = int(prob.get('n_chrono', 0))
+    vz_index = prob.get('vz_index')
+    hybrid = vz_index is not None or (nc > 0 and nc < rm.shape[0])
+    wf, cwf, ewf = prob.get('weight_factor', 1.0), prob.get('chrono_weight_factor', 1.0), prob.get('eis_weight_factor', 1.0)
+    xtol = prob.get('xtol', 1e-2)
+    x, w = state['x'].copy(), state['weights'].copy()
+    s_vec, rho, dop_rho = [v.copy() for v in state['s_vectors']], state['rho'].copy(), state.get('dop_rho')
+    if vz_index is not None:
+        a, b = prob['vb_range']
+        vz_strength = np.asarray(prob['vz_strength'], dtype=float)
+    history = []
+    it = 0
+    while it < max_iter:
+        x_in = x.copy()
+        if hybrid:
+            w[:nc] *= cwf
+            w[nc:] *= ewf
+        w = w * wf
+        l2 = l2_matrix(pen, s_vec, rho, dop_rho, hyp, ns, dop_range)
+        wrm = w[:, None] * rm
+        res = coneqp_orthant(wrm.T @ wrm + l2, -wrm.T @ (w * rv) + l1, h)
+        x = res['x']
+        s_vec, rho, dop_rho = update_hypers(x, s_vec, rho, dop_rho, pen, hyp, ns, dop_range, state['xmx_norms'],
+                                            state.get('dop_xmx_norms'))
+        w = estimate_weights(x, rv, vmm, rm, state['est_weights'], outlier_p=hyp.get('outlier_p'))
+        conv = converged(x_in, x, np.mean(x_in) * 1e-3, xtol)
+        history.append(dict(x=x.copy(), s_vectors=np.array(s_vec), rho=rho.copy(), dop_rho=dop_rho, weights=w.copy(),
+                            ipm=res['iterations']))
+        if vz_index is not None:
+            rm_vz = rm.copy()
+            rm_vz[:, a:b] = 0
+            sep = rm_vz @ x
+            sep[nc:] *= -1
+            rm[:, vz_index] = sep * vz_strength
+        if conv and it >= min_iter - 1:
+            break
+        it += 1
+    return history, rm
+
+
+def llh_terms(x, rm, rv, weights):
+    """(weighted rss, sum log w) -- the two data terms of qphb.evaluate_llh, qphb.py:1347-1377."""
+    r = weights * (rm @ x - rv)
+    return float(r @ r), float(np.sum(np.log(weights)))
+
+
+def marginal_llh(wrss, sum_log_w, n_data, alpha_0=2.0, beta_0=1.0):
+    """qphb.evaluate_llh with marginalize_weights=True, qphb.py:1359-1370."""
+    from scipy.special import loggamma
+    alpha_n = alpha_0 - 1 + n_data / 2
+    beta_n = beta_0 + 0.5 * wrss
+    return alpha_0 * np.log(beta_0) - alpha_n * np.log(beta_n) + loggamma(alpha_n) - loggamma(alpha_0) + sum_log_w
+
+
+def pfrt_fit(prob, factors=None, max_iter_per_step=10, max_init_iter=20, hypers=None):
+    """DRT._pfrt_fit_core, drt1d.py:2558-2698: a fit at s_0 * f, l2_lambda_0 / f for the first factor, then one
+    warm-started continuation per remaining factor; per step the final x, the marginal log-likelihood under
+    weights re-estimated from x alone, and calculate_pq's P under those weights and the *initial* hypers."""
+    base = dict(DEFAULT_HYPERS)
+    if hypers:
+        base.update(hypers)
+    factors = np.logspace(-1, 1, 11) if factors is None else np.asarray(factors, dtype=float)
+
+    def step_hypers(f):
+        return dict(s_0=np.asarray(base['s_0'], dtype=float) * f, l2_lambda_0=base['l2_lambda_0'] / f)
+
+    init_h = dict(base, **step_hypers(factors[0]))
+    p0 = dict(prob, max_iter=max_init_iter)
+    fit = qphb_fit(p0, init_h, record_history=True)
+    rv = np.asarray(prob['rv'], dtype=float)
+    ns, dop_range = int(prob['n_special']), prob.get('dop_range')
+    pen = [np.asarray(m, dtype=float) for m in prob['pen']]
+    steps = []
+
+    def record(x, s_vec, rho, dop_rho, rm, n_iter):
+        w = estimate_weights(x, rv, prob['vmm'], rm)
+        wrss, slw = llh_terms(x, rm, rv, w)
+        l2 = l2_matrix(pen, list(s_vec), rho, dop_rho, init_h, ns, dop_range)
+        wrm = w[:, None] * rm
+        steps.append(dict(x=x.copy(), llh=marginal_llh(wrss, slw, rv.size), p_matrix=l2 + wrm.T @ wrm, n_iter=n_iter,
+                          wrss=wrss, sum_log_w=slw))
+
+    last = fit['history'][-1]
+    rm = fit['rm_final']
+    record(last['x'], last['s'], last['rho'], fit['dop_rho'], rm, fit['n_outer'])
+    state = dict(x=last['x'], s_vectors=list(last['s']), rho=last['rho'], dop_rho=fit['dop_rho'], weights=last['w'],
+                 est_weights=fit['est_weights'], xmx_norms=fit['xmx_norms'], dop_xmx_norms=fit['dop_xmx_norms'], rm=rm)
+    for f in factors[1:]:
+        hist, rm = qphb_continue(prob, state, dict(init_h, **step_hypers(f)), max_iter=max_iter_per_step)
+        last = hist[-1]
+        record(last['x'], last['s_vectors'], last['rho'], last['dop_rho'], rm, len(hist))
+        state.update(x=last['x'], s_vectors=list(last['s_vectors']), rho=last['rho'], dop_rho=last['dop_rho'],
+                     weights=last['weights'], rm=rm)
+    return dict(init=fit, steps=steps, factors=factors)
 
 
 # ------------------------------------------------------------------------------------------------
