@@ -134,6 +134,7 @@ struct Ctx {
     const double* __restrict__ l1;
     const double* __restrict__ vz_strength;
     double* vzcol;  // global, per spectrum
+    double* vz0;    // global, per spectrum: vz_offset column frozen at the start of a continuation step, else NULL
     double* t_out;  // global, per spectrum: outlier_t (only with outlier_p)
     double outlier_p;  // < 0: no outlier error structure
     int red_phase;
@@ -1109,6 +1110,9 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
                 const double resid = acc - c.rv[r];
                 C::rowr2(c.N)[r] = resid * resid;
                 if (update_vz) {
+                    // a continuation predicts with the vz_offset column it started from (drt1d.py:1296-1302 copies
+                    // the matrix once, with that column in place); the plain fit copies it while it is still zero
+                    if (c.vz0 != nullptr) accv += c.vz0[r] * xs[c.vz];
                     const double sep = (r < nc) ? accv : -accv;
                     c.vzcol[r] = sep * c.vz_strength[r];
                 }
@@ -1249,6 +1253,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     const bool outl = hy.has_outlier_p != 0;
     c.outlier_p = outl ? hy.outlier_p : -1.0;
     c.t_out = outl ? p.outlier_t + (size_t)b * N : nullptr;
+    c.vz0 = nullptr;
     double* est_g = p.est_weights + (size_t)b * N;
 
     // var floor = var(y) * 1e-7 (qphb.py:1560-1561)
@@ -1267,9 +1272,18 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     double rho[3], dop_rho[3], xmx[3] = {1, 1, 1}, dop_xmx[3] = {1, 1, 1};
 #pragma unroll
     for (int k = 0; k < 3; ++k) { rho[k] = hy.rho_0[k]; dop_rho[k] = hy.dop_rho_0[k]; }
+    // PFRT (DRT._pfrt_fit_core, drt1d.py:2558-2698): step 0 is a plain fit at s_0 * f_0, l2_lambda_0 / f_0; every
+    // further factor continues from the previous state (_continue_from_init, :1270-1365)
+    const int n_steps = p.n_pfrt > 0 ? p.n_pfrt : 1;
+    const double fac0 = p.n_pfrt > 0 ? p.pfrt_factors[0] : 1.0;
+    const double lam_init = hy.l2_lambda_0 / fac0;     // qphb_params['hypers']['l2_lambda_0'] of the reference
     if (tid < C::NV) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { C::vec(C::SV0 + k)[tid] = hy.s_0[k]; C::vec(C::US0 + k)[tid] = sqrt(hy.s_0[k]); }
+        for (int k = 0; k < 3; ++k) {
+            const double s0 = hy.s_0[k] * fac0;        // s_0 of the step hypers fills the whole vector (drt1d.py:565)
+            C::vec(C::SV0 + k)[tid] = s0;
+            C::vec(C::US0 + k)[tid] = sqrt(s0);
+        }
     }
     for (int r = tid; r < N; r += C::kThreads) {
         C::roww()[r] = 1.0;
@@ -1295,9 +1309,25 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     for (int k = 0; k < 3; ++k) f.use[k] = hy.derivative_weights[k] > 0.0;
     double xi = 1e-6;  // drt1d.py:612
     double fun = 0.0;
-    int it = outl ? -2 : -1;   // -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p the
-                               // initialisation runs twice (-2, -1), the second time weighted by the first estimate
+    int it = 0, n_outer0 = 0;
     bool conv = false, fatal = false, final_pq = false;
+#pragma unroll 1
+    for (int step = 0; step < n_steps && !fatal; ++step) {
+    const bool cont = step > 0;
+    const double fac = p.n_pfrt > 0 ? p.pfrt_factors[step] : 1.0;
+    const double lam_step = hy.l2_lambda_0 / fac;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) hd.s_0[k] = hy.s_0[k] * fac;
+    const int max_it = cont ? p.pfrt_max_iter : hy.max_iter;
+    it = cont ? 0 : (outl ? -2 : -1);   // -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
+                                        // the initialisation runs twice (-2, -1), the second time weighted by the
+                                        // first estimate
+    conv = false;
+    if (cont && c.vz >= 0) {
+        c.vz0 = p.vz_scratch + (size_t)b * N;
+        for (int r = tid; r < N; r += C::kThreads) c.vz0[r] = c.vzcol[r];
+        __syncthreads();
+    }
 #pragma unroll 1
     while (true) {
         const bool init = it < 0;
@@ -1311,14 +1341,14 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
                 } else {
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
-                    if (it > 0) w = w * hy.weight_factor;
+                    if (it > 0 || cont) w = w * hy.weight_factor;   // a continuation scales on every pass (drt1d.py:1320)
                 }
                 C::roww()[r] = w;
             }
         }
         {
-            const double lam0 = init ? hy.iw_l2_lambda_0 : hy.l2_lambda_0;
-            const double dlam0 = init ? hy.dop_l2_lambda_0 * (hy.iw_l2_lambda_0 / hy.l2_lambda_0) : hy.dop_l2_lambda_0;
+            const double lam0 = init ? hy.iw_l2_lambda_0 : lam_step;
+            const double dlam0 = init ? hy.dop_l2_lambda_0 * (hy.iw_l2_lambda_0 / lam_step) : hy.dop_l2_lambda_0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 f.drt[k] = lam0 * hy.derivative_weights[k] * rho[k];
@@ -1362,13 +1392,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             }
             __syncthreads();
             it = 0;
-            if (hy.max_iter <= 0) break;
+            if (max_it <= 0) break;
             continue;
         }
         xi = qo.xi;
         fun = qo.pcost;
-        hyper_block<C>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0);
-        if (c.dop_a >= 0) hyper_block<C>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0);
+        hyper_block<C>(c, hd, c.ns, n - c.ns, rho, xmx, it == 0 && !cont);
+        if (c.dop_a >= 0) hyper_block<C>(c, hp, c.dop_a, c.dop_b - c.dop_a, dop_rho, dop_xmx, it == 0 && !cont);
         PROF_ADD(3);
         weights_phase<C>(c, est_g, var_floor, c.vz >= 0, false);
         PROF_ADD(4);
@@ -1381,7 +1411,8 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             conv = (t3[0] <= hy.xtol) || (t3[1] <= atol);
         }
         ++it;
-        if (conv || it >= hy.max_iter) {
+        // a continuation ignores convergence before pass min_iter (drt1d.py:1355)
+        if ((conv && (!cont || it >= p.pfrt_min_iter)) || it >= max_it) {
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
             if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = C::roww()[r];
             if (p.resid_ss) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
@@ -1396,6 +1427,39 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             final_pq = true;
         }
     }
+    if (!cont) n_outer0 = it < 0 ? 0 : it;
+    if (p.n_pfrt > 0 && !fatal) {
+        // step_update of the reference (drt1d.py:2617-2650): weights re-estimated from x alone (no blend with
+        // est_weights, no outlier structure), the two data terms of the marginal llh (qphb.py:1359-1373), and
+        // calculate_pq under those weights with the hypers of the *first* step
+        const size_t so = (size_t)b * p.n_pfrt + step;
+        if (tid < n) p.pfrt_x[so * n + tid] = xi;
+        if (tid == 0 && p.pfrt_iters) p.pfrt_iters[so] = it;
+        const double keep_p = c.outlier_p;
+        c.outlier_p = -1.0;
+        weights_phase<C>(c, nullptr, var_floor, false, false);
+        c.outlier_p = keep_p;
+        double t2[2] = {0.0, 0.0};
+        for (int r = tid; r < N; r += C::kThreads) {
+            const double w = C::roww()[r];
+            t2[0] += (w * w) * C::rowr2(c.N)[r];
+            t2[1] += log(w);
+        }
+        block_reduce<C, 2, 0u>(t2, c);
+        if (tid == 0) { p.pfrt_llh[2 * so] = t2[0]; p.pfrt_llh[2 * so + 1] = t2[1]; }
+        if (p.pfrt_p) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                f.drt[k] = lam_init * hy.derivative_weights[k] * rho[k];
+                f.dop[k] = hy.dop_l2_lambda_0 * hy.dop_derivative_weights[k] * dop_rho[k];
+            }
+            gram_phase<C>(c, f, false, 0.0, p.pfrt_p + so * n * n, nullptr);
+        }
+        __syncthreads();
+        for (int r = tid; r < N; r += C::kThreads) C::roww()[r] = p.weights[(size_t)b * N + r];   // back to the fit's weights
+        __syncthreads();
+    }
+    }   // steps
 
     if (tid < n) {
         p.x[(size_t)b * n + tid] = xi;
@@ -1421,7 +1485,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             if (p.dop_xmx_norms) p.dop_xmx_norms[(size_t)b * 3 + k] = dop_xmx[k];
         }
         if (p.fun) p.fun[b] = fun;
-        if (p.n_outer) p.n_outer[b] = it < 0 ? 0 : it;
+        if (p.n_outer) p.n_outer[b] = p.n_pfrt > 0 ? n_outer0 : (it < 0 ? 0 : it);
         if (p.n_ipm) p.n_ipm[b] = n_ipm;
         if (p.status) p.status[b] = status;
     }
@@ -1533,6 +1597,12 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
         set_error("outlier_p must lie in (0, 1) and needs the outlier_t buffer");
         return HDRT_ERR_ARG;
     }
+    if (p.n_pfrt > 0 && (!p.pfrt_factors || !p.pfrt_x || !p.pfrt_llh || !p.weights || p.pfrt_max_iter <= 0 ||
+                         p.p_matrix || p.dist_var)) {
+        set_error("PFRT needs pfrt_factors, pfrt_x, pfrt_llh, weights and pfrt_max_iter > 0 (and no p_matrix / dist_var)");
+        return HDRT_ERR_ARG;
+    }
+    if (p.n_pfrt > 1 && p.vz_index >= 0 && !p.vz_scratch) { set_error("PFRT with a vz_offset column needs vz_scratch"); return HDRT_ERR_ARG; }
     const long long smem = qphb_smem_bytes(p.n_rows, p.n_cols, p.hyp.has_outlier_p ? 3 : 2);
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;

@@ -55,6 +55,8 @@ class Problem(C.Structure):
         ('fun', _P), ('vz_col', _P), ('p_matrix', _P), ('q_vector', _P),
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
         ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P),
+        ('n_pfrt', C.c_int), ('pfrt_max_iter', C.c_int), ('pfrt_min_iter', C.c_int), ('pfrt_factors', _P),
+        ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('vz_scratch', _P),
     ]
 
 
@@ -270,7 +272,7 @@ class Engine:
 
     def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
                        dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
-                       hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False):
+                       hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False, pfrt=None):
         """Launch the batched QPHB solver.  All inputs are device float64 tensors.
 
         rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
@@ -333,6 +335,19 @@ class Engine:
             p.resid_ss = _ptr(buf('resid_ss', b, 2))
         if hyp.has_outlier_p:
             p.outlier_t = _ptr(buf('outlier_t', b, n_rows))
+        if pfrt is not None:           # dict(factors=..., max_iter_per_step=10, min_iter=2, want_p=False)
+            fac = self.dev(np.asarray(pfrt['factors'], dtype=float))
+            o['pfrt_factors'] = fac
+            nfac = fac.numel()
+            p.n_pfrt, p.pfrt_factors = nfac, _ptr(fac)
+            p.pfrt_max_iter, p.pfrt_min_iter = int(pfrt.get('max_iter_per_step', 10)), int(pfrt.get('min_iter', 2))
+            p.pfrt_x = _ptr(buf('pfrt_x', b, nfac, n))
+            p.pfrt_llh = _ptr(buf('pfrt_llh', b, nfac, 2))
+            p.pfrt_iters = _ptr(buf('pfrt_iters', b, nfac, dtype=torch.int32))
+            if pfrt.get('want_p'):
+                p.pfrt_p = _ptr(buf('pfrt_p', b, nfac, n, n))
+            if vz_index >= 0:
+                p.vz_scratch = _ptr(buf('vz_scratch', b, n_rows))
         p.n_outer = _ptr(buf('n_outer', b, dtype=torch.int32))
         p.n_ipm = _ptr(buf('n_ipm', b, dtype=torch.int32))
         p.status = _ptr(buf('status', b, dtype=torch.int32))

@@ -207,6 +207,21 @@ class BatchFit:
     def x_raw(self):
         return self.host()['x']
 
+    def pfrt_result(self):
+        """The reference's DRT.pfrt_result (drt1d.py:2687-2694), batched: factors [F], step_x [B,F,n] (raw, scaled
+        space, special parameters included), step_llh [B,F] (qphb.evaluate_llh with marginalised weights,
+        qphb.py:1359-1373, alpha_0=2, beta_0=1), step_p_mat [B,F,n,n] if it was requested, step_iters [B,F]."""
+        from math import lgamma
+        h = self.host(['pfrt_x', 'pfrt_llh', 'pfrt_iters', 'pfrt_factors'] + (['pfrt_p'] if 'pfrt_p' in self.raw else []))
+        n_data = self.plan['n_rows']
+        alpha_0, beta_0 = 2.0, 1.0
+        alpha_n = alpha_0 - 1 + n_data / 2
+        beta_n = beta_0 + 0.5 * h['pfrt_llh'][..., 0]
+        llh = alpha_0 * np.log(beta_0) - alpha_n * np.log(beta_n) + lgamma(alpha_n) - lgamma(alpha_0) \
+            + h['pfrt_llh'][..., 1]
+        return dict(factors=h['pfrt_factors'], step_x=h['pfrt_x'], step_llh=llh, step_p_mat=h.get('pfrt_p'),
+                    step_iters=h['pfrt_iters'])
+
     def fit_parameters(self):
         """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for the whole batch: dict of [B, ...] arrays."""
         pl, h, sc = self.plan, self.host(['x', 'weights']), self.scales
@@ -694,6 +709,7 @@ class DRT:
     # the batched fit core
     # ------------------------------------------------------------------------------------------------
     def _fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, want_pq=False, diag_tau=None,
+                        pfrt=None,
                         step_times=None,
                         step_sizes=None, nonneg=True, neg_allowed_tau_range=None, series_neg=False,
                         scale_data=True, update_scale=False, solve_rp=False,
@@ -810,7 +826,7 @@ class DRT:
                                  vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
                                  hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
                                  want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
-                                 want_resid=diag_tau is not None)
+                                 want_resid=diag_tau is not None, pfrt=pfrt)
         plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         if nf:
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
@@ -944,6 +960,74 @@ class DRT:
                             eis_reim_cor=eis_reim_cor, vz_offset=vz_offset, vz_offset_scale=vz_offset_scale,
                             vz_offset_eps=vz_offset_eps, eis_weight_factor=eis_weight_factor,
                             chrono_weight_factor=chrono_weight_factor, **kwargs)
+
+    # ------------------------------------------------------------------------------------------------
+    # PFRT (drt1d.py:2558-2716): one launch runs the initial fit and every continuation step
+    # ------------------------------------------------------------------------------------------------
+    def _pfrt_setup(self, factors, max_iter_per_step, max_init_iter, xtol, kw):
+        hyp0 = get_default_hypers(True, self.fit_dop)
+        factors = np.logspace(-1, 1, 11) if factors is None else np.asarray(factors, dtype=float)
+        # the step hypers always start from the *default* s_0 / l2_lambda_0 (drt1d.py:2575-2580)
+        kw = dict(kw, s_0=np.asarray(hyp0['s_0'], dtype=float), l2_lambda_0=hyp0['l2_lambda_0'])
+        pfrt = dict(factors=factors, max_iter_per_step=max_iter_per_step, min_iter=2)
+        return factors, pfrt, dict(kw, max_iter=max_init_iter, xtol=xtol)
+
+    def _pfrt_fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, factors=None, max_iter_per_step=10,
+                             max_init_iter=20, xtol=1e-2, nonneg=True, want_p=False, **kw):
+        factors, pfrt, kw = self._pfrt_setup(factors, max_iter_per_step, max_init_iter, xtol, kw)
+        pfrt['want_p'] = want_p
+        return self._fit_core_batch(times, i_signal, v_batch, frequencies, z_batch, nonneg=nonneg, pfrt=pfrt, **kw)
+
+    def pfrt_fit_eis_batch(self, frequencies, z, **kw):
+        """pfrt_fit_eis for z [batch, Nf]; BatchFit.pfrt_result() holds the per-factor outputs."""
+        return self._pfrt_fit_core_batch(None, None, None, frequencies, z, **kw)
+
+    def pfrt_fit_chrono_batch(self, times, i_signal, v_signal, **kw):
+        return self._pfrt_fit_core_batch(times, i_signal, v_signal, None, None, **kw)
+
+    def pfrt_fit_hybrid_batch(self, times, i_signal, v_signal, frequencies, z, **kw):
+        return self._pfrt_fit_core_batch(times, i_signal, v_signal, frequencies, z, **kw)
+
+    def _pfrt_fit_core(self, times, i_signal, v_signal, frequencies, z, factors=None, max_iter_per_step=10,
+                       max_init_iter=20, xtol=1e-2, nonneg=True, **kw):
+        """Single-spectrum PFRT.  As in the reference the object's fit attributes afterwards are those of the
+        initial fit (first factor); pfrt_result holds the per-factor outputs."""
+        factors_a, _, kw0 = self._pfrt_setup(factors, max_iter_per_step, max_init_iter, xtol, kw)
+        f0 = factors_a[0]
+        init_kw = dict(kw0, s_0=kw0['s_0'] * f0, l2_lambda_0=kw0['l2_lambda_0'] / f0)
+        v_b = None if v_signal is None else np.asarray(v_signal, dtype=float)[None, :]
+        z_b = None if z is None else np.asarray(z)[None, :]
+        res = self._pfrt_fit_core_batch(times, i_signal, v_b, frequencies, z_b, factors=factors,
+                                        max_iter_per_step=max_iter_per_step, max_init_iter=max_init_iter, xtol=xtol,
+                                        nonneg=nonneg, want_p=True, **kw)
+        pr = res.pfrt_result()
+        self._qphb_fit_core(times, i_signal, v_signal, frequencies, z, nonneg=nonneg, **init_kw)
+        s0 = np.asarray(get_default_hypers(True, self.fit_dop)['s_0'], dtype=float)
+        l20 = get_default_hypers(True, self.fit_dop)['l2_lambda_0']
+        self.pfrt_history = None        # per-iteration history is not exported by the batched kernel
+        self.pfrt_result = {
+            'factors': factors_a, 'step_x': list(pr['step_x'][0]), 'step_llh': list(pr['step_llh'][0]),
+            'step_p_mat': list(pr['step_p_mat'][0]),
+            'step_hypers': [{'s_0': s0 * f, 'l2_lambda_0': l20 / f} for f in factors_a],
+            'step_backgrounds': [None] * len(factors_a), 'step_iters': pr['step_iters'][0],
+        }
+
+    def pfrt_fit_eis(self, frequencies, z, factors=None, max_iter_per_step=10, max_init_iter=20, xtol=1e-2,
+                     nonneg=True, **kw):
+        self._pfrt_fit_core(None, None, None, frequencies, z, factors=factors, max_iter_per_step=max_iter_per_step,
+                            max_init_iter=max_init_iter, xtol=xtol, nonneg=nonneg, **kw)
+
+    def pfrt_fit_chrono(self, times, i_signal, v_signal, factors=None, max_iter_per_step=10, max_init_iter=20,
+                        xtol=1e-2, nonneg=True, **kw):
+        self._pfrt_fit_core(times, i_signal, v_signal, None, None, factors=factors,
+                            max_iter_per_step=max_iter_per_step, max_init_iter=max_init_iter, xtol=xtol,
+                            nonneg=nonneg, **kw)
+
+    def pfrt_fit_hybrid(self, times, i_signal, v_signal, frequencies, z, factors=None, max_iter_per_step=10,
+                        max_init_iter=20, xtol=1e-2, nonneg=True, **kw):
+        self._pfrt_fit_core(times, i_signal, v_signal, frequencies, z, factors=factors,
+                            max_iter_per_step=max_iter_per_step, max_init_iter=max_init_iter, xtol=xtol,
+                            nonneg=nonneg, **kw)
 
     def _store_single(self, res):
         """Populate the attributes DRT._qphb_fit_core leaves behind (drt1d.py:1040-1104)."""

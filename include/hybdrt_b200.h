@@ -179,6 +179,22 @@ typedef struct hdrt_qphb_problem {
     double* resid_ss;      /* [2]   sum of squared residuals of the final x: chrono rows, EIS rows (qphb.py:1347)   */
     double* outlier_t;     /* [N]   1 - outlier probability of the last weight update (qphb.py:1497-1519); required
                                     iff hyp.has_outlier_p                                                            */
+
+    /* PFRT (DRT._pfrt_fit_core, drt1d.py:2558-2698): n_pfrt > 0 turns the call into a fit at s_0 * f_0 and
+     * l2_lambda_0 / f_0 (hyp holds the base values; hyp.max_iter = max_init_iter) followed by one warm-started
+     * continuation (DRT._continue_from_init, :1270-1365) per remaining factor, all inside the kernel.            */
+    int n_pfrt;                 /* number of factors; 0 = plain fit                                                */
+    int pfrt_max_iter;          /* max_iter_per_step (drt1d.py:2558)                                               */
+    int pfrt_min_iter;          /* min_iter of a continuation (drt1d.py:1275): convergence ends it only from here  */
+    const double* pfrt_factors; /* [n_pfrt] device                                                                */
+    double* pfrt_x;             /* [batch][n_pfrt][n]     step_x: final x of every step                            */
+    double* pfrt_llh;           /* [batch][n_pfrt][2]     weighted rss and sum(log w) under weights re-estimated
+                                                          from x alone: the data terms of step_llh (qphb.py:1359)  */
+    double* pfrt_p;             /* [batch][n_pfrt][n][n]  step_p_mat (optional)                                    */
+    int* pfrt_iters;            /* [batch][n_pfrt]        outer iterations per step (optional)                     */
+    double* vz_scratch;         /* [batch][N] work buffer: the vz_offset column a continuation step starts from
+                                                          (drt1d.py:1296-1302); required iff n_pfrt > 1 and
+                                                          vz_index >= 0                                            */
 } hdrt_qphb_problem;
 
 /* Fills `hyp` with the reference defaults (qphb.py:208-255 eff_hp=True, drt1d.py:102-137). */

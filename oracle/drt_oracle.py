@@ -548,7 +548,11 @@ def qphb_continue(prob, state, hypers, max_iter=10, min_iter=2):
     x, w = state['x'].copy(), state['weights'].copy()
     s_vec, rho, dop_rho = [v.copy() for v in state['s_vectors']], state['rho'].copy(), state.get('dop_rho')
     if vz_index is not None:
+        # the prediction matrix is copied once, *with* the vz_offset column of the incoming state
+        # (drt1d.py:1296-1302; the plain fit copies it while that column is still zero, :503-511)
         a, b = prob['vb_range']
+        rm_vz = rm.copy()
+        rm_vz[:, a:b] = 0
         vz_strength = np.asarray(prob['vz_strength'], dtype=float)
     history = []
     it = 0
@@ -569,8 +573,6 @@ def qphb_continue(prob, state, hypers, max_iter=10, min_iter=2):
         history.append(dict(x=x.copy(), s_vectors=np.array(s_vec), rho=rho.copy(), dop_rho=dop_rho, weights=w.copy(),
                             ipm=res['iterations']))
         if vz_index is not None:
-            rm_vz = rm.copy()
-            rm_vz[:, a:b] = 0
             sep = rm_vz @ x
             sep[nc:] *= -1
             rm[:, vz_index] = sep * vz_strength

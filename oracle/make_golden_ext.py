@@ -10,6 +10,8 @@ oracle/refshim.py (authoring container only):
 * chrono_flex.npz     construct_chrono_var_matrix with error_structure=None (mat1d.py:455-490) and the
                       fit_chrono / fit_hybrid results with chrono_error_structure=None (+ outlier_p: the
                       tutorial's flags)
+* pfrt.npz            pfrt_fit_eis / pfrt_fit_hybrid (drt1d.py:2558-2716): per-factor coefficients, marginal
+                      log-likelihood and P matrices of the continuation path
 """
 import os
 import sys
@@ -128,7 +130,36 @@ def gen_chrono_flex():
     np.savez_compressed(os.path.join(OUT, 'chrono_flex.npz'), **d)
 
 
-GENERATORS = dict(outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex)
+def gen_pfrt():
+    """DRT.pfrt_fit_eis / pfrt_fit_hybrid (drt1d.py:2558-2716): per-factor x, llh, P."""
+    freq, z = synth.make_eis_batch(2, seed=0)
+    drt = DRT()
+    rows = []
+    for b in range(2):
+        refshim.QP_LOG.clear()
+        drt.pfrt_fit_eis(freq, z[b])
+        r = drt.pfrt_result
+        rows.append(dict(step_x=np.array(r['step_x']), step_llh=np.array(r['step_llh']),
+                         step_p_diag=np.array([np.diag(p) for p in r['step_p_mat']]),
+                         step_p_last=np.array(r['step_p_mat'][-1]),
+                         n_hist=len(drt.pfrt_history), ipm=int(np.sum(refshim.QP_LOG)),
+                         init_n_outer=len(drt.qphb_history), coefficient_scale=drt.coefficient_scale))
+        print('pfrt eis', b, 'history', rows[-1]['n_hist'], 'init outer', rows[-1]['init_n_outer'], 'ipm', rows[-1]['ipm'])
+    d = {k: np.array([r[k] for r in rows]) for k in rows[0]}
+    d.update(freq=freq, z=z, factors=np.array(drt.pfrt_result['factors']))
+    ts, is_, vs, fh, zh = small_hybrid()
+    refshim.QP_LOG.clear()
+    drt.pfrt_fit_hybrid(ts, is_, vs[0], fh, zh[0], factors=np.logspace(-0.6, 0.6, 5))
+    r = drt.pfrt_result
+    d.update(h_times=ts, h_i=is_, h_v=vs[0], h_freq=fh, h_z=zh[0], h_factors=np.array(r['factors']),
+             h_step_x=np.array(r['step_x']), h_step_llh=np.array(r['step_llh']),
+             h_step_p_diag=np.array([np.diag(p) for p in r['step_p_mat']]), h_n_hist=len(drt.pfrt_history),
+             h_ipm=int(np.sum(refshim.QP_LOG)))
+    print('pfrt hybrid: history', d['h_n_hist'], 'ipm', d['h_ipm'])
+    np.savez_compressed(os.path.join(OUT, 'pfrt.npz'), **d)
+
+
+GENERATORS = dict(outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex, pfrt=gen_pfrt)
 
 
 def main():

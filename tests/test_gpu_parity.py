@@ -390,6 +390,46 @@ def test_flexible_chrono_error_structure(eng, orc):
         drt.fit_chrono(g['times'], g['i_signal'], g['v_signal'][1], error_structure='nonsense')
 
 
+def test_pfrt_continuation(eng, orc, lookup_golden):
+    """PFRT (drt1d.py:2558-2716): the initial fit and every warm-started continuation step inside one launch,
+    against the unmodified reference (EIS and hybrid) and, kernel only, against the oracle."""
+    from hybdrt_b200.models import DRT
+    g = load_golden('pfrt.npz')
+    prep = orc.EisPrep(g['freq'], tables=lookup_golden)
+    rvs = np.array([prep.problem(zz)[0]['rv'] for zz in g['z']])
+    hyp = E_default_hypers(max_iter=20)
+    out = _eis_launch(eng, prep, rvs, hypers=hyp, pfrt=dict(factors=g['factors'], want_p=True))
+    for b in range(2):
+        assert int(out['pfrt_iters'][b].sum()) == int(g['n_hist'][b])
+        assert int(out['n_outer'][b]) == int(g['init_n_outer'][b]) and int(out['n_ipm'][b]) == int(g['ipm'][b])
+        assert rel_err(out['pfrt_x'][b], g['step_x'][b]) < FIT_TOL
+        assert rel_err(np.diagonal(out['pfrt_p'][b], axis1=1, axis2=2), g['step_p_diag'][b]) < FIT_TOL
+        assert rel_err(out['pfrt_p'][b, -1], g['step_p_last'][b]) < FIT_TOL
+    drt = DRT()
+    res = drt.pfrt_fit_eis_batch(g['freq'], g['z'])
+    pr = res.pfrt_result()
+    assert rel_err(pr['step_x'], g['step_x']) < FIT_TOL
+    assert np.max(np.abs(pr['step_llh'] - g['step_llh']) / np.abs(g['step_llh'])) < FIT_TOL
+    drt.pfrt_fit_eis(g['freq'], g['z'][1])
+    assert rel_err(np.array(drt.pfrt_result['step_x']), g['step_x'][1]) < FIT_TOL
+    assert rel_err(drt.pfrt_result['step_p_mat'][-1], g['step_p_last'][1]) < FIT_TOL
+    assert drt.qphb_params['n_outer'] == int(g['init_n_outer'][1])               # attributes = the initial fit
+    assert rel_err(drt.cvx_result['x'] , g['step_x'][1][0]) < FIT_TOL
+    drt.pfrt_fit_hybrid(g['h_times'], g['h_i'], g['h_v'], g['h_freq'], g['h_z'], factors=g['h_factors'])
+    assert int(np.sum(drt.pfrt_result['step_iters'])) == int(g['h_n_hist'])
+    assert rel_err(np.array(drt.pfrt_result['step_x']), g['h_step_x']) < FIT_TOL
+    assert np.max(np.abs(np.array(drt.pfrt_result['step_llh']) - g['h_step_llh']) / np.abs(g['h_step_llh'])) < FIT_TOL
+    assert rel_err(np.array([np.diag(m) for m in drt.pfrt_result['step_p_mat']]), g['h_step_p_diag']) < FIT_TOL
+
+
+def E_default_hypers(**kw):
+    from hybdrt_b200 import engine as E
+    hyp = E.default_hypers()
+    for k, v in kw.items():
+        setattr(hyp, k, v)
+    return hyp
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')

@@ -193,6 +193,36 @@ def test_flexible_chrono_error_structure_matches_reference(tables):
     assert rel_err(res['x'], g['chrono_cvx_x']) < 1e-8
 
 
+def test_pfrt_matches_reference(tables):
+    """DRT.pfrt_fit_eis / pfrt_fit_hybrid: per-factor x, marginal llh and P of the continuation path."""
+    g = load_golden('pfrt.npz')
+    prep = orc.EisPrep(g['freq'], tables=tables)
+    for b in range(2):
+        prob, _ = prep.problem(g['z'][b])
+        r = orc.pfrt_fit(prob)
+        assert sum(st['n_iter'] for st in r['steps']) == int(g['n_hist'][b])
+        assert r['init']['n_outer'] == int(g['init_n_outer'][b])
+        assert rel_err(np.array([st['x'] for st in r['steps']]), g['step_x'][b]) < 1e-8
+        llh = np.array([st['llh'] for st in r['steps']])
+        assert np.max(np.abs(llh - g['step_llh'][b]) / np.abs(g['step_llh'][b])) < 1e-8
+        assert rel_err(np.array([np.diag(st['p_matrix']) for st in r['steps']]), g['step_p_diag'][b]) < 1e-8
+        assert rel_err(r['steps'][-1]['p_matrix'], g['step_p_last'][b]) < 1e-8
+    hs = load_golden('hybrid_small.npz')                  # same trace and spectrum as the hybrid PFRT fixture
+    rm0 = hs['rm'].copy()
+    rm0[:, 1] = 0
+    n, nc = rm0.shape[1], hs['times'].size
+    h = np.zeros(n)
+    h[:2] = 1000
+    prob = dict(rm=rm0, rv=hs['rv'], vmm=dict(n_chrono=nc, chrono=None, eis=orc.eis_vmm(hs['freq'])),
+                pen=_layout_pen(hs['basis_tau'], float(tables['eps']), [1e-6, 1.0, 1e-6, 1e-6]), h=h, l1=np.zeros(n),
+                n_special=4, vz_index=1, vb_range=(0, 1), vz_strength=hs['vz_strength_vec'], n_chrono=nc)
+    r = orc.pfrt_fit(prob, factors=g['h_factors'])
+    assert sum(st['n_iter'] for st in r['steps']) == int(g['h_n_hist'])
+    assert rel_err(np.array([st['x'] for st in r['steps']]), g['h_step_x']) < 1e-7
+    llh = np.array([st['llh'] for st in r['steps']])
+    assert np.max(np.abs(llh - g['h_step_llh']) / np.abs(g['h_step_llh'])) < 1e-7
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
