@@ -137,6 +137,8 @@ struct Ctx {
     double* vz0;    // global, per spectrum: vz_offset column frozen at the start of a continuation step, else NULL
     double* t_out;  // global, per spectrum: outlier_t (only with outlier_p)
     double outlier_p;  // < 0: no outlier error structure
+    double rv_scale;   // running data scale (solve_rp / update_scale): the data vector is rv * rv_scale
+    double dop_cs;     // column scale of the DOP block of rm (solve_rp's DOP rescale), 1 otherwise
     int red_phase;
 };
 
@@ -294,7 +296,8 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
         {
             const int rq = r0 + 2 * (tid & 3);       // q = -rm^T (w^2 rv): rv straight from global (issued early)
             const double2 w2q = lds2(w2 + rq);
-            const double2 wv = make_double2(rq < N ? w2q.x * c.rv[rq] : 0.0, rq + 1 < N ? w2q.y * c.rv[rq + 1] : 0.0);
+            const double2 wv = make_double2(rq < N ? w2q.x * (c.rv[rq] * c.rv_scale) : 0.0,
+                                            rq + 1 < N ? w2q.y * (c.rv[rq + 1] * c.rv_scale) : 0.0);
 #pragma unroll
             for (int u = 0; u < QU; ++u) {
                 const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
@@ -359,7 +362,12 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
                             const double* us = C::vec(C::US0 + k);
                             acc += (us[r] * m) * us[cc];
                         }
-                        v = acc - *e;
+                        double gram = *e;     // negated Gram entry
+                        if (dopb) {           // DOP columns of rm carry the per-spectrum rescale (drt1d.py:589-596)
+                            if (r >= c.dop_a && r < c.dop_b) gram *= c.dop_cs;
+                            if (cc >= c.dop_a && cc < c.dop_b) gram *= c.dop_cs;
+                        }
+                        v = acc - gram;
                         if (p_out && cc <= r) {
                             p_out[(size_t)r * n + cc] = v;
                             p_out[(size_t)cc * n + r] = v;
@@ -378,7 +386,8 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
         const int col = (tid + C::kThreads * u) >> 2;
         const double s = reduce_q(qacc[u]);
         if ((tid & 3) == 0 && col < n) {
-            const double qv = -s + (l1_scalar ? l1_value : c.l1[col]);
+            const double sc = (col >= c.dop_a && col < c.dop_b) ? s * c.dop_cs : s;
+            const double qv = -sc + (l1_scalar ? l1_value : c.l1[col]);
             C::vec(C::QS)[col] = qv;
             if (q_out) q_out[col] = qv;
         }
@@ -1083,6 +1092,13 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     // residuals: one warp per row, four rows per pass.  All loads of a pass (L2 hits, several hundred cycles
     // each) are issued before the first use: row / column indices are clamped instead of branched around.
     constexpr int RU = 4, CU = (C::NV + 31) / 32;
+    double xw[CU];     // this lane's coefficients (DOP ones with the column rescale of solve_rp folded in)
+#pragma unroll
+    for (int w = 0; w < CU; ++w) {
+        const int col = lane + 32 * w;
+        xw[w] = (col < n) ? xs[col] : 0.0;
+        if (col >= c.dop_a && col < c.dop_b) xw[w] *= c.dop_cs;
+    }
     for (int rb = warp; rb < N; rb += RU * C::kWarps) {
         double v[RU][CU];
 #pragma unroll
@@ -1099,7 +1115,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
             for (int w = 0; w < CU; ++w) {
                 const int col = lane + 32 * w;
                 if (col < n) {
-                    const double t = ((col == c.vz) ? c.vzcol[r] : v[u][w]) * xs[col];
+                    const double t = ((col == c.vz) ? c.vzcol[r] : v[u][w]) * xw[w];
                     acc += t;
                     if (col != c.vz && (col < c.vb_a || col >= c.vb_b)) accv += t;
                 }
@@ -1107,7 +1123,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
             acc = warp_sum(acc);
             if (update_vz) accv = warp_sum(accv);
             if (lane == 0 && rb + u * C::kWarps < N) {
-                const double resid = acc - c.rv[r];
+                const double resid = acc - c.rv[r] * c.rv_scale;
                 C::rowr2(c.N)[r] = resid * resid;
                 if (update_vz) {
                     // a continuation predicts with the vz_offset column it started from (drt1d.py:1296-1302 copies
@@ -1254,6 +1270,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     c.outlier_p = outl ? hy.outlier_p : -1.0;
     c.t_out = outl ? p.outlier_t + (size_t)b * N : nullptr;
     c.vz0 = nullptr;
+    c.rv_scale = 1.0;
+    c.dop_cs = 1.0;
+    double us_factor = 1.0;   // product of the update_scale factors (drt1d.py:914-936)
     double* est_g = p.est_weights + (size_t)b * N;
 
     // var floor = var(y) * 1e-7 (qphb.py:1560-1561)
@@ -1319,7 +1338,8 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
 #pragma unroll
     for (int k = 0; k < 3; ++k) hd.s_0[k] = hy.s_0[k] * fac;
     const int max_it = cont ? p.pfrt_max_iter : hy.max_iter;
-    it = cont ? 0 : (outl ? -2 : -1);   // -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
+    const bool solve_rp = hy.solve_rp != 0;
+    it = cont ? 0 : (solve_rp ? -3 : (outl ? -2 : -1));   // -3: estimate_x_rp (qphb.py:1684-1717); -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
                                         // the initialisation runs twice (-2, -1), the second time weighted by the
                                         // first estimate
     conv = false;
@@ -1331,6 +1351,25 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
 #pragma unroll 1
     while (true) {
         const bool init = it < 0;
+        if (hy.update_scale && !init && !cont && !final_pq && it > 1) {
+            // keep the data at the requested rp_scale as the Rp estimate improves (drt1d.py:914-936)
+            const bool drt = tid >= c.ns && tid < n;
+            double t1[1] = {drt ? fabs(xi) : 0.0};
+            block_reduce<C, 1, 0u>(t1, c);
+            const double sf = sqrt(hy.rp_scale / (t1[0] * hy.basis_area));   // damped (drt1d.py:919)
+            xi *= sf;
+            c.rv_scale *= sf;
+            us_factor *= sf;
+            var_floor *= sf * sf;
+            const double sq = sqrt(sf);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { xmx[k] *= sq; dop_xmx[k] *= sq; }
+            for (int r = tid; r < N; r += C::kThreads) {
+                est_g[r] /= sf;
+                C::roww()[r] /= sf;
+            }
+            __syncthreads();
+        }
         const double x_in = xi;
         // weights entering the Gram: 1 (init) / weight factors (drt1d.py:881-892) / scaled weights (:991-1008)
         if (!init) {
@@ -1347,8 +1386,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             }
         }
         {
-            const double lam0 = init ? hy.iw_l2_lambda_0 : lam_step;
-            const double dlam0 = init ? hy.dop_l2_lambda_0 * (hy.iw_l2_lambda_0 / lam_step) : hy.dop_l2_lambda_0;
+            const double lam_iw = (it == -3) ? 1e-4 : hy.iw_l2_lambda_0;   // estimate_x_rp: l2_lambda_0 = 1e-4 (drt1d.py:5425)
+            const double lam0 = init ? lam_iw : lam_step;
+            const double dlam0 = init ? hy.dop_l2_lambda_0 * (lam_iw / lam_step) : hy.dop_l2_lambda_0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 f.drt[k] = lam0 * hy.derivative_weights[k] * rho[k];
@@ -1357,7 +1397,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
         __syncthreads();
         PROF_ADD(0);
-        gram_phase<C>(c, f, init, hy.iw_l1_lambda_0, (final_pq && p.p_matrix) ? p.p_matrix + (size_t)b * n * n : nullptr,
+        gram_phase<C>(c, f, init, (it == -3) ? 1e-3 : hy.iw_l1_lambda_0, (final_pq && p.p_matrix) ? p.p_matrix + (size_t)b * n * n : nullptr,
                         (final_pq && p.q_vector) ? p.q_vector + (size_t)b * n : nullptr);
         if (final_pq) {
             if (p.dist_var && !postfit_variance<C>(c, p.eval_mat, p.n_eval, p.dist_var + (size_t)b * p.n_eval))
@@ -1373,6 +1413,21 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (qo.fatal) { fatal = true; xi = qo.xi; break; }
         if (tid < n) C::vec(C::XS)[tid] = qo.xi;
         __syncthreads();
+        if (it == -3) {
+            // DRT._solve_data_scale (drt1d.py:5421-5437, applied at :573-607): Rp from a lightly regularised
+            // elastic-net solution; the data are rescaled to rp_scale, the DOP columns to the DRT magnitude
+            const bool drt = tid >= c.ns && tid < n;
+            const bool dopc = tid >= c.dop_a && tid < c.dop_b;
+            double t3[3] = {drt ? fabs(qo.xi) : 0.0, drt ? fabs(qo.xi) : 0.0, dopc ? fabs(qo.xi) : 0.0};
+            block_reduce<C, 3, 0x6u>(t3, c);
+            const double sf = hy.rp_scale / (t3[0] * hy.basis_area);
+            c.rv_scale *= sf;
+            var_floor *= sf * sf;
+            if (c.dop_a >= 0 && hy.normalize_dop) c.dop_cs = 1.0 / (t3[1] / t3[2]);
+            if (tid == 0 && p.scale_factors) p.scale_factors[3 * (size_t)b] = sf;
+            it = outl ? -2 : -1;
+            continue;
+        }
         if (init) {
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
             weights_phase<C>(c, nullptr, var_floor, false, outl);
@@ -1483,6 +1538,11 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             if (p.xmx_norms) p.xmx_norms[(size_t)b * 3 + k] = xmx[k];
             if (p.dop_rho) p.dop_rho[(size_t)b * 3 + k] = dop_rho[k];
             if (p.dop_xmx_norms) p.dop_xmx_norms[(size_t)b * 3 + k] = dop_xmx[k];
+        }
+        if (p.scale_factors) {
+            if (!hy.solve_rp) p.scale_factors[3 * (size_t)b] = 1.0;
+            p.scale_factors[3 * (size_t)b + 1] = us_factor;
+            p.scale_factors[3 * (size_t)b + 2] = c.dop_cs;
         }
         if (p.fun) p.fun[b] = fun;
         if (p.n_outer) p.n_outer[b] = p.n_pfrt > 0 ? n_outer0 : (it < 0 ? 0 : it);
@@ -1600,6 +1660,10 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (p.n_pfrt > 0 && (!p.pfrt_factors || !p.pfrt_x || !p.pfrt_llh || !p.weights || p.pfrt_max_iter <= 0 ||
                          p.p_matrix || p.dist_var)) {
         set_error("PFRT needs pfrt_factors, pfrt_x, pfrt_llh, weights and pfrt_max_iter > 0 (and no p_matrix / dist_var)");
+        return HDRT_ERR_ARG;
+    }
+    if ((p.hyp.solve_rp || p.hyp.update_scale) && (!p.scale_factors || !(p.hyp.rp_scale > 0.0) || !(p.hyp.basis_area > 0.0))) {
+        set_error("solve_rp / update_scale need scale_factors, rp_scale > 0 and basis_area > 0");
         return HDRT_ERR_ARG;
     }
     if (p.n_pfrt > 1 && p.vz_index >= 0 && !p.vz_scratch) { set_error("PFRT with a vz_offset column needs vz_scratch"); return HDRT_ERR_ARG; }

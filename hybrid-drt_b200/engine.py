@@ -31,7 +31,8 @@ class Hypers(C.Structure):
         ('xtol', C.c_double), ('weight_factor', C.c_double),
         ('chrono_weight_factor', C.c_double), ('eis_weight_factor', C.c_double),
         ('has_iw_prior', C.c_int), ('max_iter', C.c_int),
-        ('outlier_p', C.c_double), ('has_outlier_p', C.c_int), ('reserved_', C.c_int),
+        ('outlier_p', C.c_double), ('has_outlier_p', C.c_int), ('solve_rp', C.c_int),
+        ('update_scale', C.c_int), ('normalize_dop', C.c_int), ('rp_scale', C.c_double), ('basis_area', C.c_double),
     ]
 
 
@@ -54,7 +55,7 @@ class Problem(C.Structure):
         ('s_vectors', _P), ('rho', _P), ('dop_rho', _P), ('xmx_norms', _P), ('dop_xmx_norms', _P),
         ('fun', _P), ('vz_col', _P), ('p_matrix', _P), ('q_vector', _P),
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
-        ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P),
+        ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P), ('scale_factors', _P),
         ('n_pfrt', C.c_int), ('pfrt_max_iter', C.c_int), ('pfrt_min_iter', C.c_int), ('pfrt_factors', _P),
         ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('vz_scratch', _P),
     ]
@@ -335,6 +336,8 @@ class Engine:
             p.resid_ss = _ptr(buf('resid_ss', b, 2))
         if hyp.has_outlier_p:
             p.outlier_t = _ptr(buf('outlier_t', b, n_rows))
+        if hyp.solve_rp or hyp.update_scale:
+            p.scale_factors = _ptr(buf('scale_factors', b, 3))
         if pfrt is not None:           # dict(factors=..., max_iter_per_step=10, min_iter=2, want_p=False)
             fac = self.dev(np.asarray(pfrt['factors'], dtype=float))
             o['pfrt_factors'] = fac

@@ -246,7 +246,10 @@ class BatchFit:
         if 'x_dop' in sp:
             a = sp['x_dop']['index']
             b = a + sp['x_dop']['size']
-            out['x_dop'] = x[:, a:b] * (pl['dop_scale_vector'][None, :] * cs)
+            dsv = pl['dop_scale_vector'][None, :]
+            if 'dop_column_scale' in sc:
+                dsv = dsv * sc['dop_column_scale'][:, None]
+            out['x_dop'] = x[:, a:b] * (dsv * cs)
         # sigma from the unscaled weights (drt1d.py:1082-1092)
         w_true = h['weights'] * pl['weight_factor']
         sig = 1.0 / w_true
@@ -691,6 +694,11 @@ class DRT:
         ch.weight_factor = float(kw['weight_factor'])
         ch.chrono_weight_factor = float(kw['chrono_weight_factor'])
         ch.eis_weight_factor = float(kw['eis_weight_factor'])
+        if kw.get('solve_rp') or kw.get('update_scale'):          # drt1d.py:573-607, :914-936
+            ch.solve_rp, ch.update_scale = int(bool(kw.get('solve_rp'))), int(bool(kw.get('update_scale')))
+            ch.normalize_dop = int(bool(self.fit_dop and self.normalize_dop))
+            ch.rp_scale = float(hyp['rp_scale'])
+            ch.basis_area = float(np.sqrt(np.pi) / self.tau_epsilon)
         if hyp.get('outlier_p') is not None:                     # qphb.py:232; error structure qphb.py:1497-1538
             ch.has_outlier_p, ch.outlier_p = 1, float(hyp['outlier_p'])
         return ch
@@ -728,7 +736,7 @@ class DRT:
                         eis_weight_factor=None, chrono_weight_factor=None, hybrid_weight_factor_method=None,
                         eff_hp=True, weight_factor=1, xtol=1e-2, max_iter=50, peak_locations=None, **kw):
         # options outside the hot path (same keyword names as drt1d.py:102-137)
-        for flag, name in ((series_neg, 'series_neg'), (update_scale, 'update_scale'), (solve_rp, 'solve_rp'),
+        for flag, name in ((series_neg, 'series_neg'),
                            (downsample, 'downsample'), (subtract_background, 'subtract_background'),
                            (remove_extremes, 'remove_extremes'),
                            (init_weights_separately, 'init_weights_separately'),
@@ -771,7 +779,10 @@ class DRT:
                     eis_reim_cor=eis_reim_cor, iw_l1_lambda_0=iw_l1_lambda_0, iw_l2_lambda_0=iw_l2_lambda_0,
                     vz_offset=vz_offset, vz_offset_scale=vz_offset_scale, vz_offset_eps=vz_offset_eps,
                     eis_weight_factor=eis_weight_factor, chrono_weight_factor=chrono_weight_factor,
-                    weight_factor=weight_factor, xtol=xtol, max_iter=max_iter)
+                    weight_factor=weight_factor, xtol=xtol, max_iter=max_iter,
+                    solve_rp=bool(solve_rp and scale_data), update_scale=bool(update_scale and scale_data))
+        if solve_rp and not scale_data and self.warn:
+            warnings.warn('solve_rp is ignored if scale_data=False')
         self.v_baseline_deg, self.v_baseline_sqrt = v_baseline_deg, v_baseline_sqrt
         if z_batch is not None:
             z_batch = np.asarray(z_batch)
@@ -833,7 +844,21 @@ class DRT:
             if self.fit_dop:
                 plan['zm_dop_host'] = plan['zm_dop_dev'].cpu().numpy()
         copied.synchronize()        # the pinned staging buffer may be refilled by the next call from here on
-        res = BatchFit(plan, raw, scales, dict(rv=rv.copy() if want_pq else None, h2d_bytes=rv.nbytes))
+        rv_host = rv.copy() if want_pq else None
+        if opts['solve_rp'] or opts['update_scale']:
+            # DRTBase.update_data_scale (drtbase.py:516-536, galvanostatic) with the factors the kernel applied
+            torch.cuda.current_stream(eng.device).synchronize()
+            sf = raw['scale_factors'].cpu().numpy()
+            tot = sf[:, 0] * sf[:, 1]
+            scales['coefficient_scale'] = scales['coefficient_scale'] / tot
+            if nc:
+                scales['response_signal_scale'] = scales['response_signal_scale'] / tot
+                scales['scaled_response_offset'] = scales['scaled_response_offset'] * tot
+            scales['update_scale_factor'] = sf[:, 1]
+            scales['dop_column_scale'] = sf[:, 2]          # dop_scale_vector /= dop_rescale_factor (drt1d.py:589-592)
+            if rv_host is not None:
+                rv_host *= tot[:, None]
+        res = BatchFit(plan, raw, scales, dict(rv=rv_host, h2d_bytes=rv.nbytes))
         self.last_batch = res
         self.fit_type = f"qphb_{plan['data_type']}"
         return res
@@ -1067,8 +1092,16 @@ class DRT:
             rm[:, pl['special_qp_params']['vz_offset']['index']] = h['vz_col'][0]
         pen = pl['pen'].cpu().numpy()
         x_of = h['x_overfit'][0]
+        init_w = h['init_weights'][0]
+        if 'update_scale_factor' in sc:                     # drt1d.py:924-933, :589-596
+            x_of = x_of * sc['update_scale_factor'][0]
+            init_w = init_w / sc['update_scale_factor'][0]
+            if self.fit_dop:
+                a, b = self.dop_indices
+                rm[:, a:b] *= sc['dop_column_scale'][0]
+                self.dop_scale_vector = self.dop_scale_vector * sc['dop_column_scale'][0]
         self.qphb_params = {
-            'est_weights': h['est_weights'][0], 'init_weights': h['init_weights'][0], 'weights': w_scaled,
+            'est_weights': h['est_weights'][0], 'init_weights': init_w, 'weights': w_scaled,
             'true_weights': w_true, 'xmx_norms': h['xmx_norms'][0],
             'dop_xmx_norms': h['dop_xmx_norms'][0] if 'dop_xmx_norms' in h else np.ones(3),
             'x_overfit_chrono': x_of if pl['data_type'] == 'chrono' else (x_of[:nc] if nc else None),

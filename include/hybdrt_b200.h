@@ -122,7 +122,12 @@ typedef struct hdrt_hypers {
     int max_iter; /* drt1d.py:135 */
     double outlier_p;  /* prior probability of a point being an outlier (qphb.py:232, :1497-1538); read iff has_outlier_p */
     int has_outlier_p; /* 0 = hypers['outlier_p'] is None */
-    int reserved_;
+    int solve_rp;      /* drt1d.py:573-607 + qphb.estimate_x_rp :1684-1717: rescale the data (and the DOP columns)
+                          from a lightly regularised solution before the weight initialisation                  */
+    int update_scale;  /* drt1d.py:914-936: damped rescaling of the data from iteration 2 on                       */
+    int normalize_dop; /* DOP column rescale of solve_rp (drt1d.py:586)                                            */
+    double rp_scale;   /* hypers['rp_scale'] (qphb.py:213); read iff solve_rp or update_scale                      */
+    double basis_area; /* area of one basis function, sqrt(pi) / epsilon (predict_r_p, drt1d.py:3552-3571)         */
 } hdrt_hypers;
 
 typedef struct hdrt_qphb_problem {
@@ -179,6 +184,10 @@ typedef struct hdrt_qphb_problem {
     double* resid_ss;      /* [2]   sum of squared residuals of the final x: chrono rows, EIS rows (qphb.py:1347)   */
     double* outlier_t;     /* [N]   1 - outlier probability of the last weight update (qphb.py:1497-1519); required
                                     iff hyp.has_outlier_p                                                            */
+
+    double* scale_factors; /* [3]   solve_rp data factor, product of the update_scale factors, DOP column factor
+                                    (the data vector the fit ended on is rv * [0] * [1]); required iff solve_rp or
+                                    update_scale                                                                    */
 
     /* PFRT (DRT._pfrt_fit_core, drt1d.py:2558-2698): n_pfrt > 0 turns the call into a fit at s_0 * f_0 and
      * l2_lambda_0 / f_0 (hyp holds the base values; hyp.max_iter = max_init_iter) followed by one warm-started

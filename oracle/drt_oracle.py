@@ -447,6 +447,21 @@ def qphb_fit(prob, hypers=None, record_history=False):
         ipm_log.append(res['iterations'])
         return res
 
+    # solve_rp (drt1d.py:573-607, qphb.estimate_x_rp :1684-1717, DRT._solve_data_scale drt1d.py:5421-5437)
+    rp_factor, us_factor, dop_cs = 1.0, 1.0, 1.0
+    rp_scale, area = hyp.get('rp_scale', 14.0), prob.get('basis_area')
+    if prob.get('solve_rp'):
+        l2_rp = l2_matrix(pen, s_vec, rho, dop_rho, hyp, ns, dop_range, l2_lambda_0=1e-4)
+        x_rp = qp(rm, rv, l2_rp, 1e-3)['x']
+        rp_factor = rp_scale / (np.sum(np.abs(x_rp[ns:])) * area)
+        rv = rv * rp_factor
+        if dop_range is not None and prob.get('normalize_dop', True):
+            a, b = dop_range
+            dop_cs = 1.0 / (np.max(np.abs(x_rp[ns:])) / np.max(np.abs(x_rp[a:b])))
+            rm[:, a:b] *= dop_cs
+            if vz_index is not None:
+                rm_vz[:, a:b] *= dop_cs
+
     # initialize_weights, qphb.py:1609-1681 with iw hypers of drt1d.py:640-645
     l2_iw = l2_matrix(pen, s_vec, rho, dop_rho, hyp, ns, dop_range, l2_lambda_0=prob.get('iw_l2', 1e-4))
     outlier_p = hyp.get('outlier_p')
@@ -482,6 +497,17 @@ def qphb_fit(prob, hypers=None, record_history=False):
             w[nc:] *= ewf
         if it > 0:
             w = w * wf
+        if it > 1 and prob.get('update_scale'):                                  # drt1d.py:914-936
+            sf = (rp_scale / (np.sum(np.abs(x[ns:])) * area)) ** 0.5
+            x_in = x_in * sf
+            x_overfit = x_overfit * sf
+            rv = rv * sf
+            xmx = xmx * sf ** 0.5
+            dop_xmx = dop_xmx * sf ** 0.5
+            est_w = est_w / sf
+            init_w = init_w / sf
+            w = w / sf
+            us_factor *= sf
         wrm = w[:, None] * rm
         wrv = w * rv
         l2 = l2_matrix(pen, s_vec, rho, dop_rho, hyp, ns, dop_range)
@@ -520,7 +546,7 @@ def qphb_fit(prob, hypers=None, record_history=False):
         est_weights=est_w, init_weights=init_w, x_overfit=x_overfit,
         s_vectors=np.array(s_vec), rho=rho, dop_rho=dop_rho, xmx_norms=xmx, dop_xmx_norms=dop_xmx,
         n_outer=it, converged=conv, ipm_iters=np.array(ipm_log), outlier_t=outlier_t,
-        init_outlier_t=init_outlier_t,
+        init_outlier_t=init_outlier_t, scale_factors=np.array([rp_factor, us_factor, dop_cs]),
         p_matrix=l2 + wrm.T @ wrm, q_vector=-wrm.T @ (w_scaled * rv) + l1, rm_final=rm,
     )
     if record_history:

@@ -10,6 +10,7 @@ oracle/refshim.py (authoring container only):
 * chrono_flex.npz     construct_chrono_var_matrix with error_structure=None (mat1d.py:455-490) and the
                       fit_chrono / fit_hybrid results with chrono_error_structure=None (+ outlier_p: the
                       tutorial's flags)
+* rescale.npz         solve_rp (drt1d.py:573-607, qphb.py:1684-1717) and update_scale (drt1d.py:914-936) fits
 * pfrt.npz            pfrt_fit_eis / pfrt_fit_hybrid (drt1d.py:2558-2716): per-factor coefficients, marginal
                       log-likelihood and P matrices of the continuation path
 """
@@ -159,7 +160,56 @@ def gen_pfrt():
     np.savez_compressed(os.path.join(OUT, 'pfrt.npz'), **d)
 
 
-GENERATORS = dict(outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex, pfrt=gen_pfrt)
+def gen_rescale():
+    """solve_rp (drt1d.py:573-607) and update_scale (:914-936): EIS, DRT+DOP and hybrid."""
+    d = {}
+    freq, z = synth.make_eis_batch(2, seed=6)
+    z = z * np.array([3.0, 0.2])[:, None]            # Rp estimates that start away from the target scale
+    drt = DRT()
+    cases = (('us', dict(update_scale=True)), ('rp', dict(solve_rp=True)), ('both', dict(solve_rp=True, update_scale=True)))
+    for tag, kw in cases:
+        rows = []
+        for b in range(2):
+            refshim.QP_LOG.clear()
+            drt.fit_eis(freq, z[b], **kw)
+            o = fit_outputs(drt, freq)
+            o['ipm'] = int(np.sum(refshim.QP_LOG))
+            rows.append(o)
+            print('rescale eis', tag, b, 'outer', o['n_outer'], 'scale', o['coefficient_scale'])
+        for k in ('cvx_x', 'x', 'R_inf', 'inductance', 'weights', 'est_weights', 'init_weights', 'n_outer', 'z_pred',
+                  'coefficient_scale', 'rv', 'x_overfit_eis', 'xmx_norms', 'ipm', 'q_vector'):
+            d[f'{tag}_{k}'] = np.array([r[k] for r in rows])
+    d.update(freq=freq, z=z)
+    fd, zd = synth.make_dop_batch(2, seed=2)
+    drt_d = DRT(fit_dop=True)
+    rows = []
+    for b in range(2):
+        refshim.QP_LOG.clear()
+        drt_d.fit_eis(fd, zd[b], solve_rp=True)
+        o = fit_outputs(drt_d, fd)
+        o['ipm'] = int(np.sum(refshim.QP_LOG))
+        o['dop_scale_vector'] = drt_d.dop_scale_vector.copy()
+        o['rm'] = drt_d.qphb_params['rm'].copy()
+        rows.append(o)
+        print('rescale dop', b, 'outer', o['n_outer'], 'scale', o['coefficient_scale'])
+    for k in ('cvx_x', 'x', 'x_dop', 'R_inf', 'inductance', 'weights', 'n_outer', 'z_pred', 'coefficient_scale',
+              'dop_scale_vector', 'ipm', 'dop_rho_vector'):
+        d[f'dop_{k}'] = np.array([r[k] for r in rows])
+    d['dop_rm0'] = rows[0]['rm']
+    d.update(dop_freq=fd, dop_z=zd)
+    ts, is_, vs, fh, zh = small_hybrid()
+    refshim.QP_LOG.clear()
+    drt.fit_hybrid(ts, is_, vs[0], fh, zh[0], solve_rp=True, update_scale=True)
+    o = fit_outputs(drt, fh)
+    for k in ('cvx_x', 'x', 'R_inf', 'v_baseline', 'vz_offset', 'n_outer', 'z_pred', 'coefficient_scale', 'weights'):
+        d[f'hyb_{k}'] = np.asarray(o[k])
+    d.update(hyb_ipm=int(np.sum(refshim.QP_LOG)), hyb_response_signal_scale=drt.response_signal_scale,
+             hyb_scaled_response_offset=drt.scaled_response_offset, hyb_v_pred=drt.predict_response(ts))
+    print('rescale hybrid: outer', o['n_outer'], 'scale', o['coefficient_scale'])
+    np.savez_compressed(os.path.join(OUT, 'rescale.npz'), **d)
+
+
+GENERATORS = dict(outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex, pfrt=gen_pfrt, rescale=gen_rescale)
 
 
 def main():

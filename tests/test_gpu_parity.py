@@ -430,13 +430,60 @@ def E_default_hypers(**kw):
     return hyp
 
 
+def test_solve_rp_and_update_scale():
+    """solve_rp (drt1d.py:573-607, qphb.py:1684-1717) and update_scale (drt1d.py:914-936) against the unmodified
+    reference: EIS, DRT + DOP (column rescale of the DOP block) and hybrid (chrono scale attributes)."""
+    from hybdrt_b200.models import DRT
+    g = load_golden('rescale.npz')
+    drt = DRT()
+    for tag, kw in (('us', dict(update_scale=True)), ('rp', dict(solve_rp=True)),
+                    ('both', dict(solve_rp=True, update_scale=True))):
+        res = drt.fit_eis_batch(g['freq'], g['z'], **kw)
+        h, fp = res.host(), res.fit_parameters()
+        assert np.array_equal(h['n_outer'], g[f'{tag}_n_outer']) and np.array_equal(h['n_ipm'], g[f'{tag}_ipm'])
+        for b in range(2):
+            assert rel_err(h['x'][b], g[f'{tag}_cvx_x'][b]) < FIT_TOL
+            assert rel_err(fp['x'][b], g[f'{tag}_x'][b]) < FIT_TOL
+            assert abs(res.scales['coefficient_scale'][b] / g[f'{tag}_coefficient_scale'][b] - 1) < FIT_TOL
+            assert rel_err(res.predict_z()[b], g[f'{tag}_z_pred'][b]) < FIT_TOL
+        drt.fit_eis(g['freq'], g['z'][1], **kw)
+        qp = drt.qphb_params
+        assert rel_err(qp['rv'], g[f'{tag}_rv'][1]) < FIT_TOL and rel_err(qp['q_vector'], g[f'{tag}_q_vector'][1]) < FIT_TOL
+        assert rel_err(qp['est_weights'], g[f'{tag}_est_weights'][1]) < FIT_TOL
+        assert rel_err(qp['init_weights'], g[f'{tag}_init_weights'][1]) < FIT_TOL
+        assert rel_err(qp['x_overfit_eis'], g[f'{tag}_x_overfit_eis'][1]) < FIT_TOL
+        assert rel_err(qp['xmx_norms'], g[f'{tag}_xmx_norms'][1]) < FIT_TOL
+    dd = DRT(fit_dop=True)
+    res = dd.fit_eis_batch(g['dop_freq'], g['dop_z'], solve_rp=True)
+    h, fp = res.host(), res.fit_parameters()
+    assert np.array_equal(h['n_outer'], g['dop_n_outer']) and np.array_equal(h['n_ipm'], g['dop_ipm'])
+    for b in range(2):
+        assert rel_err(h['x'][b], g['dop_cvx_x'][b]) < FIT_TOL
+        assert rel_err(fp['x_dop'][b], g['dop_x_dop'][b]) < FIT_TOL
+        assert rel_err(h['dop_rho'][b], g['dop_dop_rho_vector'][b]) < FIT_TOL
+        assert rel_err(res.predict_z()[b], g['dop_z_pred'][b]) < FIT_TOL
+    dd.fit_eis(g['dop_freq'], g['dop_z'][0], solve_rp=True)
+    assert rel_err(dd.dop_scale_vector, g['dop_dop_scale_vector'][0]) < FIT_TOL
+    assert rel_err(dd.qphb_params['rm'], g['dop_rm0']) < FIT_TOL
+    hy = load_golden('chrono_flex.npz')           # the small hybrid trace
+    drt.fit_hybrid(hy['times'], hy['i_signal'], hy['v_signal'][0], hy['freq'], hy['z'][0], solve_rp=True,
+                   update_scale=True)
+    assert drt.qphb_params['n_outer'] == int(g['hyb_n_outer']) and drt.qphb_params['n_ipm'] == int(g['hyb_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['hyb_cvx_x']) < FIT_TOL
+    assert abs(drt.response_signal_scale / float(g['hyb_response_signal_scale']) - 1) < FIT_TOL
+    assert abs(drt.scaled_response_offset / float(g['hyb_scaled_response_offset']) - 1) < FIT_TOL
+    assert rel_err(drt.fit_parameters['v_baseline'], g['hyb_v_baseline']) < 1e-5
+    assert rel_err(drt.predict_z(hy['freq']), g['hyb_z_pred']) < FIT_TOL
+    assert rel_err(drt.predict_response(), g['hyb_v_pred']) < FIT_TOL
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')
     with pytest.raises(NotImplementedError):
         DRT(tau_basis_type='Cole-Cole')
     drt = DRT()
-    for kw in (dict(update_scale=True), dict(penalty_type='discrete')):
+    for kw in (dict(series_neg=True), dict(penalty_type='discrete')):
         with pytest.raises(NotImplementedError):
             drt.fit_eis(c2['freq'], c2['z'][0], **kw)
 

@@ -223,6 +223,24 @@ def test_pfrt_matches_reference(tables):
     assert np.max(np.abs(llh - g['h_step_llh']) / np.abs(g['h_step_llh'])) < 1e-7
 
 
+def test_solve_rp_and_update_scale_match_reference(tables):
+    """solve_rp (drt1d.py:573-607) and update_scale (:914-936) on EIS spectra whose first Rp estimate is off."""
+    g = load_golden('rescale.npz')
+    prep = orc.EisPrep(g['freq'], tables=tables)
+    area = np.sqrt(np.pi) / prep.eps
+    for tag, kw in (('us', dict(update_scale=True)), ('rp', dict(solve_rp=True)),
+                    ('both', dict(solve_rp=True, update_scale=True))):
+        for b in range(2):
+            r = prep.fit(g['z'][b], basis_area=area, **kw)
+            sf = r['scale_factors']
+            assert r['n_outer'] == int(g[f'{tag}_n_outer'][b]) and int(r['ipm_iters'].sum()) == int(g[f'{tag}_ipm'][b])
+            assert rel_err(r['x'], g[f'{tag}_cvx_x'][b]) < 1e-9
+            assert abs(r['coefficient_scale'] / (sf[0] * sf[1]) / g[f'{tag}_coefficient_scale'][b] - 1) < 1e-9
+            assert rel_err(r['est_weights'], g[f'{tag}_est_weights'][b]) < 1e-9
+            assert rel_err(r['init_weights'], g[f'{tag}_init_weights'][b]) < 1e-9
+            assert rel_err(r['xmx_norms'], g[f'{tag}_xmx_norms'][b]) < 1e-9
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
