@@ -69,9 +69,12 @@ __shared__ unsigned long long s_prof[32];
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int TMAX_, int W_, int MINB_>
+// EXT_ = false compiles the optional paths out (outlier error structure, solve_rp / update_scale, PFRT continuation):
+// the kernel is sensitive to its instruction footprint, and the default fit does not pay for what it does not use.
+template <int TMAX_, int W_, int MINB_, bool EXT_ = false>
 struct Cfg {
     static constexpr int TMAX = TMAX_, W = W_, MINB = MINB_;
+    static constexpr bool EXT = EXT_;
     static constexpr int kWarps = W * W, kThreads = 32 * kWarps;
     static constexpr int NV = 8 * TMAX;               // padded vector length
     static constexpr int A = (TMAX + W - 1) / W;      // slot rows per warp; slot (a, b), b <= a
@@ -109,6 +112,8 @@ struct Cfg {
 
 using CfgS = Cfg<13, 2, 3>;  // n <= 104:  4 warps, 28 register tiles per warp, three CTAs per SM
 using CfgL = Cfg<20, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, one CTA per SM
+using CfgSX = Cfg<13, 2, 3, true>;   // the same with the optional paths compiled in
+using CfgLX = Cfg<20, 4, 1, true>;
 
 __host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>
@@ -296,8 +301,9 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
         {
             const int rq = r0 + 2 * (tid & 3);       // q = -rm^T (w^2 rv): rv straight from global (issued early)
             const double2 w2q = lds2(w2 + rq);
-            const double2 wv = make_double2(rq < N ? w2q.x * (c.rv[rq] * c.rv_scale) : 0.0,
-                                            rq + 1 < N ? w2q.y * (c.rv[rq + 1] * c.rv_scale) : 0.0);
+            const double rsc = C::EXT ? c.rv_scale : 1.0;
+            const double2 wv = make_double2(rq < N ? w2q.x * (c.rv[rq] * rsc) : 0.0,
+                                            rq + 1 < N ? w2q.y * (c.rv[rq + 1] * rsc) : 0.0);
 #pragma unroll
             for (int u = 0; u < QU; ++u) {
                 const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
@@ -363,7 +369,7 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
                             acc += (us[r] * m) * us[cc];
                         }
                         double gram = *e;     // negated Gram entry
-                        if (dopb) {           // DOP columns of rm carry the per-spectrum rescale (drt1d.py:589-596)
+                        if (C::EXT && dopb) {  // DOP columns of rm carry the per-spectrum rescale (drt1d.py:589-596)
                             if (r >= c.dop_a && r < c.dop_b) gram *= c.dop_cs;
                             if (cc >= c.dop_a && cc < c.dop_b) gram *= c.dop_cs;
                         }
@@ -386,7 +392,7 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
         const int col = (tid + C::kThreads * u) >> 2;
         const double s = reduce_q(qacc[u]);
         if ((tid & 3) == 0 && col < n) {
-            const double sc = (col >= c.dop_a && col < c.dop_b) ? s * c.dop_cs : s;
+            const double sc = (C::EXT && col >= c.dop_a && col < c.dop_b) ? s * c.dop_cs : s;
             const double qv = -sc + (l1_scalar ? l1_value : c.l1[col]);
             C::vec(C::QS)[col] = qv;
             if (q_out) q_out[col] = qv;
@@ -1097,7 +1103,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     for (int w = 0; w < CU; ++w) {
         const int col = lane + 32 * w;
         xw[w] = (col < n) ? xs[col] : 0.0;
-        if (col >= c.dop_a && col < c.dop_b) xw[w] *= c.dop_cs;
+        if (C::EXT && col >= c.dop_a && col < c.dop_b) xw[w] *= c.dop_cs;
     }
     for (int rb = warp; rb < N; rb += RU * C::kWarps) {
         double v[RU][CU];
@@ -1123,12 +1129,12 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
             acc = warp_sum(acc);
             if (update_vz) accv = warp_sum(accv);
             if (lane == 0 && rb + u * C::kWarps < N) {
-                const double resid = acc - c.rv[r] * c.rv_scale;
+                const double resid = acc - (C::EXT ? c.rv[r] * c.rv_scale : c.rv[r]);
                 C::rowr2(c.N)[r] = resid * resid;
                 if (update_vz) {
                     // a continuation predicts with the vz_offset column it started from (drt1d.py:1296-1302 copies
                     // the matrix once, with that column in place); the plain fit copies it while it is still zero
-                    if (c.vz0 != nullptr) accv += c.vz0[r] * xs[c.vz];
+                    if (C::EXT && c.vz0 != nullptr) accv += c.vz0[r] * xs[c.vz];
                     const double sep = (r < nc) ? accv : -accv;
                     c.vzcol[r] = sep * c.vz_strength[r];
                 }
@@ -1138,7 +1144,8 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     __syncthreads();
     PROF_ADD(11);
     const bool uniform_chrono = nc > 0 && c.vmm_chrono == nullptr;
-    const bool outl = c.outlier_p >= 0.0;
+    const bool outl = C::EXT && c.outlier_p >= 0.0;
+    base = C::EXT && base;
     const double* uin = C::rowr2(c.N);
     if (outl) {
         // qphb.solve_outlier_t (qphb.py:1497-1519): s_bar = vmm r^2, t = 1 - P(outlier | r); the averaging matrix
@@ -1266,7 +1273,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     c.vmm_chrono = p.vmm_chrono ? p.vmm_chrono + (size_t)b * p.vmm_chrono_stride : nullptr;
     c.pen = p.pen + (size_t)b * p.pen_stride;
     c.vzcol = p.vz_col ? p.vz_col + (size_t)b * N : nullptr;
-    const bool outl = hy.has_outlier_p != 0;
+    const bool outl = C::EXT && hy.has_outlier_p != 0;
     c.outlier_p = outl ? hy.outlier_p : -1.0;
     c.t_out = outl ? p.outlier_t + (size_t)b * N : nullptr;
     c.vz0 = nullptr;
@@ -1293,8 +1300,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     for (int k = 0; k < 3; ++k) { rho[k] = hy.rho_0[k]; dop_rho[k] = hy.dop_rho_0[k]; }
     // PFRT (DRT._pfrt_fit_core, drt1d.py:2558-2698): step 0 is a plain fit at s_0 * f_0, l2_lambda_0 / f_0; every
     // further factor continues from the previous state (_continue_from_init, :1270-1365)
-    const int n_steps = p.n_pfrt > 0 ? p.n_pfrt : 1;
-    const double fac0 = p.n_pfrt > 0 ? p.pfrt_factors[0] : 1.0;
+    const bool pfrt = C::EXT && p.n_pfrt > 0;
+    const int n_steps = pfrt ? p.n_pfrt : 1;
+    const double fac0 = pfrt ? p.pfrt_factors[0] : 1.0;
     const double lam_init = hy.l2_lambda_0 / fac0;     // qphb_params['hypers']['l2_lambda_0'] of the reference
     if (tid < C::NV) {
 #pragma unroll
@@ -1332,13 +1340,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     bool conv = false, fatal = false, final_pq = false;
 #pragma unroll 1
     for (int step = 0; step < n_steps && !fatal; ++step) {
-    const bool cont = step > 0;
-    const double fac = p.n_pfrt > 0 ? p.pfrt_factors[step] : 1.0;
+    const bool cont = C::EXT && step > 0;
+    const double fac = pfrt ? p.pfrt_factors[step] : 1.0;
     const double lam_step = hy.l2_lambda_0 / fac;
 #pragma unroll
     for (int k = 0; k < 3; ++k) hd.s_0[k] = hy.s_0[k] * fac;
     const int max_it = cont ? p.pfrt_max_iter : hy.max_iter;
-    const bool solve_rp = hy.solve_rp != 0;
+    const bool solve_rp = C::EXT && hy.solve_rp != 0;
     it = cont ? 0 : (solve_rp ? -3 : (outl ? -2 : -1));   // -3: estimate_x_rp (qphb.py:1684-1717); -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
                                         // the initialisation runs twice (-2, -1), the second time weighted by the
                                         // first estimate
@@ -1351,7 +1359,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
 #pragma unroll 1
     while (true) {
         const bool init = it < 0;
-        if (hy.update_scale && !init && !cont && !final_pq && it > 1) {
+        if (C::EXT && hy.update_scale && !init && !cont && !final_pq && it > 1) {
             // keep the data at the requested rp_scale as the Rp estimate improves (drt1d.py:914-936)
             const bool drt = tid >= c.ns && tid < n;
             double t1[1] = {drt ? fabs(xi) : 0.0};
@@ -1386,7 +1394,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             }
         }
         {
-            const double lam_iw = (it == -3) ? 1e-4 : hy.iw_l2_lambda_0;   // estimate_x_rp: l2_lambda_0 = 1e-4 (drt1d.py:5425)
+            const double lam_iw = (C::EXT && it == -3) ? 1e-4 : hy.iw_l2_lambda_0;   // estimate_x_rp: l2_lambda_0 = 1e-4 (drt1d.py:5425)
             const double lam0 = init ? lam_iw : lam_step;
             const double dlam0 = init ? hy.dop_l2_lambda_0 * (lam_iw / lam_step) : hy.dop_l2_lambda_0;
 #pragma unroll
@@ -1397,7 +1405,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
         __syncthreads();
         PROF_ADD(0);
-        gram_phase<C>(c, f, init, (it == -3) ? 1e-3 : hy.iw_l1_lambda_0, (final_pq && p.p_matrix) ? p.p_matrix + (size_t)b * n * n : nullptr,
+        gram_phase<C>(c, f, init, (C::EXT && it == -3) ? 1e-3 : hy.iw_l1_lambda_0, (final_pq && p.p_matrix) ? p.p_matrix + (size_t)b * n * n : nullptr,
                         (final_pq && p.q_vector) ? p.q_vector + (size_t)b * n : nullptr);
         if (final_pq) {
             if (p.dist_var && !postfit_variance<C>(c, p.eval_mat, p.n_eval, p.dist_var + (size_t)b * p.n_eval))
@@ -1413,7 +1421,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (qo.fatal) { fatal = true; xi = qo.xi; break; }
         if (tid < n) C::vec(C::XS)[tid] = qo.xi;
         __syncthreads();
-        if (it == -3) {
+        if (C::EXT && it == -3) {
             // DRT._solve_data_scale (drt1d.py:5421-5437, applied at :573-607): Rp from a lightly regularised
             // elastic-net solution; the data are rescaled to rp_scale, the DOP columns to the DRT magnitude
             const bool drt = tid >= c.ns && tid < n;
@@ -1483,7 +1491,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         }
     }
     if (!cont) n_outer0 = it < 0 ? 0 : it;
-    if (p.n_pfrt > 0 && !fatal) {
+    if (pfrt && !fatal) {
         // step_update of the reference (drt1d.py:2617-2650): weights re-estimated from x alone (no blend with
         // est_weights, no outlier structure), the two data terms of the marginal llh (qphb.py:1359-1373), and
         // calculate_pq under those weights with the hypers of the *first* step
@@ -1539,13 +1547,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             if (p.dop_rho) p.dop_rho[(size_t)b * 3 + k] = dop_rho[k];
             if (p.dop_xmx_norms) p.dop_xmx_norms[(size_t)b * 3 + k] = dop_xmx[k];
         }
-        if (p.scale_factors) {
+        if (C::EXT && p.scale_factors) {
             if (!hy.solve_rp) p.scale_factors[3 * (size_t)b] = 1.0;
             p.scale_factors[3 * (size_t)b + 1] = us_factor;
             p.scale_factors[3 * (size_t)b + 2] = c.dop_cs;
         }
         if (p.fun) p.fun[b] = fun;
-        if (p.n_outer) p.n_outer[b] = p.n_pfrt > 0 ? n_outer0 : (it < 0 ? 0 : it);
+        if (p.n_outer) p.n_outer[b] = pfrt ? n_outer0 : (it < 0 ? 0 : it);
         if (p.n_ipm) p.n_ipm[b] = n_ipm;
         if (p.status) p.status[b] = status;
     }
@@ -1671,8 +1679,9 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
-    if (small_cfg(p.n_cols)) return launch_qphb<CfgS>(h, p, (size_t)smem, st);
-    return launch_qphb<CfgL>(h, p, (size_t)smem, st);
+    const bool ext = p.hyp.has_outlier_p || p.hyp.solve_rp || p.hyp.update_scale || p.n_pfrt > 0;
+    if (small_cfg(p.n_cols)) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
+    return ext ? launch_qphb<CfgLX>(h, p, (size_t)smem, st) : launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }
 
 #ifdef HDRT_PROFILE
