@@ -508,6 +508,38 @@ __global__ void dop_z_kernel(const double* __restrict__ freq, const double* __re
     }
 }
 
+// ---- DOP voltage-response columns (phasance.py:8-9,40-57,83-99,121-144): real arithmetic ---------------
+// column m at time t after a step: F(b) - F(a), F(nu) = 1/2 sqrt(pi) t^-nu_m / Gamma(1 - nu_m) / eps
+//                                   * t^(ln t / 4 eps^2) * erf(eps (nu - nu_m) + ln t / 2 eps); summed over steps.
+__global__ void dop_v_kernel(const double* __restrict__ times, const double* __restrict__ nu,
+                             const double* __restrict__ step_times, const double* __restrict__ step_sizes, int n_grids,
+                             int nt, int n_nu, int n_steps, double nu_eps, double* __restrict__ rm) {
+    const long long total = (long long)n_grids * nt * n_nu;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e % n_nu);
+        const long long gt = e / n_nu;
+        const int g = (int)(gt / nt);
+        const double t = times[gt];
+        const double num = nu[m];
+        const double sg = (num > 0.0) ? 1.0 : ((num < 0.0) ? -1.0 : 0.0);
+        const double la = fmin(0.0, sg), lb = fmax(0.0, sg);
+        const double inv_gamma = 1.0 / tgamma(1.0 - num);
+        double acc = 0.0;
+        for (int k = 0; k < n_steps; ++k) {
+            const double st = step_times[(size_t)g * n_steps + k];
+            if (t > st) {
+                const double lt = log(t - st);
+                double pre = 0.5 * sqrt(3.141592653589793) * (exp(-num * lt) * inv_gamma) / nu_eps;
+                pre *= exp(lt * (lt / (4.0 * nu_eps * nu_eps)));
+                const double sh = lt / (2.0 * nu_eps);
+                const double f = pre * erf(nu_eps * (lb - num) + sh) - pre * erf(nu_eps * (la - num) + sh);
+                acc += step_sizes[(size_t)g * n_steps + k] * f;
+            }
+        }
+        rm[e] = acc;
+    }
+}
+
 }  // namespace hdrt
 
 using namespace hdrt;
@@ -648,6 +680,21 @@ extern "C" int hdrt_build_chrono_vmm(const double* times, const double* step_tim
     HDRT_CUDA_CHECK(cudaFuncSetAttribute(chrono_vmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_grids, (nt + kVRows - 1) / kVRows);
     chrono_vmm_kernel<<<grid, kMThreads, smem, (cudaStream_t)stream>>>(times, step_times, nt, n_steps, vmm_eps, uniform, vmm);
+    HDRT_CUDA_CHECK(cudaGetLastError());
+    return HDRT_OK;
+}
+
+extern "C" int hdrt_build_dop_v(const double* times, const double* nu, const double* step_times, const double* step_sizes,
+                                int n_grids, int nt, int n_nu, int n_steps, double nu_eps, double* rm, void* stream) {
+    if (!times || !nu || !step_times || !step_sizes || !rm || n_grids < 0 || nt <= 0 || n_nu <= 0 || n_steps <= 0 ||
+        !(nu_eps > 0.0)) {
+        set_error("hdrt_build_dop_v: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    if (n_grids == 0) return HDRT_OK;
+    const long long total = (long long)n_grids * nt * n_nu;
+    dop_v_kernel<<<grid_for(total, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(times, nu, step_times, step_sizes,
+                                                                                     n_grids, nt, n_nu, n_steps, nu_eps, rm);
     HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }

@@ -91,6 +91,7 @@ def load_library():
     lib.hdrt_build_eis_vmm.argtypes = [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]
     lib.hdrt_build_chrono_vmm.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P]
     lib.hdrt_build_dop_z.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
+    lib.hdrt_build_dop_v.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
     lib.hdrt_default_hypers.argtypes = [C.POINTER(Hypers)]
     lib.hdrt_default_hypers.restype = None
     lib.hdrt_qphb_smem_bytes.argtypes = [C.c_int, C.c_int]
@@ -103,7 +104,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     'hdrt_version', 'hdrt_last_error', 'hdrt_create', 'hdrt_destroy', 'hdrt_sm_count', 'hdrt_build_lookup',
-    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z',
+    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z', 'hdrt_build_dop_v',
     'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64',
 ]
 
@@ -266,6 +267,19 @@ class Engine:
                                               self._stream()))
         self.launches += 1
         return torch.view_as_complex(zm)
+
+    def build_dop_v(self, times, nu, step_times, step_sizes, nu_eps):
+        """phasance.construct_phasor_v_matrix (gaussian). times [G,nt], steps [G,ns], nu [n_nu] -> [G,nt,n_nu]."""
+        times = self.dev(times).reshape(-1, np.shape(times)[-1])
+        st = self.dev(step_times).reshape(-1, np.shape(step_times)[-1])
+        sa = self.dev(step_sizes).reshape(-1, np.shape(step_sizes)[-1])
+        nu = self.dev(nu).reshape(-1)
+        g, nt = times.shape
+        rm = self.empty(g, nt, nu.numel())
+        self._check(self.lib.hdrt_build_dop_v(_ptr(times), _ptr(nu), _ptr(st), _ptr(sa), g, nt, nu.numel(),
+                                              st.shape[1], float(nu_eps), _ptr(rm), self._stream()))
+        self.launches += 1
+        return rm
 
     # -- L2 --------------------------------------------------------------------------------------
     def smem_bytes(self, n_rows, n_cols):

@@ -527,8 +527,6 @@ class DRT:
 
         # ---- chrono block, drt1d.py:5557-5623 + 5792-5819
         if times is not None:
-            if self.fit_dop:
-                _not_supported('fit_dop with chrono data (time-domain phasance matrix)')
             in_scale = float(np.max(np.abs(step_sizes)))        # drtbase.py:463, applied at drt1d.py:5543-5549
             plan['input_signal_scale'] = in_scale if kw['scale_data'] else 1.0
             iscale = plan['input_signal_scale']
@@ -557,6 +555,11 @@ class DRT:
                 rm[:nc, sp['R_inf']['index']] = dev(inf_rv / iscale)
             if 'C_inv' in sp:
                 rm[:nc, sp['C_inv']['index']] = dev(cap_rv / iscale * kw['capacitance_scale'])
+            if self.fit_dop:                                    # drt1d.py:5612-5619, :5548-5549, :5816
+                rm_dop = eng.build_dop_v(times[None], self.basis_nu, np.asarray(step_times)[None],
+                                         np.asarray(step_sizes)[None], self.nu_epsilon)[0]
+                rm[:nc, dop_a:dop_b] = rm_dop / iscale * dev(self.dop_scale_vector)[None, :]
+                plan['rm_dop_chrono'] = rm_dop
             # inductance response is identically zero for ideal steps (mat1d.py:378-396)
             plan['rm_drt_chrono'] = rm_drt
             plan['inf_rv'], plan['cap_rv'] = inf_rv, cap_rv
@@ -1181,6 +1184,8 @@ class DRT:
         times = pl['times']
         rm_drt = pl['rm_drt_chrono'].cpu().numpy()
         resp = rm_drt @ fp['x'] + pl['inf_rv'] * fp.get('R_inf', 0) + fp.get('C_inv', 0) * pl['cap_rv']
+        if fp.get('x_dop') is not None and 'rm_dop_chrono' in pl:     # drt1d.py:3431-3432
+            resp = resp + pl['rm_dop_chrono'].cpu().numpy() @ fp['x_dop']
         if include_vz_offset:
             cs, _ = self._vz_strength(times, None)
             resp = resp * (1 + fp.get('vz_offset', 0) * cs)

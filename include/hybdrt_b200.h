@@ -90,6 +90,12 @@ int hdrt_build_chrono_vmm(const double* times, const double* step_times, int n_g
 int hdrt_build_dop_z(const double* freq, const double* nu, int n_grids, int nf, int n_nu, double nu_eps, double* zm,
                      void* stream);
 
+/* phasance.construct_phasor_v_matrix, gaussian basis, galvanostatic ideal steps, normalize=False
+ * (phasance.py:8-9,40-57,83-99,121-144).  times [n_grids][nt], nu [n_nu], step_times/step_sizes [n_grids][n_steps]
+ * -> rm [n_grids][nt][n_nu] (summed over steps). */
+int hdrt_build_dop_v(const double* times, const double* nu, const double* step_times, const double* step_sizes,
+                     int n_grids, int nt, int n_nu, int n_steps, double nu_eps, double* rm, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * L2: batched QPHB fit (reference: the loop of DRT._qphb_fit_core, drt1d.py:556-1008, which calls
  * qphb.initialize_weights qphb.py:1609, qphb.iterate_qphb :606, qphb.calculate_pq :1154; the QP is

@@ -188,6 +188,26 @@ def dop_z_matrix(freq, nu, nu_eps):
     return prim(b) - prim(a)
 
 
+def dop_v_matrix(times, nu, nu_eps, step_times, step_sizes):
+    """phasance.construct_phasor_v_matrix, gaussian basis, ideal galvanostatic steps, normalize=False
+    (phasance.py:8-9,40-57,83-99,121-144)."""
+    from scipy.special import erf, gamma
+    times, nu = np.asarray(times, dtype=float), np.asarray(nu, dtype=float)
+    a, b = np.minimum(0, np.sign(nu)), np.maximum(0, np.sign(nu))
+    out = np.zeros((times.size, nu.size))
+    for st, sa in zip(step_times, step_sizes):
+        sel = times > st
+        t = (times[sel] - st)[:, None]
+        with np.errstate(divide='ignore'):
+            pre = 0.5 * np.sqrt(np.pi) * (t ** -nu[None, :] / gamma(-nu[None, :] + 1)) / nu_eps
+        pre = pre * t ** (np.log(t) / (4 * nu_eps ** 2))
+
+        def prim(lim):
+            return pre * erf(nu_eps * (lim[None, :] - nu[None, :]) + np.log(t) / (2 * nu_eps))
+        out[sel] += sa * (prim(b) - prim(a))
+    return out
+
+
 def dop_scale_vector(nu, tau, quantiles=(0.25, 0.75)):
     """phasance.phasor_scale_vector, phasance.py:165-184."""
     lt = np.log(tau)

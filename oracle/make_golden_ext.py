@@ -11,6 +11,7 @@ oracle/refshim.py (authoring container only):
                       fit_chrono / fit_hybrid results with chrono_error_structure=None (+ outlier_p: the
                       tutorial's flags)
 * rescale.npz         solve_rp (drt1d.py:573-607, qphb.py:1684-1717) and update_scale (drt1d.py:914-936) fits
+* dop_chrono.npz      phasance.construct_phasor_v_matrix (phasance.py:121-144) and DRT + DOP fits of time-domain data
 * pfrt.npz            pfrt_fit_eis / pfrt_fit_hybrid (drt1d.py:2558-2716): per-factor coefficients, marginal
                       log-likelihood and P matrices of the continuation path
 """
@@ -209,7 +210,33 @@ def gen_rescale():
     np.savez_compressed(os.path.join(OUT, 'rescale.npz'), **d)
 
 
-GENERATORS = dict(outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex, pfrt=gen_pfrt, rescale=gen_rescale)
+def gen_dop_chrono():
+    """DRT + DOP with time-domain data: phasance.construct_phasor_v_matrix and fit_chrono / fit_hybrid."""
+    from hybdrt.matrices import phasance
+    ts, is_, vs, fh, zh = small_hybrid()
+    drt = DRT(fit_dop=True)
+    refshim.QP_LOG.clear()
+    drt.fit_hybrid(ts, is_, vs[0], fh, zh[0])
+    o = fit_outputs(drt, fh)
+    d = dict(times=ts, i_signal=is_, v_signal=vs, freq=fh, z=zh, basis_nu=drt.basis_nu, nu_epsilon=drt.nu_epsilon,
+             step_times=drt.step_times, step_sizes=drt.step_sizes,
+             rm_dop=phasance.construct_phasor_v_matrix(ts, drt.basis_nu, 'gaussian', drt.nu_epsilon, 'ideal',
+                                                       drt.step_times, drt.step_sizes)[0],
+             hyb_rm=drt.qphb_params['rm'], hyb_ipm=int(np.sum(refshim.QP_LOG)), hyb_v_pred=drt.predict_response(ts))
+    for k in ('cvx_x', 'x', 'x_dop', 'R_inf', 'vz_offset', 'n_outer', 'z_pred', 'weights', 'dop_rho_vector'):
+        d[f'hyb_{k}'] = np.asarray(o[k])
+    print('dop hybrid: outer', o['n_outer'], 'ipm', d['hyb_ipm'])
+    refshim.QP_LOG.clear()
+    drt.fit_chrono(ts, is_, vs[1])
+    o = fit_outputs(drt)
+    for k in ('cvx_x', 'x', 'x_dop', 'R_inf', 'n_outer', 'weights'):
+        d[f'chr_{k}'] = np.asarray(o[k])
+    d.update(chr_ipm=int(np.sum(refshim.QP_LOG)), chr_v_pred=drt.predict_response(ts))
+    print('dop chrono: outer', o['n_outer'], 'ipm', d['chr_ipm'])
+    np.savez_compressed(os.path.join(OUT, 'dop_chrono.npz'), **d)
+
+
+GENERATORS = dict(dop_chrono=gen_dop_chrono, outlier_eis=gen_outlier_eis, chrono_flex=gen_chrono_flex, pfrt=gen_pfrt, rescale=gen_rescale)
 
 
 def main():

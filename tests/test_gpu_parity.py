@@ -477,6 +477,31 @@ def test_solve_rp_and_update_scale():
     assert rel_err(drt.predict_response(), g['hyb_v_pred']) < FIT_TOL
 
 
+def test_dop_with_time_domain_data(eng, orc):
+    """phasance.construct_phasor_v_matrix (phasance.py:121-144) and DRT + DOP fits of chrono / hybrid data."""
+    from hybdrt_b200.models import DRT
+    d = load_golden('dop_chrono.npz')
+    nu_eps = float(d['nu_epsilon'])
+    rm = _np(eng.build_dop_v(d['times'][None], d['basis_nu'], d['step_times'][None], d['step_sizes'][None], nu_eps)[0])
+    assert rel_err(rm, d['rm_dop']) < MAT_TOL
+    t2 = np.linspace(-0.01, 0.5, 37)
+    st2, sa2 = np.array([0.0, 0.2]), np.array([0.01, -0.02])
+    rm2 = _np(eng.build_dop_v(t2[None], d['basis_nu'], st2[None], sa2[None], nu_eps)[0])
+    assert rel_err(rm2, orc.dop_v_matrix(t2, d['basis_nu'], nu_eps, st2, sa2)) < MAT_TOL
+    drt = DRT(fit_dop=True)
+    drt.fit_hybrid(d['times'], d['i_signal'], d['v_signal'][0], d['freq'], d['z'][0])
+    assert rel_err(drt.qphb_params['rm'], d['hyb_rm']) < 1e-9
+    assert drt.qphb_params['n_outer'] == int(d['hyb_n_outer']) and drt.qphb_params['n_ipm'] == int(d['hyb_ipm'])
+    assert rel_err(drt.cvx_result['x'], d['hyb_cvx_x']) < FIT_TOL
+    assert rel_err(drt.fit_parameters['x_dop'], d['hyb_x_dop']) < FIT_TOL
+    assert rel_err(drt.predict_z(d['freq']), d['hyb_z_pred']) < FIT_TOL
+    assert rel_err(drt.predict_response(), d['hyb_v_pred']) < FIT_TOL
+    drt.fit_chrono(d['times'], d['i_signal'], d['v_signal'][1])
+    assert drt.qphb_params['n_outer'] == int(d['chr_n_outer']) and drt.qphb_params['n_ipm'] == int(d['chr_ipm'])
+    assert rel_err(drt.cvx_result['x'], d['chr_cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_response(), d['chr_v_pred']) < FIT_TOL
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')

@@ -241,6 +241,12 @@ def test_solve_rp_and_update_scale_match_reference(tables):
             assert rel_err(r['xmx_norms'], g[f'{tag}_xmx_norms'][b]) < 1e-9
 
 
+def test_dop_voltage_matrix_matches_reference():
+    d = load_golden('dop_chrono.npz')
+    m = orc.dop_v_matrix(d['times'], d['basis_nu'], float(d['nu_epsilon']), d['step_times'], d['step_sizes'])
+    assert rel_err(m, d['rm_dop']) < 1e-13
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
