@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libhybdrt_b200.so')
-SOURCES = ['capi.cu', 'matrix_kernels.cu', 'qphb_kernel.cu']
+SOURCES = ['capi.cu', 'matrix_kernels.cu', 'chrono_kernels.cu', 'qphb_kernel.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
 

@@ -92,6 +92,7 @@ def load_library():
     lib.hdrt_build_chrono_vmm.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P]
     lib.hdrt_build_dop_z.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
     lib.hdrt_build_dop_v.argtypes = [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, _P]
+    lib.hdrt_filter_gather.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]
     lib.hdrt_default_hypers.argtypes = [C.POINTER(Hypers)]
     lib.hdrt_default_hypers.restype = None
     lib.hdrt_qphb_smem_bytes.argtypes = [C.c_int, C.c_int]
@@ -104,7 +105,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     'hdrt_version', 'hdrt_last_error', 'hdrt_create', 'hdrt_destroy', 'hdrt_sm_count', 'hdrt_build_lookup',
-    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z', 'hdrt_build_dop_v',
+    'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z', 'hdrt_build_dop_v', 'hdrt_filter_gather',
     'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64',
 ]
 
@@ -171,6 +172,25 @@ class Engine:
         if key not in self._pinned:
             self._pinned[key] = torch.empty(*shape, dtype=dtype, pin_memory=True)
         return self._pinned[key]
+
+    # -- L0 --------------------------------------------------------------------------------------
+    def filter_gather(self, y, plan):
+        """Antialiasing filter + decimation of a batch of traces y [S, nt] (device or host) with the tap layout
+        ``plan`` of hybdrt_b200.preprocessing.filter_plan (cached on the device inside the plan).  -> [S, m]."""
+        y = self.dev(y)
+        if y.dim() == 1:
+            y = y[None]
+        if 'dev' not in plan or plan['dev'][0] != self.device:
+            plan['dev'] = (self.device, {k: self.dev(plan[k], dtype=torch.int32) for k in ('idx', 'seg_lo', 'seg_len', 'lw')},
+                           self.dev(plan['woff'], dtype=torch.int64), self.dev(plan['taps']))
+        _, ints, woff, taps = plan['dev']
+        m = len(plan['idx'])
+        out = self.empty(y.shape[0], m)
+        self._check(self.lib.hdrt_filter_gather(_ptr(y), y.shape[0], y.shape[1], _ptr(ints['idx']), _ptr(ints['seg_lo']),
+                                                _ptr(ints['seg_len']), _ptr(woff), _ptr(ints['lw']), _ptr(taps), m,
+                                                _ptr(out), self._stream()))
+        self.launches += 1
+        return out
 
     # -- L1 --------------------------------------------------------------------------------------
     def build_lookup(self, eps, grid_points=2000, quad_points=1000):

@@ -740,7 +740,7 @@ class DRT:
                         eff_hp=True, weight_factor=1, xtol=1e-2, max_iter=50, peak_locations=None, **kw):
         # options outside the hot path (same keyword names as drt1d.py:102-137)
         for flag, name in ((series_neg, 'series_neg'),
-                           (downsample, 'downsample'), (subtract_background, 'subtract_background'),
+                           (subtract_background, 'subtract_background'),
                            (remove_extremes, 'remove_extremes'),
                            (init_weights_separately, 'init_weights_separately'),
                            (discard_first_n is not None, 'discard_first_n'), (peak_locations is not None,
@@ -796,6 +796,28 @@ class DRT:
             if v_batch.ndim != 2 or v_batch.shape[1] != len(times):
                 raise ValueError('v_signal must have shape [batch, len(times)]')
         batch = len(z_batch) if z_batch is not None else len(v_batch)
+
+        self.sample_index = None if times is None else np.arange(len(times))
+        if downsample and times is not None:
+            # DRTBase.process_chrono_signals (drtbase.py:296-339): step data come from the raw signal, then the
+            # traces are filtered and decimated (on the GPU, all of them at once) before anything else happens
+            from . import preprocessing as _pp
+            times = np.asarray(times, dtype=float)
+            i_signal = np.asarray(i_signal, dtype=float)
+            if step_times is None:
+                step_times, step_sizes = step_info(times, i_signal, offset_steps, step_offset_size)
+            elif step_sizes is None:
+                step_sizes = step_sizes_from_signal(times, i_signal, np.asarray(step_times, dtype=float))
+            step_times = np.asarray(step_times, dtype=float)
+            nonconsec = step_times
+            if len(step_times) > 1:
+                keep = np.diff(step_times) > 1.1 * np.min(np.diff(times))
+                nonconsec = np.insert(step_times[1:][keep], 0, step_times[0])
+            dkw = dict(downsample_kw) if downsample_kw is not None else {'prestep_samples': 10, 'target_times': None}
+            times, i_signal, v_batch, self.sample_index = _pp.downsample_data(
+                times, i_signal, v_batch, stepwise_sample_times=True, step_times=nonconsec, op_mode=self.chrono_mode,
+                engine=self.engine, **dkw)
+            opts['step_times'], opts['step_sizes'] = step_times, np.asarray(step_sizes, dtype=float)
 
         plan = self._build_plan(times, i_signal, frequencies, opts)
         plan['opts'] = opts

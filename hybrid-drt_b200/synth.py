@@ -106,3 +106,21 @@ def make_hybrid_batch(batch, freq=None, times=None, seed=1, i0=1e-2, n_rc=4):
     z = r_inf[:, None] + np.sum(r[:, :, None] / (1 + jw * tau[:, :, None]), axis=1)
     z = z + rng.normal(0, 1e-3, z.shape) + 1j * rng.normal(0, 1e-3, z.shape)
     return times, i_signal, v, freq, z
+
+
+def make_raw_chrono_batch(batch=3, seed=5, n_pre=300, n_post=24000, dt=1e-4):
+    """Densely sampled two-step galvanostatic traces (RC ladder responses + noise), as an instrument records them
+    before downsampling.  Returns (times[Nt], i_signal[Nt], v[B,Nt])."""
+    rng = np.random.default_rng(seed)
+    times = (np.arange(-n_pre, n_post) + 0.0) * dt
+    i_signal = 1e-2 * (times >= 0) - 0.6e-2 * (times >= 1.2)
+    r_inf = rng.uniform(0.5, 2.0, batch)
+    r = rng.uniform(0.2, 1.0, (batch, 3))
+    tau = 10 ** rng.uniform([-4, -2.5, -1], [-3, -1.5, 0], (batch, 3))
+    v = np.zeros((batch, times.size))
+    for st, sa in ((0.0, 1e-2), (1.2, -0.6e-2)):
+        tp = np.maximum(times - st, 0.0)[None, None, :]
+        v += sa * (r_inf[:, None] + np.sum(r[:, :, None] * (1 - np.exp(-tp / tau[:, :, None])), axis=1)) * (times >= st)
+    v += rng.normal(0, 5e-6, v.shape)
+    i_noisy = i_signal + rng.normal(0, 2e-7, times.shape)
+    return times, i_noisy, v

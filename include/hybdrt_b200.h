@@ -97,6 +97,18 @@ int hdrt_build_dop_v(const double* times, const double* nu, const double* step_t
                      int n_grids, int nt, int n_nu, int n_steps, double nu_eps, double* rm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * L0: chrono conditioning (reference: preprocessing.downsample_data preprocessing.py:335-468 with
+ * filter_chrono_signal :507-574 and filters.nonuniform_gaussian_filter1d filters/_filters.py:261-341)
+ * ------------------------------------------------------------------------------------------- */
+/* Antialiasing filter evaluated at the kept samples only, for a batch of traces on one time grid:
+ *   out[s][j] = sum_{k=-lw[j]..lw[j]} taps[woff[j] + lw[j] + k] * y[s][mirror(idx[j] + k)]
+ * mirrored (scipy.ndimage 'reflect') inside the step segment [seg_lo[j], seg_lo[j] + seg_len[j]).
+ * y [n_sig][nt]; idx, seg_lo, seg_len, lw [m] int32; woff [m] int64; taps: the blended, normalised Gaussian
+ * weights of every kept sample (laid out by the host once per grid); out [n_sig][m].  All pointers are device. */
+int hdrt_filter_gather(const double* y, int n_sig, int nt, const int* idx, const int* seg_lo, const int* seg_len,
+                       const long long* woff, const int* lw, const double* taps, int m, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * L2: batched QPHB fit (reference: the loop of DRT._qphb_fit_core, drt1d.py:556-1008, which calls
  * qphb.initialize_weights qphb.py:1609, qphb.iterate_qphb :606, qphb.calculate_pq :1154; the QP is
  * cvxopt.solvers.qp reached at qphb.py:519)

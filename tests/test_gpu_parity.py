@@ -502,6 +502,45 @@ def test_dop_with_time_domain_data(eng, orc):
     assert rel_err(drt.predict_response(), d['chr_v_pred']) < FIT_TOL
 
 
+def test_chrono_downsampling(eng):
+    """preprocessing.downsample_data (preprocessing.py:335-468) for a batch of raw traces: decimation index on the
+    host, antialiasing filter on the GPU, against the unmodified reference; then a fit with downsample=True."""
+    from hybdrt_b200 import synth, preprocessing as pp
+    from hybdrt_b200.models import DRT
+    from oracle import chrono_oracle as co
+    g = load_golden('downsample.npz')
+    times, i_sig, v = synth.make_raw_chrono_batch(3, seed=5)
+    cases = dict(tut=dict(decimation_interval=8, decimation_factor=2, prestep_samples=25, method='decimate'),
+                 size=dict(target_size=300, decimation_factor=2, prestep_samples=10, decimation_max_period=0.05,
+                           method='decimate'),
+                 raw=dict(decimation_interval=20, decimation_factor=3, prestep_samples=5, antialiased=False,
+                          method='decimate'))
+    for tag, kw in cases.items():
+        st, si, sv, idx = pp.downsample_data(times, i_sig, v, engine=eng, **kw)
+        assert np.array_equal(idx, g[f'{tag}_index']) and np.array_equal(st, g[f'{tag}_times'])
+        assert rel_err(si, g[f'{tag}_i']) < 1e-12 and rel_err(sv, g[f'{tag}_v']) < 1e-12
+    st, si, sv1, idx = pp.downsample_data(times, i_sig, v[1], engine=eng, **cases['tut'])      # one trace
+    assert sv1.shape == (len(idx),) and rel_err(sv1, g['tut_v'][1]) < 1e-12
+    # size-independent properties on a larger batch: constants and (inside a segment) straight lines pass through
+    plan = pp.filter_plan(times, pp.identify_steps(i_sig, allow_consecutive=False), g['tut_index'])
+    big = np.concatenate([np.full((1, len(times)), 3.25), np.repeat(times[None] * 2.0 - 1.0, 2, axis=0),
+                          np.random.default_rng(3).normal(size=(509, len(times)))])
+    out = _np(eng.filter_gather(big, plan))
+    assert np.allclose(out[0], 3.25, rtol=0, atol=1e-13)
+    inner = (plan['idx'] - plan['seg_lo'] >= plan['lw']) & (plan['idx'] - plan['seg_lo'] + plan['lw'] < plan['seg_len'])
+    assert np.allclose(out[1][inner], (times * 2.0 - 1.0)[plan['idx']][inner], rtol=0, atol=1e-12)
+    for b in (3, 400, 511):
+        ref = co.filter_chrono_signal(times, big[b], co.identify_steps(i_sig, False), decimate_index=g['tut_index'])
+        assert rel_err(out[b], ref[g['tut_index']]) < 1e-12
+    drt = DRT()
+    drt.warn = False
+    drt.fit_chrono(times, i_sig, v[0], downsample=True, downsample_kw=dict(cases['tut'], step_model='ideal'))
+    assert np.array_equal(drt.t_fit, g['fit_t']) and np.array_equal(drt.sample_index, g['tut_index'])
+    assert drt.qphb_params['n_outer'] == int(g['fit_n_outer']) and drt.qphb_params['n_ipm'] == int(g['fit_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['fit_cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_response(), g['fit_v_pred']) < FIT_TOL
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')

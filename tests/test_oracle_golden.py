@@ -247,6 +247,45 @@ def test_dop_voltage_matrix_matches_reference():
     assert rel_err(m, d['rm_dop']) < 1e-13
 
 
+DS_CASES = dict(tut=dict(decimation_interval=8, decimation_factor=2, prestep_samples=25),
+                size=dict(target_size=300, decimation_factor=2, prestep_samples=10, decimation_max_period=0.05),
+                raw=dict(decimation_interval=20, decimation_factor=3, prestep_samples=5, antialiased=False))
+
+
+def test_downsample_matches_reference():
+    """preprocessing.downsample_data (decimation index + antialiasing filter): the oracle against the reference,
+    and the host-side tap layout of the product (evaluated here with numpy) against the oracle."""
+    from oracle import chrono_oracle as co
+    from hybdrt_b200 import synth, preprocessing as pp
+    g = load_golden('downsample.npz')
+    times, i_sig, v = synth.make_raw_chrono_batch(3, seed=5)
+    for tag, kw in DS_CASES.items():
+        st, si, sv, idx = co.downsample_data(times, i_sig, v[1], **kw)
+        assert np.array_equal(idx, g[f'{tag}_index']) and np.array_equal(st, g[f'{tag}_times'])
+        assert rel_err(si, g[f'{tag}_i']) < 1e-13 and rel_err(sv, g[f'{tag}_v'][1]) < 1e-13
+    # scipy's own filter, where the explicit restatement stands in for it
+    from scipy import ndimage
+    y = np.random.default_rng(0).normal(size=57)
+    for sigma in (0.3, 1.7, 9.0, 40.0):
+        assert rel_err(co.gaussian_filter1d_reflect(y, sigma), ndimage.gaussian_filter1d(y, sigma, mode='reflect')) < 1e-13
+    # product host logic: index selection and the tap layout (no GPU: the taps are applied with numpy here)
+    step_times = times[co.identify_steps(i_sig, True)]
+    t_sample = np.min(np.diff(times))
+    idx = pp.get_decimation_index(times, step_times, t_sample, 25, 8, 2, None)
+    assert np.array_equal(idx, g['tut_index'])
+    iv = pp.select_decimation_interval(times, step_times, t_sample, 10, 2, 0.05, 300)
+    assert np.array_equal(pp.get_decimation_index(times, step_times, t_sample, 10, iv, 2, 0.05), g['size_index'])
+    plan = pp.filter_plan(times, pp.identify_steps(i_sig, allow_consecutive=False), idx)
+    out = np.empty(len(idx))
+    for j in range(len(idx)):
+        lw, lo, ln = plan['lw'][j], plan['seg_lo'][j], plan['seg_len'][j]
+        pos = (plan['idx'][j] - lo + np.arange(-lw, lw + 1)) % (2 * ln)
+        pos = np.where(pos >= ln, 2 * ln - 1 - pos, pos)
+        out[j] = plan['taps'][plan['woff'][j]:plan['woff'][j] + 2 * lw + 1] @ v[2][lo + pos]
+    assert rel_err(out, g['tut_v'][2]) < 1e-13
+    assert abs(plan['taps'].sum() - len(idx)) < 1e-9                     # every kept sample's taps sum to one
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
