@@ -288,6 +288,30 @@ def run_gpu(args):
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         mat_gbs = mat_bytes / (float(np.mean(mb)) * 1e-3) / 1e9
 
+        # secondary roofline: chrono conditioning (antialiasing filter + decimation) of a batch of raw traces
+        # (HBM-read bound: every raw sample is read once, ~1 % of them are written back)
+        from hybdrt_b200 import preprocessing as pp
+        rt, ri, rvv = synth.make_raw_chrono_batch(1, seed=5)
+        n_tr = 4096
+        raw_dev = eng.dev(np.repeat(rvv, n_tr, 0) + 1e-6 * np.arange(n_tr)[:, None])
+        st_raw = rt[pp.identify_steps(ri, True)]
+        dec = pp.get_decimation_index(rt, st_raw, np.min(np.diff(rt)), 25, 8, 2, None)
+        fplan = pp.filter_plan(rt, pp.identify_steps(ri, allow_consecutive=False), dec)
+        for _ in range(3):
+            eng.filter_gather(raw_dev, fplan)
+        fb = []
+        for k in range(5):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.filter_gather(raw_dev, fplan)
+            b.record()
+            torch.cuda.synchronize()
+            fb.append(a.elapsed_time(b))
+        filt_bytes = 8.0 * n_tr * (len(rt) + len(dec))
+        filt_gbs = filt_bytes / (float(np.mean(fb)) * 1e-3) / 1e9
+        del raw_dev
+
         traffic = None
         prof = os.path.join(ROOT, 'profiles', 'qphb_traffic.json')
         if os.path.exists(prof):
@@ -331,6 +355,11 @@ def run_gpu(args):
                                       'bytes_per_launch': mat_bytes,
                                       'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback',
                                       'workload': f'{g} per-spectrum (freq, tau) grids, A_re + A_im 70 x 101 each'},
+            'roofline_chrono_filter': {'bound': 'hbm', 'achieved': filt_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                                       'frac': filt_gbs / hbm_peak, 'traffic': None, 'kernel': 'filter_gather_kernel',
+                                       'bytes_per_launch': filt_bytes,
+                                       'workload': f'{n_tr} raw traces x {len(rt)} samples -> {len(dec)} kept samples each '
+                                                   f'(downsample_data, decimation_interval=8, factor 2)'},
             'cpu_baseline': cpu,
         }
         print(json.dumps(line))

@@ -15,3 +15,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qphb -s 1 -c 1 -o $OUT/prof_$TAG -f \
   python bench.py --batch 2368 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full exit $?"
 ls -la $OUT
+# secondary kernels: one full capture each (matrix builder, chrono filter)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:impedance_interp_kernel -s 3 -c 1 -o $OUT/prof_interp_$TAG -f \
+  python tools/interp_bench.py > $OUT/ncu_interp_$TAG.log 2>&1; echo "ncu interp exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_gather -s 4 -c 1 -o $OUT/prof_filter_$TAG -f \
+  python bench.py --batch 512 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_filter_$TAG.log 2>&1; echo "ncu filter exit $?"
