@@ -199,7 +199,12 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
     __syncthreads();
     tr.uniform = s_nonuniform[0] == 0;
     ti.uniform = s_nonuniform[1] == 0;
-    const int pstep_r = (2 * kIThreads) / nb, pstep_m = (2 * kIThreads) % nb;   // index advance per pair-loop trip
+    // thread -> (column, row group): the column of a thread is fixed, so ln(tau) sits in a register and the row loop
+    // carries no index arithmetic; consecutive threads write consecutive columns (coalesced 8-byte stores)
+    const int groups = nb <= kIThreads ? kIThreads / nb : 1;
+    const int col0 = nb <= kIThreads ? tid % nb : tid;
+    const int rg = nb <= kIThreads ? tid / nb : 0;
+    const bool active = rg < groups;
     const long long items = (long long)n_grids * tiles_per_grid;
     int buf = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
@@ -213,33 +218,17 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
             else s_lw[i - nb] = log(freq[(size_t)g * nf + r0 + (i - nb)] * 2.0 * 3.141592653589793);  // 2 pi f
         }
         __syncthreads();   // also orders the slope table on the first pass; the other buffer is free by now
-        const size_t base = ((size_t)g * nf + r0) * nb;
-        const int cnt = rows * nb;
-        const int head = (int)(base & 1);               // element offset to the first 16-byte aligned pair
-        if (tid == 0 && head) {
-            const double x = s_lw[0] + s_lt[0];
-            a_re[base] = interp_smem(x, tr, npts);
-            a_im[base] = interp_smem(x, ti, npts);
-        }
-        const int npairs = (cnt - head) >> 1;
-        int rr = (head + 2 * tid) / nb, m = (head + 2 * tid) - rr * nb;
-        for (int p = tid; p < npairs; p += kIThreads, rr += pstep_r, m += pstep_m) {
-            if (m >= nb) { m -= nb; ++rr; }
-            const int idx = head + 2 * p;
-            const bool wrap = (m + 1 == nb);
-            const double xa = s_lw[rr] + s_lt[m];
-            const double xb = wrap ? s_lw[rr + 1] + s_lt[0] : s_lw[rr] + s_lt[m + 1];
-            const double2 vr = make_double2(interp_smem(xa, tr, npts), interp_smem(xb, tr, npts));
-            const double2 vi = make_double2(interp_smem(xa, ti, npts), interp_smem(xb, ti, npts));
-            __stcs(reinterpret_cast<double2*>(a_re + base + idx), vr);
-            __stcs(reinterpret_cast<double2*>(a_im + base + idx), vi);
-        }
-        if (tid == kIThreads - 1 && ((cnt - head) & 1)) {
-            const int idx = cnt - 1;
-            const int rr = idx / nb, m = idx - rr * nb;
-            const double x = s_lw[rr] + s_lt[m];
-            a_re[base + idx] = interp_smem(x, tr, npts);
-            a_im[base + idx] = interp_smem(x, ti, npts);
+        double* __restrict__ o_re = a_re + ((size_t)g * nf + r0) * nb;
+        double* __restrict__ o_im = a_im + ((size_t)g * nf + r0) * nb;
+        if (active) {
+            for (int col = col0; col < nb; col += kIThreads) {
+                const double lt = s_lt[col];
+                for (int rr = rg; rr < rows; rr += groups) {
+                    const double x = s_lw[rr] + lt;
+                    __stcs(o_re + (size_t)rr * nb + col, interp_smem(x, tr, npts));
+                    __stcs(o_im + (size_t)rr * nb + col, interp_smem(x, ti, npts));
+                }
+            }
         }
     }
 }
