@@ -222,34 +222,46 @@ class BatchFit:
         return dict(factors=h['pfrt_factors'], step_x=h['pfrt_x'], step_llh=llh, step_p_mat=h.get('pfrt_p'),
                     step_iters=h['pfrt_iters'])
 
-    def fit_parameters(self):
-        """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for the whole batch: dict of [B, ...] arrays."""
-        pl, h, sc = self.plan, self.host(['x', 'weights']), self.scales
-        x = h['x']
-        cs = sc['coefficient_scale'][:, None]
+    def extract_parameters(self, x):
+        """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for raw coefficient arrays x [B, n] or [B, F, n]
+        (scaled space, special parameters first): dict of unscaled arrays with the same leading shape."""
+        pl, sc = self.plan, self.scales
+        x = np.asarray(x)
+        lead = x.shape[:-1]
+
+        def per_b(a):                    # [B] -> broadcastable against x[..., i]
+            return np.asarray(a).reshape((len(a),) + (1,) * (len(lead) - 1))
+        cs = per_b(sc['coefficient_scale'])
         ns = pl['n_special']
-        out = {'x': x[:, ns:] * cs}
+        out = {'x': x[..., ns:] * cs[..., None]}
         sp = pl['special_qp_params']
-        out['R_inf'] = x[:, sp['R_inf']['index']] * cs[:, 0] if 'R_inf' in sp else np.zeros(len(x))
-        out['inductance'] = (x[:, sp['inductance']['index']] * cs[:, 0] * pl['inductance_scale']
-                             if 'inductance' in sp else np.zeros(len(x)))
-        out['C_inv'] = (x[:, sp['C_inv']['index']] * cs[:, 0] * pl['capacitance_scale']
-                        if 'C_inv' in sp else np.zeros(len(x)))
+        out['R_inf'] = x[..., sp['R_inf']['index']] * cs if 'R_inf' in sp else np.zeros(lead)
+        out['inductance'] = (x[..., sp['inductance']['index']] * cs * pl['inductance_scale']
+                             if 'inductance' in sp else np.zeros(lead))
+        out['C_inv'] = (x[..., sp['C_inv']['index']] * cs * pl['capacitance_scale']
+                        if 'C_inv' in sp else np.zeros(lead))
         if 'v_baseline' in sp:
             a = sp['v_baseline']['index']
             b = a + sp['v_baseline']['size']
-            vb = x[:, a:b] * (1.0 / pl['v_baseline_scale'])[None, :]
-            vb[:, 0] -= sc['scaled_response_offset']
-            out['v_baseline'] = vb * sc['response_signal_scale'][:, None]
+            vb = x[..., a:b] * (1.0 / pl['v_baseline_scale'])
+            vb[..., 0] -= per_b(sc['scaled_response_offset'])
+            out['v_baseline'] = vb * per_b(sc['response_signal_scale'])[..., None]
         if 'vz_offset' in sp:
-            out['vz_offset'] = x[:, sp['vz_offset']['index']]
+            out['vz_offset'] = x[..., sp['vz_offset']['index']]
         if 'x_dop' in sp:
             a = sp['x_dop']['index']
             b = a + sp['x_dop']['size']
-            dsv = pl['dop_scale_vector'][None, :]
+            dsv = pl['dop_scale_vector'] * np.ones(lead + (1,))
             if 'dop_column_scale' in sc:
-                dsv = dsv * sc['dop_column_scale'][:, None]
-            out['x_dop'] = x[:, a:b] * (dsv * cs)
+                dsv = dsv * per_b(sc['dop_column_scale'])[..., None]
+            out['x_dop'] = x[..., a:b] * (dsv * cs[..., None])
+        return out
+
+    def fit_parameters(self):
+        """DRT.extract_qphb_parameters (drt1d.py:6228-6289) for the whole batch: dict of [B, ...] arrays."""
+        pl, h, sc = self.plan, self.host(['x', 'weights']), self.scales
+        out = self.extract_parameters(h['x'])
+        cs = sc['coefficient_scale'][:, None]
         # sigma from the unscaled weights (drt1d.py:1082-1092)
         w_true = h['weights'] * pl['weight_factor']
         sig = 1.0 / w_true
@@ -257,6 +269,12 @@ class BatchFit:
         out['v_sigma_tot'] = sig[:, :nc] * sc['response_signal_scale'][:, None] if nc else None
         out['z_sigma_tot'] = (sig[:, nc:nc + nf] + 1j * sig[:, nc + nf:]) * cs if nf else None
         return out
+
+    def predict_drt(self, tau=None, ppd=20, order=0):
+        """DRT.predict_drt (drt1d.py:3040-3061) for the whole batch: gamma(tau) [B, len(tau)]."""
+        drt = self.plan['model']
+        tau = drt.get_tau_eval(ppd) if tau is None else np.asarray(tau, dtype=float)
+        return self.fit_parameters()['x'] @ drt._basis_eval_matrix(tau, order, self.plan['basis_tau']).T
 
     # ---- post-fit diagnostics of the mapping path (drtmd.py:256-279); need diag_tau at fit time
     def _uniform_weights(self):
@@ -311,15 +329,25 @@ class BatchFit:
         """DRT.predict_z at the fit frequencies (drt1d.py:3500-3542) for the whole batch."""
         pl = self.plan
         fp = self.fit_parameters()
-        if frequencies is not None and not np.array_equal(frequencies, pl['frequencies']):
-            _not_supported('batched predict_z at frequencies other than the fit grid')
-        f = pl['frequencies']
-        z = fp['x'] @ pl['zm_drt_host'].T + fp['R_inf'][:, None] + fp['inductance'][:, None] * 2j * np.pi * f[None, :]
+        same = frequencies is None or (pl['frequencies'] is not None and np.array_equal(frequencies, pl['frequencies']))
+        if same:
+            f, zm, zd = pl['frequencies'], pl['zm_drt_host'], pl.get('zm_dop_host')
+            es = pl.get('eis_vz_strength')
+        else:                           # matrices of the requested grid are built on the GPU
+            drt = pl['model']
+            f = np.asarray(frequencies, dtype=float)
+            a_re, a_im = drt.engine.build_impedance(f[None], pl['basis_tau'][None], drt.tau_epsilon, drt._mode(),
+                                                    drt.interpolate_lookups)
+            zm = (a_re[0] + 1j * a_im[0]).cpu().numpy()
+            zd = (drt.engine.build_dop_z(f[None], drt.basis_nu, drt.nu_epsilon)[0].cpu().numpy()
+                  if 'x_dop' in fp else None)
+            es = drt._vz_strength(None, f)[1] if 'vz_offset' in fp else None
+        z = fp['x'] @ zm.T + fp['R_inf'][:, None] + fp['inductance'][:, None] * 2j * np.pi * f[None, :]
         z = z + fp['C_inv'][:, None] * (2j * np.pi * f[None, :]) ** -1
         if 'x_dop' in fp:
-            z = z + fp['x_dop'] @ pl['zm_dop_host'].T
+            z = z + fp['x_dop'] @ zd.T
         if 'vz_offset' in fp:
-            z = z * (1 - fp['vz_offset'][:, None] * pl['eis_vz_strength'][None, :])
+            z = z * (1 - fp['vz_offset'][:, None] * es[None, :])
         return z
 
 
@@ -821,6 +849,7 @@ class DRT:
 
         plan = self._build_plan(times, i_signal, frequencies, opts)
         plan['opts'] = opts
+        plan['model'] = self
         sp, nc, nf = plan['special_qp_params'], plan['n_chrono'], plan['n_freq']
         self.fit_kwargs = dict(smooth_inf_response=smooth_inf_response, offset_steps=offset_steps,
                                step_offset_size=step_offset_size, nonneg=nonneg, eff_hp=eff_hp,
@@ -1172,12 +1201,64 @@ class DRT:
                 es[sel] = np.exp(-(veps * np.log(f_inv[sel] / chrono_tau_min)) ** 2)
         return cs, es
 
+    def extract_qphb_parameters(self, x):
+        """drt1d.py:6228-6289 for one raw coefficient vector (scaled space, special parameters first)."""
+        fp = self.last_batch.extract_parameters(np.asarray(x, dtype=float)[None])
+        return {k: (v[0] if np.ndim(v) >= 1 else v) for k, v in fp.items()}
+
+    def get_tau_eval(self, ppd):
+        """drtbase.py:263-283: one decade beyond the basis grid on either side."""
+        bt = self.fixed_basis_tau if self.fixed_basis_tau is not None else self.basis_tau
+        if bt is None:
+            raise ValueError('basis_tau must be set, either by specifying fixed_basis_tau or by fitting the '
+                             'DRT instanceto data, before using get_tau_eval')
+        lo, hi = np.min(np.log10(bt)) - 1, np.max(np.log10(bt)) + 1
+        return np.logspace(lo, hi, int((hi - lo) * ppd) + 1)
+
+    def _basis_eval_matrix(self, tau, order=0, basis_tau=None):
+        """basis.construct_func_eval_matrix, gaussian basis (basis.py:488-514, derivatives :218-233)."""
+        bt = self.basis_tau if basis_tau is None else basis_tau
+        y = np.log(np.asarray(tau, dtype=float))[:, None] - np.log(bt)[None, :]
+        e = self.tau_epsilon
+        phi = np.exp(-(e * y) ** 2)
+        if order == 0:
+            return phi
+        if order == 1:
+            return -2 * e ** 2 * y * phi
+        if order == 2:
+            return (-2 * e ** 2 + 4 * e ** 4 * y ** 2) * phi
+        if order == 3:
+            return (12 * e ** 4 * y - 8 * e ** 6 * y ** 3) * phi
+        _not_supported(f'distribution derivative order {order}')
+
+    def predict_drt(self, tau=None, ppd=20, x=None, order=0, sign=1, normalize=False, normalize_by=None,
+                    abs_norm=False):
+        """drt1d.py:3040-3061: the distribution (or a derivative of it) on ``tau``."""
+        tau = self.get_tau_eval(ppd) if tau is None else np.asarray(tau, dtype=float)
+        if x is None:
+            xd = self.fit_parameters['x']
+        elif isinstance(x, dict):
+            xd = x['x']
+        else:
+            x = np.asarray(x, dtype=float)
+            xd = x if len(x) <= len(self.basis_tau) else self.extract_qphb_parameters(x)['x']
+        if normalize_by is not None:
+            normalize = True
+        if normalize and normalize_by is None:
+            normalize_by = float(np.sum(np.abs(xd) if abs_norm else xd) * self.tau_basis_area)
+        return self._basis_eval_matrix(tau, order) @ xd / (normalize_by if normalize else 1)
+
+    def predict_distribution(self, *args, **kw):
+        warnings.warn('predict_distribution is deprecated and will be removed in the future. '
+                      'Please use predict_drt instead', DeprecationWarning)
+        return self.predict_drt(*args, **kw)
+
     def predict_z(self, frequencies, include_vz_offset=True, x=None, include_dop=True, include_drt=True,
                   include_inductance=True, include_ohmic=True, include_cap=True):
         frequencies = np.asarray(frequencies, dtype=float)
         fp = self.fit_parameters if x is None else x
         if not isinstance(fp, dict):
-            _not_supported('predict_z with a raw coefficient vector')
+            fp = self.extract_qphb_parameters(fp)
         a_re, a_im = self.engine.build_impedance(frequencies[None], self.basis_tau[None], self.tau_epsilon,
                                                  self._mode(), self.interpolate_lookups)
         zm = (a_re[0] + 1j * a_im[0]).cpu().numpy()
@@ -1198,25 +1279,59 @@ class DRT:
             z *= (1 - fp.get('vz_offset', 0) * es)
         return z
 
-    def predict_response(self, times=None, include_vz_offset=True):
-        """Voltage response at the fit times (drt1d.py:3363-3461)."""
-        if times is not None and not np.array_equal(times, self.t_fit):
-            _not_supported('predict_response at times other than the fit times')
-        pl, fp = self.last_batch.plan, self.fit_parameters
-        times = pl['times']
-        rm_drt = pl['rm_drt_chrono'].cpu().numpy()
-        resp = rm_drt @ fp['x'] + pl['inf_rv'] * fp.get('R_inf', 0) + fp.get('C_inv', 0) * pl['cap_rv']
-        if fp.get('x_dop') is not None and 'rm_dop_chrono' in pl:     # drt1d.py:3431-3432
-            resp = resp + pl['rm_dop_chrono'].cpu().numpy() @ fp['x_dop']
+    def predict_response(self, times=None, input_signal=None, step_times=None, step_sizes=None, x=None,
+                         include_vz_offset=True, include_dop=True, include_drt=True, include_ohmic=True,
+                         include_cap=True, v_baseline=None):
+        """Voltage response (drt1d.py:3363-3461): at the fit times from the matrices of the fit, at any other
+        times (with the fitted steps, or explicit step_times / step_sizes) from matrices rebuilt on the GPU."""
+        pl = self.last_batch.plan
+        if x is None:
+            fp = self.fit_parameters
+        else:
+            fp = x if isinstance(x, dict) else self.extract_qphb_parameters(x)
+        if input_signal is not None:
+            _not_supported('predict_response from a new input signal (pass step_times and step_sizes)')
+        if step_times is not None and step_sizes is None:
+            raise ValueError('If input signal steps are provided, both step_times and step_sizes must be provided; '
+                             'received step_times only')
+        if times is None and step_times is None:
+            times = pl['times']
+            rm_drt = pl['rm_drt_chrono'].cpu().numpy()
+            inf_rv, cap_rv = pl['inf_rv'], pl['cap_rv']
+            rm_dop = pl['rm_dop_chrono'].cpu().numpy() if 'rm_dop_chrono' in pl else None
+        else:
+            times = np.asarray(pl['times'] if times is None else times, dtype=float)
+            st = np.asarray(self.step_times if step_times is None else step_times, dtype=float)
+            sa = np.asarray(self.step_sizes if step_times is None else step_sizes, dtype=float)
+            eng = self.engine
+            rm_drt = eng.build_response(times[None], self.basis_tau[None], st[None], sa[None], self.tau_epsilon,
+                                        self._mode(), self.interpolate_lookups)[0].cpu().numpy()
+            inf_rv, cap_rv = np.zeros(len(times)), np.zeros(len(times))
+            for t0, a0 in zip(st, sa):                          # mat1d.py:399-443 (smooth_inf_response)
+                inf_rv += a0 * unit_step(times, t0)
+                cap_rv[times >= t0] += a0 * (times[times >= t0] - t0)
+            rm_dop = (eng.build_dop_v(times[None], self.basis_nu, st[None], sa[None], self.nu_epsilon)[0].cpu().numpy()
+                      if self.fit_dop else None)
+        resp = np.zeros(len(times))
+        if include_drt:
+            resp += rm_drt @ fp['x']
+        if include_ohmic:
+            resp += inf_rv * fp.get('R_inf', 0)
+        if include_cap:
+            resp += fp.get('C_inv', 0) * cap_rv
+        if fp.get('x_dop') is not None and include_dop and rm_dop is not None:     # drt1d.py:3431-3432
+            resp += rm_dop @ fp['x_dop']
         if include_vz_offset:
             cs, _ = self._vz_strength(times, None)
             resp = resp * (1 + fp.get('vz_offset', 0) * cs)
-        vb = np.zeros((len(times), len(fp['v_baseline'])))
-        for d in range(self.v_baseline_deg + 1):
-            vb[:, d] = (times - times[0]) ** d
-        if self.v_baseline_sqrt:
-            vb[:, -1] = (times - times[0]) ** 0.5
-        return resp + vb @ fp['v_baseline']
+        if v_baseline is None:                                  # predict_v_baseline, drt1d.py:3466-3473
+            vb = np.zeros((len(times), len(fp['v_baseline'])))
+            for d in range(self.v_baseline_deg + 1):
+                vb[:, d] = (times - times[0]) ** d
+            if self.v_baseline_sqrt:
+                vb[:, -1] = (times - times[0]) ** 0.5
+            v_baseline = vb @ fp['v_baseline']
+        return resp + v_baseline
 
     def predict_r_p(self, absolute=False):
         """Polarisation resistance: sum of DRT coefficients times basis area (drt1d.py:3552-3590)."""

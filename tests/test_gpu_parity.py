@@ -541,6 +541,31 @@ def test_chrono_downsampling(eng):
     assert rel_err(drt.predict_response(), g['fit_v_pred']) < FIT_TOL
 
 
+def test_predictions_away_from_the_fit_grids():
+    """predict_drt (drt1d.py:3040-3061), predict_z at new frequencies, predict_response at new times and with
+    explicit steps (drt1d.py:3363-3461), single spectrum and batched, against the unmodified reference."""
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200 import synth
+    g = load_golden('predict.npz')
+    hy = load_golden('chrono_flex.npz')           # the small hybrid trace
+    drt = DRT()
+    drt.fit_hybrid(hy['times'], hy['i_signal'], hy['v_signal'][0], hy['freq'], hy['z'][0])
+    assert rel_err(drt.predict_z(g['f_new']), g['z_new']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['f_new'], x=drt.cvx_result['x']), g['z_raw_x']) < FIT_TOL
+    assert rel_err(drt.predict_response(g['t_new']), g['v_new']) < FIT_TOL
+    assert rel_err(drt.predict_response(g['t_new'], step_times=np.array([0.0, 0.3]), step_sizes=np.array([0.01, -0.01])),
+                   g['v_steps']) < FIT_TOL
+    for order, key in ((0, 'drt0'), (1, 'drt1'), (2, 'drt2')):
+        assert rel_err(drt.predict_drt(g['tau'], order=order), g[key]) < FIT_TOL
+    assert rel_err(drt.get_tau_eval(20), g['tau_default']) < 1e-13
+    assert rel_err(drt.predict_drt(), g['drt_default']) < FIT_TOL
+    assert rel_err(drt.predict_drt(g['tau'], normalize=True), g['drt_norm']) < FIT_TOL
+    freq, z = synth.make_eis_batch(3, seed=0)
+    res = DRT().fit_eis_batch(freq, z)
+    assert rel_err(res.predict_z(g['f_new']), g['b_z_new']) < FIT_TOL
+    assert rel_err(res.predict_drt(g['tau']), g['b_drt0']) < FIT_TOL
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')
