@@ -1351,6 +1351,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                                         // the initialisation runs twice (-2, -1), the second time weighted by the
                                         // first estimate
     conv = false;
+    final_pq = false;
     if (cont && c.vz >= 0) {
         c.vz0 = p.vz_scratch + (size_t)b * N;
         for (int r = tid; r < N; r += C::kThreads) c.vz0[r] = c.vzcol[r];
@@ -1478,7 +1479,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if ((conv && (!cont || it >= p.pfrt_min_iter)) || it >= max_it) {
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
             if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = C::roww()[r];
-            if (p.resid_ss) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
+            if (p.resid_ss && !cont) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
                 double t2[2] = {0.0, 0.0};
                 for (int r = tid; r < N; r += C::kThreads) {
                     if (r < c.nc) t2[0] += C::rowr2(c.N)[r]; else t2[1] += C::rowr2(c.N)[r];
@@ -1486,7 +1487,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                 block_reduce<C, 2, 0u>(t2, c);
                 if (tid == 0) { p.resid_ss[2 * (size_t)b] = t2[0]; p.resid_ss[2 * (size_t)b + 1] = t2[1]; }
             }
-            if (p.p_matrix == nullptr && p.dist_var == nullptr) break;
+            // calculate_pq / the post-fit diagnostics belong to the plain fit (with PFRT: to its first step, whose
+            // attributes the reference keeps, drt1d.py:2588-2603)
+            if (cont || (p.p_matrix == nullptr && p.dist_var == nullptr)) break;
             final_pq = true;
         }
     }
@@ -1665,9 +1668,8 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
         set_error("outlier_p must lie in (0, 1) and needs the outlier_t buffer");
         return HDRT_ERR_ARG;
     }
-    if (p.n_pfrt > 0 && (!p.pfrt_factors || !p.pfrt_x || !p.pfrt_llh || !p.weights || p.pfrt_max_iter <= 0 ||
-                         p.p_matrix || p.dist_var)) {
-        set_error("PFRT needs pfrt_factors, pfrt_x, pfrt_llh, weights and pfrt_max_iter > 0 (and no p_matrix / dist_var)");
+    if (p.n_pfrt > 0 && (!p.pfrt_factors || !p.pfrt_x || !p.pfrt_llh || !p.weights || p.pfrt_max_iter <= 0)) {
+        set_error("PFRT needs pfrt_factors, pfrt_x, pfrt_llh, weights and pfrt_max_iter > 0");
         return HDRT_ERR_ARG;
     }
     if ((p.hyp.solve_rp || p.hyp.update_scale) && (!p.scale_factors || !(p.hyp.rp_scale > 0.0) || !(p.hyp.basis_area > 0.0))) {

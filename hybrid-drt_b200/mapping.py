@@ -14,8 +14,12 @@ The post-fit diagnostics the reference computes after every fit (drtmd.py:256-27
 diag of ``estimate_distribution_cov`` on the tau supergrid with ``extend_var``, ``obs_llh``, ``obs_rss`` with uniform
 weights, normalised) come out of the same kernel launch (``diag_tau``).
 
+``fit_type='pfrt'`` (drtmd.py:1140-1160, 1304-1342): every observation gets one solution per factor
+(``obs_x`` [n, F, n_tau], ``obs_special[key]`` [n, F]); the whole group still goes to the GPU as one launch
+(initial fit + all continuation steps inside the kernel).
+
 Not mirrored (outside SURVEY.md section 8): file readers, resolve / filter / badness scoring, prediction
-helpers, PFRT.
+helpers.
 """
 import time
 
@@ -32,12 +36,14 @@ class DRTMD:
                  fit_inductance=True, fit_ohmic=True, fit_capacitance=False, fixed_basis_nu=None, fit_dop=False,
                  normalize_dop=True, nu_basis_type='gaussian', nu_epsilon=None, time_precision=10,
                  input_signal_precision=10, frequency_precision=10, fit_kw=None, fit_type='drt',
-                 print_diagnostics=False, print_progress=True, warn=False, llh_kw=None, rss_kw=None, device=0):
+                 pfrt_factors=None, print_diagnostics=False, print_progress=True, warn=False, llh_kw=None,
+                 rss_kw=None, device=0):
         for kw_dict in (llh_kw, rss_kw):
             if kw_dict and (kw_dict.get('normalize', True) is not True or kw_dict.get('weights', 'uniform') != 'uniform'):
                 raise NotImplementedError('hybdrt_b200: llh_kw / rss_kw other than the DRTMD defaults')
-        if fit_type != 'drt':
-            raise NotImplementedError("hybdrt_b200: fit_type other than 'drt' (PFRT) is outside the accelerated path")
+        if fit_type not in ('drt', 'pfrt'):
+            raise ValueError(f"Invalid fit_type {fit_type}. Options: ['drt', 'pfrt']")
+        self.pfrt_factors = np.logspace(-0.7, 0.7, 11) if pfrt_factors is None else np.asarray(pfrt_factors, dtype=float)
         self.tau_supergrid = np.asarray(tau_supergrid, dtype=float)
         self.drt1d = DRT(interpolate_integrals=True, tau_supergrid=self.tau_supergrid, tau_epsilon=tau_epsilon,
                          tau_basis_type=tau_basis_type, fixed_basis_nu=fixed_basis_nu, nu_epsilon=nu_epsilon,
@@ -65,14 +71,14 @@ class DRTMD:
         self.clear_fits()
 
     def clear_fits(self):
-        n, nt = self._n, len(self.tau_supergrid)
+        n = self._n
         self.obs_fit_attr = [None] * n
         self.obs_fit_status = np.zeros(n, dtype=bool)
         self.obs_fit_errors = [None] * n
         self.obs_fit_badness = np.zeros(n)
         self.obs_tau_indices = [None] * n
-        self.obs_x = np.zeros((n, nt))
-        self.obs_drt_var = np.zeros((n, nt))
+        self.obs_x = np.zeros((n, *self.drt_param_shape()))
+        self.obs_drt_var = np.zeros((n, *self.drt_param_shape()))
         self.obs_llh, self.obs_rss = np.zeros(n), np.zeros(n)
         self.obs_special = None
         self.obs_outer_iterations = np.zeros(n, dtype=int)   # not in the reference: iteration count per fit
@@ -91,11 +97,19 @@ class DRTMD:
         return self.drt1d.tau_basis_area
 
     def drt_param_shape(self, factor_index=None):
+        """drtmd.py:1304-1316"""
+        if self.fit_type == 'pfrt':
+            if factor_index is None:
+                return [len(self.pfrt_factors), len(self.tau_supergrid)]
+            nf = len(np.atleast_1d(factor_index))
+            return [nf, len(self.tau_supergrid)] if nf > 1 else [len(self.tau_supergrid)]
         return [len(self.tau_supergrid)]
 
     def special_param_shape(self, key):
+        """drtmd.py:1318-1337"""
         size = self.drt1d.special_qp_params[key].get('size', 1)
-        return [] if size == 1 else [size]
+        lead = [len(self.pfrt_factors)] if self.fit_type == 'pfrt' else []
+        return lead if size == 1 else lead + [size]
 
     # ---- observations (drtmd.py:186-243) -------------------------------------------------------------
     def add_observation(self, psi, chrono_data, eis_data, group_id=None, fit=False):
@@ -119,8 +133,8 @@ class DRTMD:
         self.obs_tau_indices.append(None)
         self.obs_fit_status = np.append(self.obs_fit_status, False)
         self.obs_fit_badness = np.append(self.obs_fit_badness, 0)
-        self.obs_x = np.vstack([self.obs_x, np.zeros((1, nt))])
-        self.obs_drt_var = np.vstack([self.obs_drt_var, np.zeros((1, nt))])
+        self.obs_x = np.concatenate([self.obs_x, np.zeros((1, *self.drt_param_shape()))], axis=0)
+        self.obs_drt_var = np.concatenate([self.obs_drt_var, np.zeros((1, *self.drt_param_shape()))], axis=0)
         self.obs_llh, self.obs_rss = np.append(self.obs_llh, 0), np.append(self.obs_rss, 0)
         self.obs_outer_iterations = np.append(self.obs_outer_iterations, 0)
         self.obs_status = np.append(self.obs_status, 0)
@@ -154,8 +168,8 @@ class DRTMD:
         self.obs_tau_indices.extend([None] * nb)
         self.obs_fit_status = np.concatenate([self.obs_fit_status, np.zeros(nb, dtype=bool)])
         self.obs_fit_badness = np.concatenate([self.obs_fit_badness, np.zeros(nb)])
-        self.obs_x = np.vstack([self.obs_x, np.zeros((nb, nt))])
-        self.obs_drt_var = np.vstack([self.obs_drt_var, np.zeros((nb, nt))])
+        self.obs_x = np.concatenate([self.obs_x, np.zeros((nb, *self.drt_param_shape()))], axis=0)
+        self.obs_drt_var = np.concatenate([self.obs_drt_var, np.zeros((nb, *self.drt_param_shape()))], axis=0)
         self.obs_llh = np.concatenate([self.obs_llh, np.zeros(nb)])
         self.obs_rss = np.concatenate([self.obs_rss, np.zeros(nb)])
         self.obs_outer_iterations = np.concatenate([self.obs_outer_iterations, np.zeros(nb, dtype=int)])
@@ -234,14 +248,27 @@ class DRTMD:
             # every rank builds the plan (cheap) so that special_qp_params / basis_tau agree everywhere
             zz = z if (z is None or len(z)) else np.ones((1, z.shape[1]), dtype=complex)
             vv = v if (v is None or len(v)) else np.ones((1, v.shape[1]))
-            if chrono0[0] is None:
+            if self.fit_type == 'pfrt':
+                # drtmd.py:1339-1342 calls DRT._pfrt_fit_core(*chrono, *eis, **fit_kw): the factors are those of
+                # fit_kw (default logspace(-1, 1, 11)); DRTMD.pfrt_factors only sizes the containers
+                res = drt._pfrt_fit_core_batch(chrono0[0], chrono0[1], vv if chrono0[0] is not None else None,
+                                               eis0[0], zz if eis0[0] is not None else None,
+                                               diag_tau=self.tau_supergrid, **self.fit_kw)
+            elif chrono0[0] is None:
                 res = drt.fit_eis_batch(eis0[0], zz, diag_tau=self.tau_supergrid, **self.fit_kw)
             elif eis0[0] is None:
                 res = drt.fit_chrono_batch(chrono0[0], chrono0[1], vv, diag_tau=self.tau_supergrid, **self.fit_kw)
             else:
                 res = drt.fit_hybrid_batch(chrono0[0], chrono0[1], vv, eis0[0], zz, diag_tau=self.tau_supergrid,
                                            **self.fit_kw)
-        fp = res.fit_parameters()
+        if self.fit_type == 'pfrt':
+            step_x = res.pfrt_result()['step_x']
+            if step_x.shape[1] != len(self.pfrt_factors):
+                raise ValueError(f'{step_x.shape[1]} PFRT factors were fitted but pfrt_factors has '
+                                 f'{len(self.pfrt_factors)} entries')
+            fp = res.extract_parameters(step_x)                 # format_1d_params, drtmd.py:1145-1158
+        else:
+            fp = res.fit_parameters()
         host = res.host(['status', 'n_outer'])
         left = nearest_index(self.tau_supergrid, drt.basis_tau[0])
         right = nearest_index(self.tau_supergrid, drt.basis_tau[-1]) + 1
@@ -261,16 +288,17 @@ class DRTMD:
             if key not in self.obs_special:
                 self.obs_special[key] = np.zeros([self.num_obs, *self.special_param_shape(key)])
         bad = (out['status'] & (_engine.ST_NAN | _engine.ST_KKT_FAIL)) != 0
-        bad |= ~np.all(np.isfinite(out['x']), axis=1)
+        bad |= ~np.all(np.isfinite(out['x']).reshape(len(out['x']), -1), axis=1)
         if bad.any() and not ignore_errors:
             raise ValueError(f'Error encountered at obs_index {int(members[np.argmax(bad)])}: '
                              'Rank(A) < p or Rank([P; A; G]) < n')
         good = members[~bad]
-        self.obs_x[good, :] = 0.0
-        self.obs_x[good, left:right] = out['x'][~bad]
+        self.obs_x[good] = 0.0
+        self.obs_x[good, ..., left:right] = out['x'][~bad]
         for key in sp_keys:
             self.obs_special[key][good] = out['sp_' + key][~bad]
-        self.obs_drt_var[good] = out['drt_var'][~bad]
+        dv = out['drt_var'][~bad]                               # of the initial fit; one row per factor (drtmd.py:270)
+        self.obs_drt_var[good] = dv[:, None, :] if self.fit_type == 'pfrt' else dv
         self.obs_llh[good] = out['llh'][~bad]
         self.obs_rss[good] = out['rss'][~bad]
         self.obs_fit_status[good] = True

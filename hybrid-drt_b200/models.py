@@ -1052,10 +1052,11 @@ class DRT:
         return factors, pfrt, dict(kw, max_iter=max_init_iter, xtol=xtol)
 
     def _pfrt_fit_core_batch(self, times, i_signal, v_batch, frequencies, z_batch, factors=None, max_iter_per_step=10,
-                             max_init_iter=20, xtol=1e-2, nonneg=True, want_p=False, **kw):
+                             max_init_iter=20, xtol=1e-2, nonneg=True, want_p=False, diag_tau=None, **kw):
         factors, pfrt, kw = self._pfrt_setup(factors, max_iter_per_step, max_init_iter, xtol, kw)
         pfrt['want_p'] = want_p
-        return self._fit_core_batch(times, i_signal, v_batch, frequencies, z_batch, nonneg=nonneg, pfrt=pfrt, **kw)
+        return self._fit_core_batch(times, i_signal, v_batch, frequencies, z_batch, nonneg=nonneg, pfrt=pfrt,
+                                    diag_tau=diag_tau, **kw)
 
     def pfrt_fit_eis_batch(self, frequencies, z, **kw):
         """pfrt_fit_eis for z [batch, Nf]; BatchFit.pfrt_result() holds the per-factor outputs."""

@@ -38,8 +38,23 @@ def main():
     for key, val in md.obs_special.items():
         out['special_' + key] = np.asarray(val)
     path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_small.npz')
-    np.savez_compressed(path, **out)
-    print('wrote', path, {k: np.shape(v) for k, v in out.items()})
+    if '--pfrt-only' not in sys.argv:
+        np.savez_compressed(path, **out)
+        print('wrote', path, {k: np.shape(v) for k, v in out.items()})
+    # fit_type='pfrt': one solution per factor and observation (drtmd.py:1140-1160)
+    mp = DRTMD(tau_supergrid=supergrid, psi_dim_names=['row', 'col'], print_progress=False, fit_type='pfrt')
+    for b in range(3):
+        mp.add_observation(psi[b], None, (freq, z[b]))
+    mp.fit_all()
+    assert mp.obs_fit_status.all()
+    outp = dict(freq=freq, z=z[:3], psi=psi[:3], tau_supergrid=supergrid, obs_x=mp.obs_x,
+                obs_tau_indices=np.array(mp.obs_tau_indices), obs_drt_var=mp.obs_drt_var, obs_llh=mp.obs_llh,
+                obs_rss=mp.obs_rss, pfrt_factors=mp.pfrt_factors)
+    for key, val in mp.obs_special.items():
+        outp['special_' + key] = np.asarray(val)
+    path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_pfrt.npz')
+    np.savez_compressed(path, **outp)
+    print('wrote', path, {k: np.shape(v) for k, v in outp.items()})
 
 
 if __name__ == '__main__':

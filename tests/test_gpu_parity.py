@@ -613,6 +613,26 @@ def test_mapping_drtmd_against_the_reference():
         md2.add_observation([0, 0], None, (g['freq'],))
 
 
+def test_mapping_drtmd_pfrt_against_the_reference():
+    """DRTMD(fit_type='pfrt') (drtmd.py:1140-1160, 1304-1342): one solution per factor and observation; the
+    diagnostics are those of the initial fit."""
+    from hybdrt_b200.mapping import DRTMD
+    g = load_golden('drtmd_pfrt.npz')
+    md = DRTMD(tau_supergrid=g['tau_supergrid'], psi_dim_names=['row', 'col'], print_progress=False, fit_type='pfrt')
+    assert np.allclose(md.pfrt_factors, g['pfrt_factors'])
+    md.add_observations(g['psi'], g['freq'], g['z'])
+    md.fit_all()
+    assert md.obs_fit_status.all() and md.obs_x.shape == g['obs_x'].shape
+    assert np.array_equal(np.array(md.obs_tau_indices), g['obs_tau_indices'])
+    assert rel_err(md.obs_x, g['obs_x']) < FIT_TOL
+    assert rel_err(md.obs_special['R_inf'], g['special_R_inf']) < FIT_TOL
+    assert rel_err(md.obs_special['inductance'], g['special_inductance']) < FIT_TOL
+    assert rel_err(md.obs_drt_var, g['obs_drt_var']) < 1e-5
+    assert rel_err(md.obs_rss, g['obs_rss']) < FIT_TOL and rel_err(md.obs_llh, g['obs_llh']) < FIT_TOL
+    with pytest.raises(ValueError):
+        DRTMD(tau_supergrid=g['tau_supergrid'], fit_type='nonsense')
+
+
 def test_full_size_c2_batch_properties():
     """BASELINE config C2 at its full size (10,000 spectra) through the public API: size-independent properties,
     plus the oracle on a few members of the big batch."""
