@@ -605,17 +605,13 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
     double* panr = C::pan() + 64 * c.wr + 2 * lane;   // tile j = W a + wr: + 64 W a
     double* panc = C::pan() + 64 * c.wc + 2 * lane;
     PROF_ADD(16);
-    // the diagonal tile of column 0
-    if (c.wr == 0 && c.wc == 0) {
-        double2 ykk;
-        const bool ok = diag_factor(S[0], C::binv(), ykk, lane);
-        S[0] = ykk;
-        if (lane == 0) *C::flag() = ok ? 1 : 0;
-    }
+    // k = -1 is the prologue: only the look-ahead part runs (the diagonal tile of column 0 needs no update), so
+    // that the sweep holds a single instance of the diagonal-tile code
 #pragma unroll 1
-    for (int k = 0; k < T; ++k) {
-        const int kw = k % W, kd = k / W;
-        const bool diag_owner = (kw == c.wr) && (kw == c.wc);
+    for (int k = -1; k < T; ++k) {
+        const int kw = (k + W) % W, kd = k < 0 ? -1 : k / W;
+        const bool diag_owner = (kw == c.wr) && (kw == c.wc) && k >= 0;
+        if (k >= 0) {
         PROF_ADD(17);
         __syncthreads();  // (A) -L_kk^-1 published
         PROF_ADD(18);
@@ -673,6 +669,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
         PROF_ADD(19);
         __syncthreads();  // (B) column k published
         PROF_ADD(20);
+        }
         if (k + 1 < T) {
             // look-ahead: the owner of the next diagonal tile updates and factorises it before anything else
             const int k1w = (k + 1) % W, k1d = (k + 1) / W;
@@ -682,7 +679,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
 #pragma unroll
                 for (int a = 0; a < C::A; ++a) {
                     if (a == k1d) {
-                        tile_mma(S[C::sidx(a, a)], lds2(panr + a * (W * 64)), lds2(panc + a * (W * 64)));
+                        if (k >= 0) tile_mma(S[C::sidx(a, a)], lds2(panr + a * (W * 64)), lds2(panc + a * (W * 64)));
                         sk = S[C::sidx(a, a)];
                     }
                 }
@@ -694,6 +691,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                 if (lane == 0) *C::flag() = ok ? 1 : 0;
             }
             PROF_ADD(17);
+            if (k >= 0) {
 #pragma unroll
             for (int a = 0; a < C::A; ++a) {
                 const int j = W * a + c.wr;
@@ -703,6 +701,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                     for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(panc + b * (W * 64)));
                     if (c.dv && !(next_owner && a == k1d)) tile_mma(S[C::sidx(a, a)], Fa, lds2(panc + a * (W * 64)));
                 }
+            }
             }
             PROF_ADD(21);
         }
@@ -803,40 +802,44 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
             if (iters <= 0) { out.fatal = true; xi = nan(""); }
             break;
         }
-        if (iters < 0) {
-            // solve [P+I] x = -q - h ; z = -x - h ; s = -z, shifted into the cone
-            if (act) bs[tid] = -qi - hi;
-            __syncthreads();
-            solve_phase<C>(c, S, bs);
-            xi = act ? sum_parts<C>(C::W, C::W, tid) : 0.0;
-            zi = -xi - hi;
-            si = -zi;
-            double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
-            block_reduce<C, 4, 0xAu>(t4, c);
-            const double nrms = sqrt(t4[0]), ts = t4[1], nrmz = sqrt(t4[2]), tz = t4[3];
-            if (ts >= -1e-8 * fmax(nrms, 1.0)) si += 1.0 + ts;
-            if (tz >= -1e-8 * fmax(nrmz, 1.0)) zi += 1.0 + tz;
-            continue;
-        }
+        // One instance of the solve serves the initial point (a single pass with rhs -q - h) and the two Mehrotra
+        // passes of an iteration.
+        const bool start = iters < 0;
         const double lamsq = lam * lam;
         const double mu = gap / (double)n;
         double sigma = 0.0, step = 1.0;
-        double ws3 = 0.0, dxi = 0.0, dsi = 0.0, dzi = 0.0;
+        double ws3 = 0.0, dxi = 0.0, dsi = 0.0, dzi = 0.0, zs = 0.0;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            dsi = 0.0;
-            if (pass == 1) dsi -= ws3;
-            dsi -= lamsq;
-            dsi += sigma * mu;
-            dxi = -rxi;
-            dzi = -rzi;
-            dsi = dsi / lam;
-            dzi = dzi - di * dsi;
-            const double zs = dinv * dzi;
-            if (act) bs[tid] = dxi - dinv * zs;
+        for (int pass = start ? 1 : 0; pass < 2; ++pass) {
+            if (start) {
+                // solve [P+I] x = -q - h ; z = -x - h ; s = -z, shifted into the cone
+                if (act) bs[tid] = -qi - hi;
+            } else {
+                dsi = 0.0;
+                if (pass == 1) dsi -= ws3;
+                dsi -= lamsq;
+                dsi += sigma * mu;
+                dxi = -rxi;
+                dzi = -rzi;
+                dsi = dsi / lam;
+                dzi = dzi - di * dsi;
+                zs = dinv * dzi;
+                if (act) bs[tid] = dxi - dinv * zs;
+            }
             __syncthreads();
             solve_phase<C>(c, S, bs);
             dxi = act ? sum_parts<C>(C::W, C::W, tid) : 0.0;
+            if (start) {
+                xi = dxi;
+                zi = -xi - hi;
+                si = -zi;
+                double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
+                block_reduce<C, 4, 0xAu>(t4, c);
+                const double nrms = sqrt(t4[0]), ts = t4[1], nrmz = sqrt(t4[2]), tz = t4[3];
+                if (ts >= -1e-8 * fmax(nrms, 1.0)) si += 1.0 + ts;
+                if (tz >= -1e-8 * fmax(nrmz, 1.0)) zi += 1.0 + tz;
+                break;
+            }
             dzi = -dinv * dxi - zs;
             dsi = dsi - dzi;
             const double prod = dsi * dzi;
@@ -854,6 +857,7 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
                 sigma = sg * sg * sg;
             }
         }
+        if (start) continue;
         PROF_ADD(10);
         xi += step * dxi;
         dsi = step * dsi + 1.0;
