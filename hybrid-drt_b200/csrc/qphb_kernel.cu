@@ -683,6 +683,7 @@ __device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
                         sk = S[C::sidx(a, a)];
                     }
                 }
+                PROF_ADD(22);
                 double2 ykk;
                 const bool ok = diag_factor(sk, C::binv(), ykk, lane);
                 PROF_COUNT(24);

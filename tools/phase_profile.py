@@ -18,7 +18,7 @@ out = os.path.join(ROOT, 'hybrid-drt_b200', '_lib', 'libhybdrt_b200_prof.so')
 if '--nobuild' not in sys.argv:
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-DHDRT_PROFILE',
                            '-Xcompiler', '-fPIC', '-shared', '-I', os.path.join(ROOT, 'include'), '-I', csrc, '-o', out] +
-                          [os.path.join(csrc, f) for f in ('capi.cu', 'matrix_kernels.cu', 'qphb_kernel.cu')] + ['-lcudart'])
+                          [os.path.join(csrc, f) for f in ('capi.cu', 'matrix_kernels.cu', 'chrono_kernels.cu', 'qphb_kernel.cu')] + ['-lcudart'])
 if not torch.cuda.is_available():
     sys.exit(0)
 from hybdrt_b200 import engine as E, synth  # noqa: E402
@@ -42,7 +42,7 @@ grid = min(batch, 148 * 3)
 fits_block0 = int(np.ceil(batch / grid))  # approximately; the work queue decides
 names = {0: 'other(outer)', 1: 'gram', 2: 'qp total', 3: 'hyper', 4: 'weights', 8: 'qp: matvec+residual', 9: 'qp: factor_invert',
          10: 'qp: solves+step', 16: 'fi: load', 17: 'fi: diag (owner)', 18: 'fi: wait A', 19: 'fi: finalize', 20: 'fi: wait B',
-         21: 'fi: update', 5: 'gram: chunks', 6: 'gram: L2 add', 11: 'w: residual', 12: 'w: vmm', 13: 'hyper: s loop', 14: 'hyper: rho loop'}
+         21: 'fi: update', 22: 'fi: look-ahead tile update (owner)', 5: 'gram: chunks', 6: 'gram: L2 add', 11: 'w: residual', 12: 'w: vmm', 13: 'hyper: s loop', 14: 'hyper: rho loop'}
 tot = v[0] + v[1] + v[2] + v[3] + v[4]
 print(f'block 0 total cycles {tot:.3e}  fits {v[25]:.0f}  diag calls (warp 0) {v[24]:.0f} -> {v[17] / max(v[24], 1):.0f} cycles each; per fit {tot / max(v[25], 1):.3e}')
 for k in sorted(names):
