@@ -1389,12 +1389,13 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
         if (!init) {
             for (int r = tid; r < N; r += C::kThreads) {
                 double w = C::roww()[r];
+                const double wf = (C::EXT && p.weight_factor_vec) ? p.weight_factor_vec[r] : hy.weight_factor;
                 if (final_pq) {
-                    w *= hy.weight_factor;
+                    w *= wf;
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
                 } else {
                     if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
-                    if (it > 0 || cont) w = w * hy.weight_factor;   // a continuation scales on every pass (drt1d.py:1320)
+                    if (it > 0 || cont) w = w * wf;   // a continuation scales on every pass (drt1d.py:1320)
                 }
                 C::roww()[r] = w;
             }
@@ -1686,7 +1687,7 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
-    const bool ext = p.hyp.has_outlier_p || p.hyp.solve_rp || p.hyp.update_scale || p.n_pfrt > 0;
+    const bool ext = p.hyp.has_outlier_p || p.hyp.solve_rp || p.hyp.update_scale || p.n_pfrt > 0 || p.weight_factor_vec;
     if (small_cfg(p.n_cols)) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
     return ext ? launch_qphb<CfgLX>(h, p, (size_t)smem, st) : launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }

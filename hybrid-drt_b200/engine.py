@@ -57,7 +57,7 @@ class Problem(C.Structure):
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
         ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P), ('scale_factors', _P),
         ('n_pfrt', C.c_int), ('pfrt_max_iter', C.c_int), ('pfrt_min_iter', C.c_int), ('pfrt_factors', _P),
-        ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('vz_scratch', _P),
+        ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('weight_factor_vec', _P), ('vz_scratch', _P),
     ]
 
 
@@ -307,7 +307,8 @@ class Engine:
 
     def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
                        dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
-                       hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False, pfrt=None):
+                       hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False, pfrt=None,
+                       weight_factor_vec=None):
         """Launch the batched QPHB solver.  All inputs are device float64 tensors.
 
         rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
@@ -370,6 +371,9 @@ class Engine:
             p.resid_ss = _ptr(buf('resid_ss', b, 2))
         if hyp.has_outlier_p:
             p.outlier_t = _ptr(buf('outlier_t', b, n_rows))
+        if weight_factor_vec is not None:
+            assert weight_factor_vec.is_cuda and weight_factor_vec.dtype == torch.float64 and weight_factor_vec.numel() == n_rows
+            p.weight_factor_vec = _ptr(weight_factor_vec)
         if hyp.solve_rp or hyp.update_scale:
             p.scale_factors = _ptr(buf('scale_factors', b, 3))
         if pfrt is not None:           # dict(factors=..., max_iter_per_step=10, min_iter=2, want_p=False)

@@ -722,7 +722,7 @@ class DRT:
         if hyp['iw_alpha'] is not None:
             ch.has_iw_prior, ch.iw_alpha, ch.iw_beta = 1, float(hyp['iw_alpha']), float(hyp['iw_beta'])
         ch.xtol, ch.max_iter = float(kw['xtol']), int(kw['max_iter'])
-        ch.weight_factor = float(kw['weight_factor'])
+        ch.weight_factor = float(kw['weight_factor']) if np.isscalar(kw['weight_factor']) else 1.0
         ch.chrono_weight_factor = float(kw['chrono_weight_factor'])
         ch.eis_weight_factor = float(kw['eis_weight_factor'])
         if kw.get('solve_rp') or kw.get('update_scale'):          # drt1d.py:573-607, :914-936
@@ -771,8 +771,7 @@ class DRT:
                            (subtract_background, 'subtract_background'),
                            (remove_extremes, 'remove_extremes'),
                            (init_weights_separately, 'init_weights_separately'),
-                           (discard_first_n is not None, 'discard_first_n'), (peak_locations is not None,
-                                                                            'peak_locations'),
+                           (peak_locations is not None, 'peak_locations'),
                            (hybrid_weight_factor_method is not None, 'hybrid_weight_factor_method')):
             if flag:
                 _not_supported(f'{name}')
@@ -825,6 +824,19 @@ class DRT:
                 raise ValueError('v_signal must have shape [batch, len(times)]')
         batch = len(z_batch) if z_batch is not None else len(v_batch)
 
+        if discard_first_n is not None and times is not None:
+            # drt1d.py:170-181 + pp.discard_first_n_chrono (preprocessing.py:473-504): drop the first n samples of
+            # every segment (the pre-step one included) and move the assumed step time back accordingly
+            times = np.asarray(times, dtype=float)
+            i_signal = np.asarray(i_signal, dtype=float)
+            dt_short = np.min(np.diff(times))
+            starts = np.insert(identify_steps(i_signal, False), 0, 0)
+            ends = np.append(starts[1:], len(times))
+            keep = np.concatenate([np.arange(a + discard_first_n, b) for a, b in zip(starts, ends)])
+            times, i_signal, v_batch = times[keep], i_signal[keep], v_batch[:, keep]
+            if step_offset_size is None:
+                step_offset_size = -(dt_short + np.min(np.diff(times)) * (discard_first_n - 1e-8))
+                opts['step_offset_size'] = step_offset_size
         self.sample_index = None if times is None else np.arange(len(times))
         if downsample and times is not None:
             # DRTBase.process_chrono_signals (drtbase.py:296-339): step data come from the raw signal, then the
@@ -884,6 +896,12 @@ class DRT:
         copied = torch.cuda.Event()
         copied.record()
         dop_range = self.dop_indices if self.fit_dop else None
+        wf_vec = None
+        if not np.isscalar(weight_factor):          # per-row factors (kk_fit, drt1d.py:1394-1405)
+            wfa = np.asarray(weight_factor, dtype=float)
+            if wfa.shape != (plan['n_rows'],):
+                raise ValueError(f"weight_factor must be a scalar or have one entry per data row ({plan['n_rows']})")
+            wf_vec = eng.dev(wfa)
         vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
         vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
         raw = eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
@@ -891,7 +909,7 @@ class DRT:
                                  vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
                                  hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
                                  want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
-                                 want_resid=diag_tau is not None, pfrt=pfrt)
+                                 want_resid=diag_tau is not None, pfrt=pfrt, weight_factor_vec=wf_vec)
         plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         if nf:
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
@@ -983,6 +1001,7 @@ class DRT:
         v_b = None if v_signal is None else np.asarray(v_signal, dtype=float)[None, :]
         z_b = None if z is None else np.asarray(z)[None, :]
         res = self._fit_core_batch(times, i_signal, v_b, frequencies, z_b, want_pq=True, **kw)
+        self.z_fit = None if z is None else np.asarray(z).copy()
         self._store_single(res)
 
     def _outlier_index(self, times, i_signal, v_signal, frequencies, z, outlier_thresh, kw):
@@ -1108,6 +1127,96 @@ class DRT:
         self._pfrt_fit_core(times, i_signal, v_signal, frequencies, z, factors=factors,
                             max_iter_per_step=max_iter_per_step, max_init_iter=max_init_iter, xtol=xtol,
                             nonneg=nonneg, **kw)
+
+    # ------------------------------------------------------------------------------------------------
+    # Kramers-Kronig test (drt1d.py:1370-1491, models/kk.py): a lightly regularised free-sign DRT fit on an
+    # extended basis; points the fit cannot follow are flagged and the clean frequency window is returned
+    # ------------------------------------------------------------------------------------------------
+    def kk_fit(self, frequencies, z, nonneg=False, l2_lambda_0=1e-2, extend_basis_decades=2, outlier_index=None):
+        keep = self.extend_basis_decades
+        self.extend_basis_decades = extend_basis_decades
+        try:
+            weight_factor = 1
+            if outlier_index is not None:           # zero weight, but the points stay in the residuals
+                nf = len(frequencies)
+                weight_factor = np.ones(2 * nf)
+                weight_factor[np.asarray(outlier_index, dtype=int)] = 1e-10
+                weight_factor[np.asarray(outlier_index, dtype=int) + nf] = 1e-10
+            self.fit_eis(frequencies, z, nonneg=nonneg, l2_lambda_0=l2_lambda_0, weight_factor=weight_factor)
+        finally:
+            self.extend_basis_decades = keep
+
+    def eval_kk_residuals(self, norm='modulus'):
+        """kk.normalize_residuals (models/kk.py:9-19) of the last fit, in % of |Z| by default."""
+        f_fit = np.asarray(self.f_fit)
+        z_err = self.z_fit - self.predict_z(f_fit)
+        return 100 * z_err / np.abs(self.z_fit) if norm == 'modulus' else z_err / norm
+
+    def get_kk_outliers(self, norm='modulus', n_iter=2, p_thresh=1e-4, n_sigma=None, std_sample_fraction=0.6):
+        """kk.get_outliers (models/kk.py:21-53): the squared error modulus against a chi-squared law whose scale
+        comes from a robust (inter-quantile) standard deviation, re-estimated without the flagged points."""
+        from scipy.stats import chi2, norm as _norm
+        err = self.eval_kk_residuals(norm=norm)
+        mask = np.zeros(len(err), dtype=bool)
+        s_interp = np.linspace(0, 14, 2000)                    # stats.std_normal_quantile, utils/stats.py:108-116
+        n_std = float(np.interp(std_sample_fraction / 2 + 0.5, _norm.cdf(s_interp), s_interp))
+        for _ in range(n_iter):
+            e = np.concatenate([err[~mask].real, err[~mask].imag])
+            q_lo = np.percentile(e, 50 - 100 * std_sample_fraction / 2)
+            q_hi = np.percentile(e, 50 + 100 * std_sample_fraction / 2)
+            std = (q_hi - q_lo) / (2 * n_std)                  # stats.robust_std, utils/stats.py:124-134
+            if n_sigma is None:
+                mask = (1 - chi2.cdf(np.abs(err) ** 2, 2, loc=0, scale=std ** 2)) < p_thresh
+            else:
+                mask = np.abs(err) > std * n_sigma
+        return np.where(mask)[0]
+
+    def get_kk_limits(self, outlier_index, max_num_outliers=2):
+        """kk.get_limits (models/kk.py:56-123): the widest frequency window whose ends are clean points with a clean
+        neighbour and that holds at most ``max_num_outliers`` flagged points."""
+        f_fit = np.asarray(self.f_fit, dtype=float)
+        order = np.argsort(f_fit)[::-1]
+        f_sorted = f_fit[order]
+        pos = {int(i): k for k, i in enumerate(order)}
+        is_out = np.zeros(len(f_fit))
+        is_out[[pos[int(i)] for i in outlier_index]] = 1
+        padded = np.concatenate(([is_out[0]], is_out, [is_out[-1]]))       # uniform_filter1d, size 3, 'reflect'
+        badness = (padded[:-2] + padded[1:-1] + padded[2:]) / 3
+        clean = np.where(badness == 0)[0]
+        i_left, i_right = clean[0], clean[-1]
+        n_bad = np.sum(is_out[i_left:i_right])
+        if n_bad > max_num_outliers:
+            need = n_bad - max_num_outliers
+            from_left = np.cumsum(is_out[i_left:i_right + 1])
+            from_right = np.cumsum(is_out[i_left:i_right + 1][::-1])
+            ll, rr = np.meshgrid(from_left, from_right)
+            index = np.argwhere(ll + rr >= need)
+            r, l = index[np.argmin(np.sum(index, axis=1))]
+            i_left, i_right = i_left + l, i_right - r
+        if is_out[i_left] == 1:
+            i_left = np.min(clean[clean >= i_left])
+        if is_out[i_right] == 1:
+            i_right = np.max(clean[clean <= i_right])
+        return f_sorted[i_right], f_sorted[i_left]
+
+    def kk_test(self, frequencies, z, nonneg=False, l2_lambda_0=1e-2, extend_basis_decades=2, norm='modulus',
+                max_num_outliers=2, p_thresh=1e-4, n_sigma=None, std_sample_fraction=0.6, n_iter=2,
+                n_outlier_iter=2, show_plot=False):
+        """drt1d.py:1370-1390.  Returns (outlier_index, (f_min, f_max), (frequencies, z) inside the limits).
+        Plotting is not part of this package: show_plot is accepted for signature compatibility only."""
+        frequencies, z = np.asarray(frequencies, dtype=float), np.asarray(z)
+        outlier_index = None
+        for _ in range(n_iter):
+            self.kk_fit(frequencies, z, nonneg=nonneg, l2_lambda_0=l2_lambda_0,
+                        extend_basis_decades=extend_basis_decades, outlier_index=outlier_index)
+            outlier_index = self.get_kk_outliers(norm=norm, p_thresh=p_thresh, n_iter=n_outlier_iter, n_sigma=n_sigma,
+                                                 std_sample_fraction=std_sample_fraction)
+            f_min, f_max = self.get_kk_limits(outlier_index, max_num_outliers=max_num_outliers)
+            sel = (frequencies <= f_max) & (frequencies >= f_min)
+            fz_clean = (frequencies[sel], z[sel])
+        if show_plot and self.warn:
+            warnings.warn('kk_test: plotting is outside hybdrt_b200; show_plot is ignored')
+        return outlier_index, (f_min, f_max), fz_clean
 
     def _store_single(self, res):
         """Populate the attributes DRT._qphb_fit_core leaves behind (drt1d.py:1040-1104)."""

@@ -219,6 +219,8 @@ typedef struct hdrt_qphb_problem {
                                                           from x alone: the data terms of step_llh (qphb.py:1359)  */
     double* pfrt_p;             /* [batch][n_pfrt][n][n]  step_p_mat (optional)                                    */
     int* pfrt_iters;            /* [batch][n_pfrt]        outer iterations per step (optional)                     */
+    const double* weight_factor_vec; /* [N] per-row weight factor, shared by the batch (kk_fit down-weights outliers this
+                                        way, drt1d.py:1394-1405); NULL = the scalar hyp.weight_factor                  */
     double* vz_scratch;         /* [batch][N] work buffer: the vz_offset column a continuation step starts from
                                                           (drt1d.py:1296-1302); required iff n_pfrt > 1 and
                                                           vz_index >= 0                                            */

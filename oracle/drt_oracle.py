@@ -698,11 +698,11 @@ class EisPrep:
 
     def __init__(self, freq, mode='interp', tables=None, nonneg=True, ppd=10,
                  inductance_scale=1e-5, special_penalty=1e-6, vmm_eps=0.25, reim_cor=0.25,
-                 error_structure=None):
+                 error_structure=None, extend_basis_decades=1):
         self.freq = np.asarray(freq, dtype=float)
         self.eps = 1 / np.log(10 ** (1 / ppd))                                   # preprocessing.py:1016
         self.tables = tables if (tables is not None or mode != 'interp') else lookup_tables(self.eps)
-        self.tau = basis_tau_for(self.freq, ppd=ppd)
+        self.tau = basis_tau_for(self.freq, ppd=ppd, extend=extend_basis_decades)
         nb, nf = self.tau.size, self.freq.size
         a_re = impedance_matrix(self.freq, self.tau, self.eps, 'real', mode, self.tables)
         a_im = impedance_matrix(self.freq, self.tau, self.eps, 'imag', mode, self.tables)

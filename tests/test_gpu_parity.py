@@ -386,6 +386,14 @@ def test_flexible_chrono_error_structure(eng, orc):
     assert rel_err(drt.cvx_result['x'], g['tut_cvx_x']) < FIT_TOL
     assert rel_err(drt.qphb_params['outlier_t'], g['tut_outlier_t']) < FIT_TOL
     assert rel_err(drt.predict_z(g['freq']), g['tut_z_pred']) < FIT_TOL
+    # the hybrid tutorial's exact call: discard_first_n too (drt1d.py:170-181)
+    drt.fit_hybrid(g['times'], g['i_signal'], g['tut_v_signal'], g['freq'], g['z'][0], discard_first_n=1,
+                   chrono_error_structure=None, chrono_vmm_epsilon=4, outlier_p=0.01)
+    assert np.array_equal(drt.t_fit, g['tut2_t_fit']) and rel_err(drt.step_times, g['tut2_step_times']) < 1e-12
+    assert drt.qphb_params['n_outer'] == int(g['tut2_n_outer']) and drt.qphb_params['n_ipm'] == int(g['tut2_ipm'])
+    assert rel_err(drt.cvx_result['x'], g['tut2_cvx_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['freq']), g['tut2_z_pred']) < FIT_TOL
+    assert rel_err(drt.predict_response(), g['tut2_v_pred']) < FIT_TOL
     with pytest.raises(ValueError):
         drt.fit_chrono(g['times'], g['i_signal'], g['v_signal'][1], error_structure='nonsense')
 
@@ -564,6 +572,37 @@ def test_predictions_away_from_the_fit_grids():
     res = DRT().fit_eis_batch(freq, z)
     assert rel_err(res.predict_z(g['f_new']), g['b_z_new']) < FIT_TOL
     assert rel_err(res.predict_drt(g['tau']), g['b_drt0']) < FIT_TOL
+
+
+def test_kramers_kronig_test(eng, orc, lookup_golden):
+    """DRT.kk_test (drt1d.py:1370-1491, models/kk.py): per-row weight factors in the fit kernel, residual
+    statistics and window selection on the host, against the unmodified reference."""
+    from hybdrt_b200.models import DRT
+    g = load_golden('kk.npz')
+    drt = DRT()
+    for b in range(2):
+        out_idx, (f_min, f_max), (fc, zc) = drt.kk_test(g['freq'], g['z'][b])
+        assert np.array_equal(np.asarray(out_idx), g[f'outlier_index_{b}'])
+        assert f_min == g[f'limits_{b}'][0] and f_max == g[f'limits_{b}'][1] and len(fc) == int(g[f'n_clean_{b}'])
+        assert rel_err(drt.basis_tau, g[f'basis_tau_{b}']) < 1e-13
+        # the fit is deliberately under-regularised (l2_lambda_0 = 1e-2, free sign): its coefficients are huge
+        # cancelling numbers that no two implementations share, its prediction is what the test uses
+        # (nor, exactly, its prediction: 50 non-converged passes amplify rounding differences to ~1e-4, and the
+        # numpy oracle is no closer to the reference than the kernel is); the decisions above are exact
+        z_ref = g['z'][b] - g[f'resid_{b}'] * np.abs(g['z'][b]) / 100
+        assert rel_err(drt.predict_z(g['freq']), z_ref) < 1e-3
+    assert drt.extend_basis_decades == 1
+    with pytest.raises(ValueError):
+        drt.fit_eis(g['freq'], g['z'][0], weight_factor=np.ones(5))
+    # the per-row weight factor on a well-posed fit: kernel against the oracle, at the usual tolerance
+    prep = orc.EisPrep(g['freq'], tables=lookup_golden)
+    wf = np.random.default_rng(2).uniform(0.5, 1.5, 2 * len(g['freq']))
+    wf[[30, 100]] = 1e-10
+    prob, _ = prep.problem(g['z'][1])
+    out = _eis_launch(eng, prep, prob['rv'][None], weight_factor_vec=eng.dev(wf))
+    ref = prep.fit(g['z'][1], weight_factor=wf)
+    assert int(out['n_outer'][0]) == ref['n_outer'] and int(out['n_ipm'][0]) == int(ref['ipm_iters'].sum())
+    assert rel_err(out['x'][0], ref['x']) < FIT_TOL and rel_err(out['weights'][0], ref['weights'] / wf) < FIT_TOL
 
 
 def test_unsupported_options_raise():
