@@ -190,6 +190,37 @@ def test_batch_invariances(eng, orc, lookup_golden):
     assert np.all(full['n_outer'] >= 1) and np.all(full['n_outer'] <= 50)
 
 
+def test_problem_size_edges(eng, orc, lookup_golden):
+    """Shapes around the kernel's internal boundaries: a handful of columns (one or two 8 x 8 tiles), the last size of
+    the small configuration (n = 104) and the first of the large one (n = 105), the largest supported n (160), few
+    and many data rows -- each against the oracle."""
+    from hybdrt_b200 import synth
+    cases = [np.logspace(3.0, 2.2, 3),           # n = 32 (four tiles), N = 6: fewer rows than columns
+             np.logspace(4.0, 3.0, 41),          # n = 34 (one column into the fifth tile), N = 82
+             np.logspace(6.0, -2.05, 70),        # n = 104: last CfgS size
+             np.logspace(6.0, -2.15, 70),        # n = 105: first CfgL size
+             np.logspace(7.0, -6.65, 400)]       # n = 160: the largest, N = 800
+    for k, freq in enumerate(cases):
+        _, z = synth.make_eis_batch(2, freq=freq, seed=20 + k)
+        prep = orc.EisPrep(freq, tables=lookup_golden)
+        n = prep.rm.shape[1]
+        assert n == (32, 34, 104, 105, 160)[k]
+        rvs = np.array([prep.problem(zz)[0]['rv'] for zz in z])
+        out = _eis_launch(eng, prep, rvs, want_pq=True)
+        for b in range(2):
+            ref = prep.fit(z[b])
+            assert int(out['n_outer'][b]) == ref['n_outer'], (k, b)
+            assert int(out['n_ipm'][b]) == int(ref['ipm_iters'].sum()), (k, b)
+            assert rel_err(out['x'][b], ref['x']) < FIT_TOL, (k, b)
+            assert rel_err(out['weights'][b], ref['weights']) < FIT_TOL, (k, b)
+            assert rel_err(out['p_matrix'][b], ref['p_matrix']) < FIT_TOL, (k, b)
+    with pytest.raises(Exception):               # n = 161 does not fit
+        freq = np.logspace(7.0, -6.75, 50)
+        prep = orc.EisPrep(freq, tables=lookup_golden)
+        assert prep.rm.shape[1] > 160
+        _eis_launch(eng, prep, np.zeros((1, 2 * len(freq))))
+
+
 def test_empty_batch_and_bad_arguments(eng, orc, lookup_golden):
     from hybdrt_b200 import engine as E
     c1 = load_golden('c1_golden.npz')
