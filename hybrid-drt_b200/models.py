@@ -329,6 +329,15 @@ class BatchFit:
         """DRT.predict_z at the fit frequencies (drt1d.py:3500-3542) for the whole batch."""
         pl = self.plan
         fp = self.fit_parameters()
+        if pl.get('multi'):
+            if frequencies is not None:
+                _not_supported('predict_z at new frequencies for a fit with per-spectrum frequency grids')
+            dev = pl['model'].engine.dev
+            xd = dev(fp['x'])
+            z = torch.complex(torch.einsum('bfm,bm->bf', pl['a_re'], xd), torch.einsum('bfm,bm->bf', pl['a_im'], xd))
+            f = pl['frequencies']
+            return (z.cpu().numpy() + fp['R_inf'][:, None] + fp['inductance'][:, None] * 2j * np.pi * f
+                    + fp['C_inv'][:, None] * (2j * np.pi * f) ** -1)
         same = frequencies is None or (pl['frequencies'] is not None and np.array_equal(frequencies, pl['frequencies']))
         if same:
             f, zm, zd = pl['frequencies'], pl['zm_drt_host'], pl.get('zm_dop_host')
@@ -377,6 +386,7 @@ class DRT:
         self.tau_basis_type, self.nu_basis_type = tau_basis_type, nu_basis_type
         self.tau_epsilon = tau_epsilon
         self.extend_basis_decades = extend_basis_decades
+        self.basis_tau_ppd = basis_tau_ppd
         self.step_model, self.chrono_mode = step_model, chrono_mode
         self.fixed_basis_nu = fixed_basis_nu
         self.nu_epsilon = nu_epsilon
@@ -705,6 +715,78 @@ class DRT:
             plan['vz_strength'] = dev(plan['vz_strength_host'])
         return plan
 
+    def _build_plan_multi_eis(self, freqs, kw):
+        """fit_eis_batch with one frequency grid PER SPECTRUM (freqs [B, Nf], e.g. instruments that log slightly
+        different frequencies per sweep): every matrix of every spectrum is built on the GPU in one launch per
+        kind (hdrt_build_* with n_grids = B) and the fit kernel reads them per spectrum (non-zero strides).  All
+        spectra must lead to the same basis size; DOP and tau_supergrid are not available in this mode."""
+        if self.fit_dop or self.tau_supergrid is not None or self.fixed_basis_tau is not None:
+            _not_supported('per-spectrum frequency grids together with fit_dop / tau_supergrid / fixed_basis_tau')
+        eng, dev, hyp = self.engine, self.engine.dev, kw['hypers']
+        freqs = np.asarray(freqs, dtype=float)
+        nbat, nf = freqs.shape
+        sp = {}
+        if self.fit_ohmic:
+            self._add_special_qp_param(sp, 'R_inf', True)
+        if self.fit_inductance:
+            self._add_special_qp_param(sp, 'inductance', True)
+        if self.fit_capacitance:
+            self._add_special_qp_param(sp, 'C_inv', True)
+        self.special_qp_params, self.basis_nu = sp, None
+        ns = self.get_qp_mat_offset()
+        # preprocessing.get_tau_lim + get_basis_tau (preprocessing.py:948-1013), vectorised over the spectra
+        ext, ppd = self.extend_basis_decades, self.basis_tau_ppd
+        lmin = np.log10(1 / (2 * np.pi * freqs.max(axis=1))) - ext
+        lmax = np.log10(1 / (2 * np.pi * freqs.min(axis=1))) + ext
+        exact = (lmax - lmin) * ppd + 1
+        num = np.ceil(exact).astype(int)
+        if np.any(num != num[0]):
+            raise ValueError('per-spectrum frequency grids must lead to basis grids of one size; '
+                             f'got sizes {sorted(set(num.tolist()))}: fit the groups separately')
+        nb = int(num[0])
+        add = 0.5 * (num - exact) / ppd
+        taus = 10 ** ((lmin - add)[:, None] + ((lmax + add) - (lmin - add))[:, None] * np.linspace(0, 1, nb)[None, :])
+        if self.tau_epsilon is None:
+            self.tau_epsilon = 1 / np.log(10 ** (1 / ppd))
+        eps, n, n_rows = self.tau_epsilon, ns + nb, 2 * nf
+        self.basis_tau, self.f_fit, self.t_fit = taus, freqs, []
+        a_re, a_im = eng.build_impedance(freqs, taus, eps, self._mode(), self.interpolate_lookups)
+        rm = torch.zeros(nbat, n_rows, n, dtype=torch.float64, device=eng.device)
+        rm[:, :nf, ns:], rm[:, nf:, ns:] = a_re, a_im
+        omega = dev(2 * np.pi * freqs)
+        if 'R_inf' in sp:
+            rm[:, :nf, sp['R_inf']['index']] = 1.0
+        if 'inductance' in sp:
+            rm[:, nf:, sp['inductance']['index']] = omega * kw['inductance_scale']
+        if 'C_inv' in sp:
+            rm[:, nf:, sp['C_inv']['index']] = -1.0 / omega * kw['capacitance_scale']
+        pen = torch.zeros(nbat, 3, n, n, dtype=torch.float64, device=eng.device)
+        pen[:, :, ns:, ns:] = eng.build_penalty(np.log(taus), eps, True)      # log-uniform by construction
+        for name, val in (('R_inf', kw['ohmic_penalty']), ('inductance', kw['inductance_penalty']),
+                          ('C_inv', kw['capacitance_penalty'])):
+            if name in sp:
+                pen[:, :, sp[name]['index'], sp[name]['index']] = val
+        es = kw['eis_error_structure']
+        if es not in (None, 'uniform'):
+            raise ValueError(f'Invalid error structure {es}')
+        h = np.zeros(n)
+        if not kw['nonneg']:
+            if kw['neg_allowed_tau_range'] is not None:
+                _not_supported('neg_allowed_tau_range with per-spectrum frequency grids')
+            h[:] = 1e5
+            for v in sp.values():
+                if v['nonneg']:
+                    h[v['index']:v['index'] + v.get('size', 1)] = 0
+        l1 = np.zeros(n)
+        l1[ns:] = hyp['l1_lambda_0']
+        self.inductance_scale, self.capacitance_scale = kw['inductance_scale'], kw['capacitance_scale']
+        return dict(data_type='eis', special_qp_params=sp, n_special=ns, n=n, n_rows=n_rows, n_chrono=0, n_freq=nf,
+                    frequencies=freqs, times=None, basis_tau=taus, inductance_scale=kw['inductance_scale'],
+                    capacitance_scale=kw['capacitance_scale'], weight_factor=kw['weight_factor'], hypers=hyp,
+                    step_times=None, rm=rm, pen=pen, a_re=a_re, a_im=a_im, multi=True, vmm_chrono=None,
+                    vmm_eis=eng.build_eis_vmm(freqs, kw['eis_vmm_epsilon'], kw['eis_reim_cor'], es == 'uniform'),
+                    h_host=h, l1_host=l1, h=dev(h), l1=dev(l1))
+
     def _c_hypers(self, kw):
         hyp = kw['hypers']
         ch = _engine.default_hypers()
@@ -814,10 +896,13 @@ class DRT:
         if solve_rp and not scale_data and self.warn:
             warnings.warn('solve_rp is ignored if scale_data=False')
         self.v_baseline_deg, self.v_baseline_sqrt = v_baseline_deg, v_baseline_sqrt
+        multi = frequencies is not None and np.ndim(frequencies) == 2
         if z_batch is not None:
             z_batch = np.asarray(z_batch)
-            if z_batch.ndim != 2 or z_batch.shape[1] != len(frequencies):
+            if z_batch.ndim != 2 or z_batch.shape[1] != np.shape(frequencies)[-1]:
                 raise ValueError('z must have shape [batch, len(frequencies)]')
+            if multi and (times is not None or np.shape(frequencies)[0] != len(z_batch)):
+                raise ValueError('per-spectrum frequencies must have shape [batch, Nf] (EIS fits only)')
         if v_batch is not None:
             v_batch = np.asarray(v_batch, dtype=float)
             if v_batch.ndim != 2 or v_batch.shape[1] != len(times):
@@ -859,7 +944,7 @@ class DRT:
                 engine=self.engine, **dkw)
             opts['step_times'], opts['step_sizes'] = step_times, np.asarray(step_sizes, dtype=float)
 
-        plan = self._build_plan(times, i_signal, frequencies, opts)
+        plan = self._build_plan_multi_eis(frequencies, opts) if multi else self._build_plan(times, i_signal, frequencies, opts)
         plan['opts'] = opts
         plan['model'] = self
         sp, nc, nf = plan['special_qp_params'], plan['n_chrono'], plan['n_freq']
@@ -911,7 +996,7 @@ class DRT:
                                  want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
                                  want_resid=diag_tau is not None, pfrt=pfrt, weight_factor_vec=wf_vec)
         plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
-        if nf:
+        if nf and not plan.get('multi'):
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
             if self.fit_dop:
                 plan['zm_dop_host'] = plan['zm_dop_dev'].cpu().numpy()

@@ -636,6 +636,42 @@ def test_kramers_kronig_test(eng, orc, lookup_golden):
     assert rel_err(out['x'][0], ref['x']) < FIT_TOL and rel_err(out['weights'][0], ref['weights'] / wf) < FIT_TOL
 
 
+def test_per_spectrum_frequency_grids(orc, lookup_golden):
+    """fit_eis_batch with one frequency grid per spectrum (ragged sweeps): all matrices of all spectra are built in
+    one launch per kind and read per spectrum by the fit kernel; each member must equal its own single-grid fit."""
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200 import synth
+    nb_ = 48
+    base, z0 = synth.make_eis_batch(nb_, seed=31)
+    freqs = base[None, :] * (1 + 2e-3 * np.arange(nb_)[:, None] / nb_) * (1 + 1e-4 * np.sin(np.arange(70)))[None, :]
+    p, _ = synth.zarc_params(nb_, seed=31)
+    z = synth.zarc_impedance(freqs[0], p) * 0
+    for b in range(nb_):                                        # spectra evaluated on their own grids
+        pb = {k: v[b:b + 1] for k, v in p.items()}
+        z[b] = synth.zarc_impedance(freqs[b], pb)[0]
+    z = z + (z0 - synth.zarc_impedance(base, p))                # the same noise realisation as the shared-grid batch
+    drt = DRT()
+    res = drt.fit_eis_batch(freqs, z)
+    h, fp = res.host(), res.fit_parameters()
+    assert res.plan['rm'].shape[:2] == (nb_, 140) and np.all((h['status'] & 3) != 0)
+    single = DRT()
+    for b in (0, 17, 47):
+        single.fit_eis(freqs[b], z[b])
+        assert rel_err(single.basis_tau, drt.basis_tau[b]) < 1e-13
+        assert single.qphb_params['n_outer'] == int(h['n_outer'][b])
+        assert rel_err(h['x'][b], single.cvx_result['x']) < 1e-10
+        assert rel_err(res.predict_z()[b], single.predict_z(freqs[b])) < 1e-10
+        assert rel_err(fp['x'][b], single.fit_parameters['x']) < 1e-10
+    ref = orc.EisPrep(freqs[5], tables=lookup_golden).fit(z[5])
+    assert int(h['n_outer'][5]) == ref['n_outer'] and rel_err(h['x'][5], ref['x']) < FIT_TOL
+    with pytest.raises(ValueError):                             # grids that need basis grids of different sizes
+        bad = freqs.copy()
+        bad[3] = np.logspace(6, -3, 70)
+        drt.fit_eis_batch(bad, z)
+    with pytest.raises(ValueError):
+        drt.fit_eis_batch(freqs[:5], z)
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')

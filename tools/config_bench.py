@@ -15,7 +15,7 @@ from hybdrt_b200 import synth  # noqa: E402
 from hybdrt_b200.models import DRT  # noqa: E402
 from hybdrt_b200.mapping import DRTMD  # noqa: E402
 
-which = [a for a in sys.argv[1:] if a in ('c3', 'c4', 'c5')] or ['c3', 'c4', 'c5']
+which = [a for a in sys.argv[1:] if a in ('c2r', 'c3', 'c4', 'c5')] or ['c2r', 'c3', 'c4', 'c5']
 out = {}
 
 
@@ -29,6 +29,16 @@ def timed(fn, reps=2):
     return (time.perf_counter() - t0) / reps, r
 
 
+if 'c2r' in which:
+    B = 10000
+    freq, z = synth.make_eis_batch(B, seed=0)
+    freqs = freq[None, :] * (1 + 1e-3 * np.arange(B)[:, None] / B)      # every spectrum on its own grid
+    drt = DRT()
+    dt, res = timed(lambda: drt.fit_eis_batch(freqs, z).fit_parameters() and drt.last_batch)
+    h = res.host(['status', 'n_outer', 'x'])
+    out['C2 ragged (10000 spectra, one frequency grid each: matrices built and read per spectrum)'] = dict(
+        fits_per_s=B / dt, seconds=dt, mean_outer=float(h['n_outer'].mean()), finite=bool(np.isfinite(h['x']).all()),
+        n=res.plan['n'], matrix_bytes=int(res.plan['rm'].numel() + res.plan['pen'].numel() + res.plan['vmm_eis'].numel()) * 8)
 if 'c3' in which:
     B = 4096
     times, i_sig, v, freq, z = synth.make_hybrid_batch(B, seed=1)
