@@ -851,7 +851,8 @@ class DRT:
         # options outside the hot path (same keyword names as drt1d.py:102-137)
         for flag, name in ((series_neg, 'series_neg'),
                            (subtract_background, 'subtract_background'),
-                           (remove_extremes, 'remove_extremes'),
+                           (remove_extremes, 'remove_extremes in a batched call (the flagged points differ per '
+                                             'spectrum; use the single-spectrum fit_* methods)'),
                            (init_weights_separately, 'init_weights_separately'),
                            (peak_locations is not None, 'peak_locations'),
                            (hybrid_weight_factor_method is not None, 'hybrid_weight_factor_method')):
@@ -1057,6 +1058,32 @@ class DRT:
             times, i_signal, v_signal = np.array(times), np.array(i_signal), np.array(v_signal)
         if frequencies is not None:
             frequencies, z = np.array(frequencies), np.array(z)
+        if kw.pop('remove_extremes', False):                # drt1d.py:188-215, preprocessing.py:844-857
+            ekw = kw.pop('extreme_kw', None) or {'qr_size': 0.8, 'qr_thresh': 1.5}
+
+            def extreme(y):
+                q_lo = np.percentile(y, 50 - 100 * ekw['qr_size'] / 2)
+                q_hi = np.percentile(y, 50 + 100 * ekw['qr_size'] / 2)
+                qr = q_hi - q_lo
+                return (y < q_lo - qr * ekw['qr_thresh']) | (y > q_hi + qr * ekw['qr_thresh'])
+            if times is not None:
+                flag = extreme(i_signal) | extreme(v_signal)
+                if flag.any():
+                    if self.warn:
+                        warnings.warn('Identified extreme values in chrono data at the following '
+                                      f'indices: {np.where(flag)[0].tolist()}. '
+                                      'These data points will be removed before fitting')
+                    times, i_signal, v_signal = times[~flag], i_signal[~flag], v_signal[~flag]
+            if frequencies is not None:
+                flag = extreme(z.real) | extreme(z.imag)
+                if flag.any():
+                    if self.warn:
+                        warnings.warn('Identified extreme values in EIS data at the following '
+                                      f'indices: {np.where(flag)[0].tolist()}. '
+                                      'These data points will be removed before fitting')
+                    frequencies, z = frequencies[~flag], z[~flag]
+        else:
+            kw.pop('extreme_kw', None)
         self.eis_outlier_index = self.eis_outliers = None
         self.chrono_outlier_index = self.chrono_outliers = None
         if remove_outliers:

@@ -381,6 +381,10 @@ def test_outlier_error_structure_and_removal(eng, orc, lookup_golden):
         assert drt.qphb_params['n_outer'] == int(g['ro_n_outer'][b])
         assert rel_err(drt.fit_parameters['x'], g['ro_x'][b]) < FIT_TOL
         assert rel_err(drt.predict_z(g['freq']), g['ro_z_pred'][b]) < FIT_TOL
+    drt.fit_eis(g['freq'], g['ext_z'], remove_extremes=True)          # drt1d.py:188-215
+    assert np.array_equal(np.asarray(drt.f_fit), g['ext_f_fit']) and drt.qphb_params['n_outer'] == int(g['ext_n_outer'])
+    assert rel_err(drt.fit_parameters['x'], g['ext_x']) < FIT_TOL
+    assert rel_err(drt.predict_z(g['freq']), g['ext_z_pred']) < FIT_TOL
     with pytest.raises(ValueError):
         drt.fit_eis(g['freq'], g['z'][0], remove_outliers=True)
     with pytest.raises(E.EngineError):
