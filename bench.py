@@ -312,6 +312,14 @@ def run_gpu(args):
         filt_gbs = filt_bytes / (float(np.mean(fb)) * 1e-3) / 1e9
         del raw_dev
 
+        mat_traffic = filt_traffic = None
+        try:        # ncu captures of the two secondary kernels, scaled to these launches
+            bt = json.load(open(os.path.join(ROOT, 'profiles', 'builder_traffic.json')))
+            mi, fi = bt['impedance_interp_kernel'], bt['filter_gather_kernel']
+            mat_traffic = (mi['dram_bytes_read'] + mi['dram_bytes_write']) / mi['grids_in_profiled_launch'] * g
+            filt_traffic = (fi['dram_bytes_read'] + fi['dram_bytes_write']) / fi['traces_in_profiled_launch'] * n_tr
+        except Exception:
+            pass
         traffic = None
         prof = os.path.join(ROOT, 'profiles', 'qphb_traffic.json')
         if os.path.exists(prof):
@@ -351,12 +359,12 @@ def run_gpu(args):
                                         '(MEASURED_PEAKS.json has no FP64 entry)',
                          'flops_per_launch': flops},
             'roofline_matrix_build': {'bound': 'hbm', 'achieved': mat_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                                      'frac': mat_gbs / hbm_peak, 'traffic': None, 'kernel': 'impedance_interp_kernel',
+                                      'frac': mat_gbs / hbm_peak, 'traffic': mat_traffic, 'kernel': 'impedance_interp_kernel',
                                       'bytes_per_launch': mat_bytes,
                                       'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback',
                                       'workload': f'{g} per-spectrum (freq, tau) grids, A_re + A_im 70 x 101 each'},
             'roofline_chrono_filter': {'bound': 'hbm', 'achieved': filt_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                                       'frac': filt_gbs / hbm_peak, 'traffic': None, 'kernel': 'filter_gather_kernel',
+                                       'frac': filt_gbs / hbm_peak, 'traffic': filt_traffic, 'kernel': 'filter_gather_kernel',
                                        'bytes_per_launch': filt_bytes,
                                        'workload': f'{n_tr} raw traces x {len(rt)} samples -> {len(dec)} kept samples each '
                                                    f'(downsample_data, decimation_interval=8, factor 2)'},
