@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import engine as _engine
+from . import kk as _kk
 
 
 def _not_supported(what):
@@ -1259,57 +1260,17 @@ class DRT:
             self.extend_basis_decades = keep
 
     def eval_kk_residuals(self, norm='modulus'):
-        """kk.normalize_residuals (models/kk.py:9-19) of the last fit, in % of |Z| by default."""
-        f_fit = np.asarray(self.f_fit)
-        z_err = self.z_fit - self.predict_z(f_fit)
-        return 100 * z_err / np.abs(self.z_fit) if norm == 'modulus' else z_err / norm
+        """drt1d.py:1472-1481: residuals of the last fit, in % of |Z| by default."""
+        return _kk.normalize_residuals(self.z_fit, self.predict_z(np.asarray(self.f_fit)), norm=norm)
 
     def get_kk_outliers(self, norm='modulus', n_iter=2, p_thresh=1e-4, n_sigma=None, std_sample_fraction=0.6):
-        """kk.get_outliers (models/kk.py:21-53): the squared error modulus against a chi-squared law whose scale
-        comes from a robust (inter-quantile) standard deviation, re-estimated without the flagged points."""
-        from scipy.stats import chi2, norm as _norm
-        err = self.eval_kk_residuals(norm=norm)
-        mask = np.zeros(len(err), dtype=bool)
-        s_interp = np.linspace(0, 14, 2000)                    # stats.std_normal_quantile, utils/stats.py:108-116
-        n_std = float(np.interp(std_sample_fraction / 2 + 0.5, _norm.cdf(s_interp), s_interp))
-        for _ in range(n_iter):
-            e = np.concatenate([err[~mask].real, err[~mask].imag])
-            q_lo = np.percentile(e, 50 - 100 * std_sample_fraction / 2)
-            q_hi = np.percentile(e, 50 + 100 * std_sample_fraction / 2)
-            std = (q_hi - q_lo) / (2 * n_std)                  # stats.robust_std, utils/stats.py:124-134
-            if n_sigma is None:
-                mask = (1 - chi2.cdf(np.abs(err) ** 2, 2, loc=0, scale=std ** 2)) < p_thresh
-            else:
-                mask = np.abs(err) > std * n_sigma
-        return np.where(mask)[0]
+        """drt1d.py:1483-1486"""
+        return _kk.get_outliers(self.eval_kk_residuals(norm=norm), n_iter, p_thresh, n_sigma=n_sigma,
+                                std_sample_fraction=std_sample_fraction)
 
     def get_kk_limits(self, outlier_index, max_num_outliers=2):
-        """kk.get_limits (models/kk.py:56-123): the widest frequency window whose ends are clean points with a clean
-        neighbour and that holds at most ``max_num_outliers`` flagged points."""
-        f_fit = np.asarray(self.f_fit, dtype=float)
-        order = np.argsort(f_fit)[::-1]
-        f_sorted = f_fit[order]
-        pos = {int(i): k for k, i in enumerate(order)}
-        is_out = np.zeros(len(f_fit))
-        is_out[[pos[int(i)] for i in outlier_index]] = 1
-        padded = np.concatenate(([is_out[0]], is_out, [is_out[-1]]))       # uniform_filter1d, size 3, 'reflect'
-        badness = (padded[:-2] + padded[1:-1] + padded[2:]) / 3
-        clean = np.where(badness == 0)[0]
-        i_left, i_right = clean[0], clean[-1]
-        n_bad = np.sum(is_out[i_left:i_right])
-        if n_bad > max_num_outliers:
-            need = n_bad - max_num_outliers
-            from_left = np.cumsum(is_out[i_left:i_right + 1])
-            from_right = np.cumsum(is_out[i_left:i_right + 1][::-1])
-            ll, rr = np.meshgrid(from_left, from_right)
-            index = np.argwhere(ll + rr >= need)
-            r, l = index[np.argmin(np.sum(index, axis=1))]
-            i_left, i_right = i_left + l, i_right - r
-        if is_out[i_left] == 1:
-            i_left = np.min(clean[clean >= i_left])
-        if is_out[i_right] == 1:
-            i_right = np.max(clean[clean <= i_right])
-        return f_sorted[i_right], f_sorted[i_left]
+        """drt1d.py:1488-1491"""
+        return _kk.get_limits(np.asarray(self.f_fit), outlier_index, max_num_outliers=max_num_outliers)
 
     def kk_test(self, frequencies, z, nonneg=False, l2_lambda_0=1e-2, extend_basis_decades=2, norm='modulus',
                 max_num_outliers=2, p_thresh=1e-4, n_sigma=None, std_sample_fraction=0.6, n_iter=2,
@@ -1324,8 +1285,7 @@ class DRT:
             outlier_index = self.get_kk_outliers(norm=norm, p_thresh=p_thresh, n_iter=n_outlier_iter, n_sigma=n_sigma,
                                                  std_sample_fraction=std_sample_fraction)
             f_min, f_max = self.get_kk_limits(outlier_index, max_num_outliers=max_num_outliers)
-            sel = (frequencies <= f_max) & (frequencies >= f_min)
-            fz_clean = (frequencies[sel], z[sel])
+            fz_clean = _kk.trim_data(frequencies, z, f_min, f_max)
         if show_plot and self.warn:
             warnings.warn('kk_test: plotting is outside hybdrt_b200; show_plot is ignored')
         return outlier_index, (f_min, f_max), fz_clean

@@ -84,3 +84,22 @@ def test_synthetic_generators_are_seeded():
     f, z = synth.make_eis_batch(12, seed=0)
     c2 = load_golden('c2_eis.npz')
     assert np.array_equal(z, c2['z']) and np.array_equal(f, c2['freq'])
+
+
+def test_kk_statistics_match_reference_fixture():
+    """models/kk.py: outlier flags and frequency window from the residuals of the reference's own KK fits."""
+    from hybdrt_b200 import kk
+    g = load_golden('kk.npz')
+    for b in range(2):
+        out = kk.get_outliers(g[f'resid_{b}'])
+        assert np.array_equal(out, g[f'outlier_index_{b}'])
+        f_min, f_max = kk.get_limits(g['freq'], out)
+        assert f_min == g[f'limits_{b}'][0] and f_max == g[f'limits_{b}'][1]
+        assert len(kk.trim_data(g['freq'], g['z'][b], f_min, f_max)[0]) == int(g[f'n_clean_{b}'])
+    # hand-made cases for the window logic: a clean run is kept, a cluster at one end is cut off
+    f = np.logspace(5, 0, 21)
+    assert kk.get_limits(f, np.array([], dtype=int)) == (f[-1], f[0])
+    f_min, f_max = kk.get_limits(f, np.array([0, 1, 2, 10]), max_num_outliers=1)
+    assert f_max == f[4] and f_min == f[-1]        # the first clean point with clean neighbours
+    (f_min, f_max), (il, ir) = kk.get_limits(f, np.array([18, 19, 20]), return_index=True)
+    assert f_max == f[0] and f_min == f[16] and (il, ir) == (0, 16)
