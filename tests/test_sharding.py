@@ -45,13 +45,16 @@ def _worker(rank, ws, port, n, interleave, dst, q):
         idx = sharding.shard_indices(n, ws, rank, interleave)
         # every "fit result" is a function of the global index, so the gathered arrays are checkable
         local = {'x': np.stack([np.full(4, float(i)) for i in idx]) if len(idx) else np.zeros((0, 4)),
-                 'status': torch.as_tensor(idx.astype(np.int32) * 3)}
+                 'status': torch.as_tensor(idx.astype(np.int32) * 3),
+                 # per-factor results of a PFRT map ([B, F, n_tau]) travel through the same gather
+                 'pfrt_x': np.stack([np.full((3, 2), float(i)) for i in idx]) if len(idx) else np.zeros((0, 3, 2))}
         out = sharding.gather_results(local, n, interleave=interleave, dst=dst)
         if dst is None or rank == dst:
             ok = np.array_equal(out['x'], np.repeat(np.arange(n, dtype=float)[:, None], 4, 1)) and \
-                np.array_equal(out['status'], np.arange(n) * 3)
+                np.array_equal(out['status'], np.arange(n) * 3) and \
+                np.array_equal(out['pfrt_x'], np.broadcast_to(np.arange(n, dtype=float)[:, None, None], (n, 3, 2)))
         else:
-            ok = out['x'] is None and out['status'] is None
+            ok = out['x'] is None and out['status'] is None and out['pfrt_x'] is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
