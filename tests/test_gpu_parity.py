@@ -771,3 +771,58 @@ def test_full_size_c2_batch_properties():
         assert int(h['n_outer'][b]) == ref['n_outer']
         assert rel_err(h['x'][b], ref['x']) < FIT_TOL
         assert abs(fp['R_inf'][b] - ref['params']['R_inf']) < FIT_TOL * abs(ref['params']['R_inf'])
+
+
+def test_full_size_c3_c4_c5_properties():
+    """BASELINE configs C3 (4,096 hybrid fits, N = 2060), C4 (10,000 DRT + DOP fits, n = 153) and C5 (256 x 256 map
+    through DRTMD) at their full sizes: size-independent properties, and members of the big batches against the
+    same spectra fitted in small batches (bitwise: one code path, independent spectra)."""
+    from hybdrt_b200 import synth
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200.mapping import DRTMD
+    rng = np.random.default_rng(4)
+    # ---- C3
+    t, i_sig, v, f, z = synth.make_hybrid_batch(4096, seed=1)
+    drt = DRT()
+    res = drt.fit_hybrid_batch(t, i_sig, v, f, z)
+    h = res.host(['x', 'status', 'n_outer', 'weights'])
+    st = h['status']
+    assert res.plan['n_rows'] == 2060 and np.all((st & 3) != 0) and np.all((st & 3) != 3) and not np.any(st & (8 | 16))
+    assert np.all(np.isfinite(h['x'])) and np.all(h['weights'] > 0)
+    zp = res.predict_z()
+    rel = np.linalg.norm(zp - z, axis=1) / np.linalg.norm(z, axis=1)
+    assert np.median(rel) < 0.15 and rel.max() < 0.3         # (the reference's own fits of these spectra sit at ~8 %)
+    idx = rng.permutation(4096)[:6]
+    sub = drt.fit_hybrid_batch(t, i_sig, v[idx], f, z[idx]).host(['x', 'n_ipm'])
+    assert np.array_equal(sub['x'], h['x'][idx])
+    # ---- C4
+    f4, z4 = synth.make_dop_batch(10000, seed=2)
+    dd = DRT(fit_dop=True)
+    res = dd.fit_eis_batch(f4, z4)
+    h = res.host(['x', 'status', 'n_outer'])
+    st = h['status']
+    assert res.plan['n'] == 153 and np.all((st & 3) != 0) and not np.any(st & (8 | 16)) and np.all(np.isfinite(h['x']))
+    assert h['x'].min() > -1e-5                               # DRT and DOP coefficients are non-negative
+    rel = np.linalg.norm(res.predict_z() - z4, axis=1) / np.linalg.norm(z4, axis=1)
+    assert np.median(rel) < 3e-2
+    idx = rng.permutation(10000)[:6]
+    assert np.array_equal(dd.fit_eis_batch(f4, z4[idx]).host(['x'])['x'], h['x'][idx])
+    # ---- C5
+    rows = cols = 256
+    f5, z5 = synth.make_map_batch(rows, cols, seed=3)
+    psi = np.stack(np.meshgrid(np.arange(rows), np.arange(cols), indexing='ij'), axis=-1).reshape(-1, 2).astype(float)
+    md = DRTMD(tau_supergrid=np.logspace(-8, 3, 111), psi_dim_names=['row', 'col'], print_progress=False)
+    md.add_observations(psi, f5, z5)
+    md.fit_all()
+    assert md.obs_fit_status.all() and np.all(np.isfinite(md.obs_x)) and np.all(np.isfinite(md.obs_drt_var))
+    assert md.obs_x.min() > -1e-5 and np.all(md.obs_drt_var >= 0) and np.all(np.isfinite(md.obs_llh))
+    # the map varies smoothly: R_inf is constant (1.0) over the map up to noise, and neighbours have close Rp
+    assert abs(np.median(md.obs_special['R_inf']) - 1.0) < 0.02
+    rp = (md.obs_x * md.tau_basis_area).sum(axis=1).reshape(rows, cols)
+    assert np.median(np.abs(np.diff(rp, axis=0))) < 0.05 * np.median(rp)
+    md2 = DRTMD(tau_supergrid=np.logspace(-8, 3, 111), print_progress=False)
+    pick = rng.permutation(rows * cols)[:5]
+    md2.add_observations(psi[pick], f5, z5[pick])
+    md2.fit_all()
+    assert np.array_equal(md2.obs_x, md.obs_x[pick])
+
