@@ -1334,6 +1334,27 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     hd.use_gmat = true;
     hp.use_gmat = false;
 
+    // chrono / EIS weight factors of a hybrid fit (drt1d.py:745-800, applied at :882-884): the scalars of hyp, or one
+    // pair per spectrum from the host (hybrid_weight_factor_method='rp'), or computed from the initial weight scales
+    // after the initialisation ('weight')
+    double cwf = hy.chrono_weight_factor, ewf = hy.eis_weight_factor;
+    if (C::EXT && p.hybrid_wf_in) { cwf = p.hybrid_wf_in[2 * (size_t)b]; ewf = p.hybrid_wf_in[2 * (size_t)b + 1]; }
+    const bool separate = C::EXT && hy.init_weights_separately != 0 && c.nc > 0 && c.nc < N;
+    double var_floor_c = var_floor, var_floor_e = var_floor;
+    if (separate) {   // qphb.estimate_weights floors the variance at var(y) 1e-7 of the vector it is given (drt1d.py:647-669)
+        double t2[2] = {0.0, 0.0};
+        for (int r = tid; r < N; r += C::kThreads) { if (r < c.nc) t2[0] += c.rv[r]; else t2[1] += c.rv[r]; }
+        block_reduce<C, 2, 0u>(t2, c);
+        const double mc = t2[0] / (double)c.nc, me = t2[1] / (double)(N - c.nc);
+        double v2[2] = {0.0, 0.0};
+        for (int r = tid; r < N; r += C::kThreads) {
+            const double d = c.rv[r] - (r < c.nc ? mc : me);
+            if (r < c.nc) v2[0] += d * d; else v2[1] += d * d;
+        }
+        block_reduce<C, 2, 0u>(v2, c);
+        var_floor_c = v2[0] / (double)c.nc * 1e-7;
+        var_floor_e = v2[1] / (double)(N - c.nc) * 1e-7;
+    }
     int status = 0, n_ipm = 0;
     PROF_DECL;
     L2Factors f;
@@ -1352,7 +1373,8 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
     for (int k = 0; k < 3; ++k) hd.s_0[k] = hy.s_0[k] * fac;
     const int max_it = cont ? p.pfrt_max_iter : hy.max_iter;
     const bool solve_rp = C::EXT && hy.solve_rp != 0;
-    it = cont ? 0 : (solve_rp ? -3 : (outl ? -2 : -1));   // -3: estimate_x_rp (qphb.py:1684-1717); -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
+    it = cont ? 0 : (solve_rp ? -3 : (outl ? -2 : (separate ? -5 : -1)));   // -3: estimate_x_rp (qphb.py:1684-1717);
+                                        // -5 / -4: initialize_weights on the chrono rows, then on the EIS rows; -1: initialize_weights (drt1d.py:640-675, qphb.py:1609-1681); with outlier_p
                                         // the initialisation runs twice (-2, -1), the second time weighted by the
                                         // first estimate
     conv = false;
@@ -1385,6 +1407,10 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             __syncthreads();
         }
         const double x_in = xi;
+        if (C::EXT && (it == -5 || it == -4)) {   // one domain at a time: the other rows carry no weight
+            for (int r = tid; r < N; r += C::kThreads) C::roww()[r] = ((r < c.nc) == (it == -5)) ? 1.0 : 0.0;
+            __syncthreads();
+        }
         // weights entering the Gram: 1 (init) / weight factors (drt1d.py:881-892) / scaled weights (:991-1008)
         if (!init) {
             for (int r = tid; r < N; r += C::kThreads) {
@@ -1392,9 +1418,9 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                 const double wf = (C::EXT && p.weight_factor_vec) ? p.weight_factor_vec[r] : hy.weight_factor;
                 if (final_pq) {
                     w *= wf;
-                    if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
+                    if (p.hybrid) w *= (r < c.nc) ? cwf : ewf;
                 } else {
-                    if (p.hybrid) w *= (r < c.nc) ? hy.chrono_weight_factor : hy.eis_weight_factor;
+                    if (p.hybrid) w *= (r < c.nc) ? cwf : ewf;
                     if (it > 0 || cont) w = w * wf;   // a continuation scales on every pass (drt1d.py:1320)
                 }
                 C::roww()[r] = w;
@@ -1443,9 +1469,24 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             it = outl ? -2 : -1;
             continue;
         }
-        if (init) {
+        if (C::EXT && it == -5) {                 // chrono rows done: keep their estimate, go on to the EIS rows
             if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
-            weights_phase<C>(c, nullptr, var_floor, false, outl);
+            weights_phase<C>(c, nullptr, var_floor_c, false, false);
+            for (int r = tid; r < c.nc; r += C::kThreads) est_g[r] = C::roww()[r];
+            __syncthreads();
+            it = -4;
+            continue;
+        }
+        if (init) {
+            if (C::EXT && it == -4) {
+                if (tid < n && p.x_overfit_eis) p.x_overfit_eis[(size_t)b * n + tid] = qo.xi;
+                weights_phase<C>(c, nullptr, var_floor_e, false, false);
+                for (int r = tid; r < c.nc; r += C::kThreads) C::roww()[r] = est_g[r];
+                __syncthreads();
+            } else {
+                if (tid < n && p.x_overfit) p.x_overfit[(size_t)b * n + tid] = qo.xi;
+                weights_phase<C>(c, nullptr, var_floor, false, outl);
+            }
             PROF_ADD(4);
             if (it == -2) { it = -1; continue; }   // qphb.py:1634-1655: second pass with w = est_weights
             for (int r = tid; r < N; r += C::kThreads) {
@@ -1461,6 +1502,20 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
                 C::roww()[r] = wi;
             }
             __syncthreads();
+            if (C::EXT && p.hybrid && hy.hybrid_wf_method == 1 && !p.hybrid_wf_in) {
+                // hybrid_weight_factor_method='weight' (drt1d.py:749-759): balance the two domains by the fourth root of
+                // the ratio of their weight scales, mean(est_weights^-2)^-1/2
+                double t2[2] = {0.0, 0.0};
+                for (int r = tid; r < N; r += C::kThreads) {
+                    const double e = est_g[r];
+                    if (r < c.nc) t2[0] += 1.0 / (e * e); else t2[1] += 1.0 / (e * e);
+                }
+                block_reduce<C, 2, 0u>(t2, c);
+                const double cws = 1.0 / sqrt(t2[0] / (double)c.nc), ews = 1.0 / sqrt(t2[1] / (double)(N - c.nc));
+                const double ratio = sqrt(sqrt(ews / cws));
+                ewf = 1.0 / ratio;
+                cwf = ratio;
+            }
             it = 0;
             if (max_it <= 0) break;
             continue;
@@ -1556,6 +1611,7 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             if (p.dop_rho) p.dop_rho[(size_t)b * 3 + k] = dop_rho[k];
             if (p.dop_xmx_norms) p.dop_xmx_norms[(size_t)b * 3 + k] = dop_xmx[k];
         }
+        if (C::EXT && p.hybrid_wf_out) { p.hybrid_wf_out[2 * (size_t)b] = cwf; p.hybrid_wf_out[2 * (size_t)b + 1] = ewf; }
         if (C::EXT && p.scale_factors) {
             if (!hy.solve_rp) p.scale_factors[3 * (size_t)b] = 1.0;
             p.scale_factors[3 * (size_t)b + 1] = us_factor;
@@ -1687,7 +1743,12 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
     if (smem < 0) { set_error("problem %d x %d does not fit in shared memory", p.n_rows, p.n_cols); return HDRT_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
-    const bool ext = p.hyp.has_outlier_p || p.hyp.solve_rp || p.hyp.update_scale || p.n_pfrt > 0 || p.weight_factor_vec;
+    const bool ext = p.hyp.has_outlier_p || p.hyp.solve_rp || p.hyp.update_scale || p.n_pfrt > 0 || p.weight_factor_vec ||
+                     p.hyp.init_weights_separately || p.hyp.hybrid_wf_method || p.hybrid_wf_in;
+    if (p.hyp.init_weights_separately && (p.hyp.has_outlier_p || p.hyp.solve_rp)) {
+        set_error("init_weights_separately cannot be combined with outlier_p / solve_rp");
+        return HDRT_ERR_UNSUPPORTED;
+    }
     if (small_cfg(p.n_cols)) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
     return ext ? launch_qphb<CfgLX>(h, p, (size_t)smem, st) : launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }

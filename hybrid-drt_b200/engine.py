@@ -32,7 +32,8 @@ class Hypers(C.Structure):
         ('chrono_weight_factor', C.c_double), ('eis_weight_factor', C.c_double),
         ('has_iw_prior', C.c_int), ('max_iter', C.c_int),
         ('outlier_p', C.c_double), ('has_outlier_p', C.c_int), ('solve_rp', C.c_int),
-        ('update_scale', C.c_int), ('normalize_dop', C.c_int), ('rp_scale', C.c_double), ('basis_area', C.c_double),
+        ('update_scale', C.c_int), ('normalize_dop', C.c_int), ('init_weights_separately', C.c_int),
+        ('hybrid_wf_method', C.c_int), ('rp_scale', C.c_double), ('basis_area', C.c_double),
     ]
 
 
@@ -57,7 +58,8 @@ class Problem(C.Structure):
         ('n_outer', _P), ('n_ipm', _P), ('status', _P),
         ('eval_mat', _P), ('n_eval', C.c_int), ('dist_var', _P), ('resid_ss', _P), ('outlier_t', _P), ('scale_factors', _P),
         ('n_pfrt', C.c_int), ('pfrt_max_iter', C.c_int), ('pfrt_min_iter', C.c_int), ('pfrt_factors', _P),
-        ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('weight_factor_vec', _P), ('vz_scratch', _P),
+        ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('hybrid_wf_in', _P), ('hybrid_wf_out', _P), ('x_overfit_eis', _P),
+        ('weight_factor_vec', _P), ('vz_scratch', _P),
     ]
 
 
@@ -308,7 +310,7 @@ class Engine:
     def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
                        dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
                        hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False, pfrt=None,
-                       weight_factor_vec=None):
+                       weight_factor_vec=None, hybrid_wf=None):
         """Launch the batched QPHB solver.  All inputs are device float64 tensors.
 
         rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
@@ -371,6 +373,13 @@ class Engine:
             p.resid_ss = _ptr(buf('resid_ss', b, 2))
         if hyp.has_outlier_p:
             p.outlier_t = _ptr(buf('outlier_t', b, n_rows))
+        if hybrid and (hybrid_wf is not None or hyp.hybrid_wf_method or hyp.init_weights_separately):
+            p.hybrid_wf_out = _ptr(buf('hybrid_wf', b, 2))
+            if hybrid_wf is not None:          # per-spectrum chrono / EIS factors [B, 2]
+                assert hybrid_wf.is_cuda and hybrid_wf.dtype == torch.float64 and tuple(hybrid_wf.shape) == (b, 2)
+                p.hybrid_wf_in = _ptr(hybrid_wf.contiguous())
+            if hyp.init_weights_separately:
+                p.x_overfit_eis = _ptr(buf('x_overfit_eis', b, n))
         if weight_factor_vec is not None:
             assert weight_factor_vec.is_cuda and weight_factor_vec.dtype == torch.float64 and weight_factor_vec.numel() == n_rows
             p.weight_factor_vec = _ptr(weight_factor_vec)

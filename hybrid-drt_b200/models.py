@@ -813,6 +813,10 @@ class DRT:
             ch.normalize_dop = int(bool(self.fit_dop and self.normalize_dop))
             ch.rp_scale = float(hyp['rp_scale'])
             ch.basis_area = float(np.sqrt(np.pi) / self.tau_epsilon)
+        if kw.get('init_weights_separately'):
+            ch.init_weights_separately = 1
+        if kw.get('wf_method') == 'weight':
+            ch.hybrid_wf_method = 1
         if hyp.get('outlier_p') is not None:                     # qphb.py:232; error structure qphb.py:1497-1538
             ch.has_outlier_p, ch.outlier_p = 1, float(hyp['outlier_p'])
         return ch
@@ -854,9 +858,8 @@ class DRT:
                            (subtract_background, 'subtract_background'),
                            (remove_extremes, 'remove_extremes in a batched call (the flagged points differ per '
                                              'spectrum; use the single-spectrum fit_* methods)'),
-                           (init_weights_separately, 'init_weights_separately'),
                            (peak_locations is not None, 'peak_locations'),
-                           (hybrid_weight_factor_method is not None, 'hybrid_weight_factor_method')):
+                           ):
             if flag:
                 _not_supported(f'{name}')
         if penalty_type != 'integral':
@@ -878,8 +881,13 @@ class DRT:
         if (eis_weight_factor is None) != (chrono_weight_factor is None):
             warnings.warn('Both eis_weight_factor and chrono_weight_factor must be provided. '
                           'If only one is provided, it will be ignored.')
+        if hybrid_weight_factor_method not in (None, 'weight', 'rp'):
+            raise ValueError(f"Invalid hybrid_weight_factor_method argument {hybrid_weight_factor_method}. "
+                             "Options: 'weight', 'rp', None")
+        wf_method = None
         if eis_weight_factor is None or chrono_weight_factor is None:
             eis_weight_factor = chrono_weight_factor = 1
+            wf_method = hybrid_weight_factor_method            # drt1d.py:745-800: only when no factors are given
         opts = dict(hypers=hypers, step_times=step_times, step_sizes=step_sizes, nonneg=nonneg,
                     neg_allowed_tau_range=neg_allowed_tau_range, scale_data=scale_data, offset_steps=offset_steps,
                     step_offset_size=step_offset_size, offset_baseline=offset_baseline,
@@ -894,7 +902,8 @@ class DRT:
                     vz_offset=vz_offset, vz_offset_scale=vz_offset_scale, vz_offset_eps=vz_offset_eps,
                     eis_weight_factor=eis_weight_factor, chrono_weight_factor=chrono_weight_factor,
                     weight_factor=weight_factor, xtol=xtol, max_iter=max_iter,
-                    solve_rp=bool(solve_rp and scale_data), update_scale=bool(update_scale and scale_data))
+                    solve_rp=bool(solve_rp and scale_data), update_scale=bool(update_scale and scale_data),
+                    init_weights_separately=bool(init_weights_separately), wf_method=wf_method)
         if solve_rp and not scale_data and self.warn:
             warnings.warn('solve_rp is ignored if scale_data=False')
         self.v_baseline_deg, self.v_baseline_sqrt = v_baseline_deg, v_baseline_sqrt
@@ -989,6 +998,14 @@ class DRT:
             if wfa.shape != (plan['n_rows'],):
                 raise ValueError(f"weight_factor must be a scalar or have one entry per data row ({plan['n_rows']})")
             wf_vec = eng.dev(wfa)
+        hybrid_wf = None
+        if opts['wf_method'] == 'rp' and plan['data_type'] == 'hybrid':
+            # hybrid_weight_factor_method='rp' (drt1d.py:761-791): balance by the Rp each domain sees on its own
+            rp_eis = estimate_rp_batch(None, None, None, None, z_batch)
+            rp_chrono = estimate_rp_batch(plan['times'], self.step_times, self.step_sizes, v_batch, None)
+            rp_tot = cscale * hypers['rp_scale']
+            hybrid_wf = eng.dev(np.stack([rp_chrono ** 0.75 / (rp_eis ** 0.25 * rp_tot ** 0.5),
+                                          rp_eis ** 0.75 / (rp_chrono ** 0.25 * rp_tot ** 0.5)], axis=1))
         vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
         vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
         raw = eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
@@ -996,7 +1013,8 @@ class DRT:
                                  vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
                                  hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
                                  want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
-                                 want_resid=diag_tau is not None, pfrt=pfrt, weight_factor_vec=wf_vec)
+                                 want_resid=diag_tau is not None, pfrt=pfrt, weight_factor_vec=wf_vec,
+                                 hybrid_wf=hybrid_wf)
         plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         if nf and not plan.get('multi'):
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
@@ -1320,9 +1338,12 @@ class DRT:
                            'status': 'unknown' if st & (_engine.ST_QP_MAXITERS | _engine.ST_KKT_FAIL) else 'optimal'}
         w_true = h['weights'][0] * opts['weight_factor']
         w_scaled = w_true.copy()
+        cwf, ewf = opts['chrono_weight_factor'], opts['eis_weight_factor']
+        if 'hybrid_wf' in h:                                 # factors chosen per spectrum (drt1d.py:745-800)
+            cwf, ewf = float(h['hybrid_wf'][0, 0]), float(h['hybrid_wf'][0, 1])
         if pl['data_type'] == 'hybrid':
-            w_scaled[:nc] *= opts['chrono_weight_factor']
-            w_scaled[nc:] *= opts['eis_weight_factor']
+            w_scaled[:nc] *= cwf
+            w_scaled[nc:] *= ewf
         rm = pl['rm'].cpu().numpy()
         if 'vz_offset' in pl['special_qp_params']:
             rm[:, pl['special_qp_params']['vz_offset']['index']] = h['vz_col'][0]
@@ -1340,8 +1361,9 @@ class DRT:
             'est_weights': h['est_weights'][0], 'init_weights': init_w, 'weights': w_scaled,
             'true_weights': w_true, 'xmx_norms': h['xmx_norms'][0],
             'dop_xmx_norms': h['dop_xmx_norms'][0] if 'dop_xmx_norms' in h else np.ones(3),
-            'x_overfit_chrono': x_of if pl['data_type'] == 'chrono' else (x_of[:nc] if nc else None),
-            'x_overfit_eis': x_of if pl['data_type'] == 'eis' else (x_of[nc:] if pl['n_freq'] else None),
+            'x_overfit_chrono': x_of if (pl['data_type'] == 'chrono' or 'x_overfit_eis' in h) else (x_of[:nc] if nc else None),
+            'x_overfit_eis': (h['x_overfit_eis'][0] if 'x_overfit_eis' in h else
+                              (x_of if pl['data_type'] == 'eis' else (x_of[nc:] if pl['n_freq'] else None))),
             'p_matrix': fp['p_matrix'], 'q_vector': fp['q_vector'], 'rho_vector': h['rho'][0],
             'dop_rho_vector': h['dop_rho'][0] if 'dop_rho' in h else None,
             's_vectors': [h['s_vectors'][0, k] for k in range(3)],
@@ -1349,7 +1371,7 @@ class DRT:
             'l1_lambda_vector': pl['l1_host'], 'rm': rm, 'rv': res.extra['rv'][0],
             'penalty_matrices': {f'm{k}': pen[k] for k in range(3)}, 'hypers': pl['hypers'],
             'num_eis': pl['n_freq'], 'num_chrono': nc,
-            'chrono_weight_factor': opts['chrono_weight_factor'], 'eis_weight_factor': opts['eis_weight_factor'],
+            'chrono_weight_factor': cwf, 'eis_weight_factor': ewf,
             'vz_strength_vec': pl.get('vz_strength_host', 1),
             'n_outer': int(h['n_outer'][0]), 'n_ipm': int(h['n_ipm'][0]), 'status': st,
             'outlier_t': h['outlier_t'][0] if 'outlier_t' in h else np.ones(pl['n_rows']),

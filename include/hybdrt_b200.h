@@ -144,6 +144,8 @@ typedef struct hdrt_hypers {
                           from a lightly regularised solution before the weight initialisation                  */
     int update_scale;  /* drt1d.py:914-936: damped rescaling of the data from iteration 2 on                       */
     int normalize_dop; /* DOP column rescale of solve_rp (drt1d.py:586)                                            */
+    int init_weights_separately; /* drt1d.py:647-669: initialise the chrono and the EIS weights from separate fits  */
+    int hybrid_wf_method;        /* 1 = hybrid_weight_factor_method='weight' (drt1d.py:749-759); 0 = factors as given */
     double rp_scale;   /* hypers['rp_scale'] (qphb.py:213); read iff solve_rp or update_scale                      */
     double basis_area; /* area of one basis function, sqrt(pi) / epsilon (predict_r_p, drt1d.py:3552-3571)         */
 } hdrt_hypers;
@@ -219,6 +221,11 @@ typedef struct hdrt_qphb_problem {
                                                           from x alone: the data terms of step_llh (qphb.py:1359)  */
     double* pfrt_p;             /* [batch][n_pfrt][n][n]  step_p_mat (optional)                                    */
     int* pfrt_iters;            /* [batch][n_pfrt]        outer iterations per step (optional)                     */
+    const double* hybrid_wf_in;  /* [batch][2] chrono / EIS weight factors per spectrum (hybrid_weight_factor_method='rp',
+                                    computed by the caller, drt1d.py:761-791); NULL = the scalars of hyp             */
+    double* hybrid_wf_out;       /* [batch][2] the factors the fit used (optional)                                  */
+    double* x_overfit_eis;       /* [batch][n] x of the EIS-only initial fit when hyp.init_weights_separately (then
+                                    x_overfit holds the chrono-only one)                                            */
     const double* weight_factor_vec; /* [N] per-row weight factor, shared by the batch (kk_fit down-weights outliers this
                                         way, drt1d.py:1394-1405); NULL = the scalar hyp.weight_factor                  */
     double* vz_scratch;         /* [batch][N] work buffer: the vz_offset column a continuation step starts from

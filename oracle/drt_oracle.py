@@ -492,6 +492,20 @@ def qphb_fit(prob, hypers=None, record_history=False):
             x_overfit = res['x']
             est_w, outlier_t = estimate_weights(x_overfit, rv, vmm, rm, outlier_p=outlier_p, base=True,
                                                 return_t=True)
+    elif prob.get('init_weights_separately') and 0 < nc < rm.shape[0]:         # drt1d.py:647-669
+        def vmm_part(a, b):
+            if isinstance(vmm, dict):
+                return dict(n_chrono=(nc if a == 0 else 0), chrono=vmm.get('chrono') if a == 0 else None,
+                            eis=None if a == 0 else vmm.get('eis'))
+            return vmm[a:b, a:b]
+        parts, x_parts = [], []
+        for a, b in ((0, nc), (nc, rm.shape[0])):
+            res = qp(rm[a:b], rv[a:b], l2_iw, prob.get('iw_l1', 1e-4))
+            x_parts.append(res['x'])
+            parts.append(estimate_weights(res['x'], rv[a:b], vmm_part(a, b), rm[a:b]))
+        est_w = np.concatenate(parts)
+        x_overfit, x_overfit_eis = x_parts
+        outlier_t = np.ones(rm.shape[0])
     else:
         res = qp(rm, rv, l2_iw, prob.get('iw_l1', 1e-4))
         x_overfit = res['x']
@@ -504,6 +518,9 @@ def qphb_fit(prob, hypers=None, record_history=False):
     else:
         init_w = est_w.copy()
     w = init_w.copy()
+    if hybrid and prob.get('hybrid_weight_factor_method') == 'weight':            # drt1d.py:749-759
+        ratio = (np.mean(est_w[nc:] ** -2.0) ** -0.5 / np.mean(est_w[:nc] ** -2.0) ** -0.5) ** 0.25
+        ewf, cwf = 1 / ratio, ratio
 
     xmx = np.ones(kk)
     dop_xmx = np.ones(kk)
@@ -566,7 +583,7 @@ def qphb_fit(prob, hypers=None, record_history=False):
         est_weights=est_w, init_weights=init_w, x_overfit=x_overfit,
         s_vectors=np.array(s_vec), rho=rho, dop_rho=dop_rho, xmx_norms=xmx, dop_xmx_norms=dop_xmx,
         n_outer=it, converged=conv, ipm_iters=np.array(ipm_log), outlier_t=outlier_t,
-        init_outlier_t=init_outlier_t, scale_factors=np.array([rp_factor, us_factor, dop_cs]),
+        chrono_weight_factor=cwf, eis_weight_factor=ewf, init_outlier_t=init_outlier_t, scale_factors=np.array([rp_factor, us_factor, dop_cs]),
         p_matrix=l2 + wrm.T @ wrm, q_vector=-wrm.T @ (w_scaled * rv) + l1, rm_final=rm,
     )
     if record_history:

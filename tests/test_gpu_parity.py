@@ -676,6 +676,30 @@ def test_per_spectrum_frequency_grids(orc, lookup_golden):
         drt.fit_eis_batch(freqs[:5], z)
 
 
+def test_hybrid_fit_options():
+    """hybrid_weight_factor_method='weight' / 'rp' (drt1d.py:745-800) and init_weights_separately (:647-669) against
+    the unmodified reference."""
+    from hybdrt_b200.models import DRT
+    g = load_golden('hybrid_options.npz')
+    hy = load_golden('chrono_flex.npz')           # the small hybrid trace
+    args = (hy['times'], hy['i_signal'], hy['v_signal'][0], hy['freq'], hy['z'][0])
+    drt = DRT()
+    for tag, kw in (('weight', dict(hybrid_weight_factor_method='weight')), ('rp', dict(hybrid_weight_factor_method='rp')),
+                    ('sep', dict(init_weights_separately=True))):
+        drt.fit_hybrid(*args, **kw)
+        qp = drt.qphb_params
+        assert qp['n_outer'] == int(g[f'{tag}_n_outer']) and qp['n_ipm'] == int(g[f'{tag}_ipm']), tag
+        assert rel_err(np.array([qp['chrono_weight_factor'], qp['eis_weight_factor']]), g[f'{tag}_factors']) < FIT_TOL, tag
+        assert rel_err(drt.cvx_result['x'], g[f'{tag}_cvx_x']) < FIT_TOL, tag
+        assert rel_err(qp['weights'], g[f'{tag}_weights']) < FIT_TOL, tag
+        assert rel_err(qp['est_weights'], g[f'{tag}_est_weights']) < FIT_TOL, tag
+        assert rel_err(drt.predict_z(hy['freq']), g[f'{tag}_z_pred']) < FIT_TOL, tag
+    assert rel_err(drt.qphb_params['x_overfit_eis'], g['sep_x_overfit_eis']) < FIT_TOL
+    assert rel_err(drt.qphb_params['x_overfit_chrono'], g['sep_x_overfit_chrono']) < FIT_TOL
+    with pytest.raises(ValueError):
+        drt.fit_hybrid(*args, hybrid_weight_factor_method='nonsense')
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')

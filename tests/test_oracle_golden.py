@@ -286,6 +286,31 @@ def test_downsample_matches_reference():
     assert abs(plan['taps'].sum() - len(idx)) < 1e-9                     # every kept sample's taps sum to one
 
 
+def test_hybrid_options_match_reference(tables):
+    """hybrid_weight_factor_method='weight' (drt1d.py:749-759) and init_weights_separately (:647-669)."""
+    g = load_golden('hybrid_options.npz')
+    hs = load_golden('hybrid_small.npz')
+    rm0 = hs['rm'].copy()
+    rm0[:, 1] = 0
+    n, nc = rm0.shape[1], hs['times'].size
+    h = np.zeros(n)
+    h[:2] = 1000
+    base = dict(rm=rm0, rv=hs['rv'], vmm=dict(n_chrono=nc, chrono=None, eis=orc.eis_vmm(hs['freq'])),
+                pen=_layout_pen(hs['basis_tau'], float(tables['eps']), [1e-6, 1.0, 1e-6, 1e-6]), h=h, l1=np.zeros(n),
+                n_special=4, vz_index=1, vb_range=(0, 1), vz_strength=hs['vz_strength_vec'], n_chrono=nc)
+    res = orc.qphb_fit(dict(base, hybrid_weight_factor_method='weight'))
+    assert res['n_outer'] == int(g['weight_n_outer']) and int(res['ipm_iters'].sum()) == int(g['weight_ipm'])
+    assert rel_err(np.array([res['chrono_weight_factor'], res['eis_weight_factor']]), g['weight_factors']) < 1e-10
+    assert rel_err(res['x'], g['weight_cvx_x']) < 1e-8
+    res = orc.qphb_fit(dict(base, init_weights_separately=True))
+    assert res['n_outer'] == int(g['sep_n_outer']) and int(res['ipm_iters'].sum()) == int(g['sep_ipm'])
+    assert rel_err(res['est_weights'], g['sep_est_weights']) < 1e-8
+    assert rel_err(res['x'], g['sep_cvx_x']) < 1e-8
+    cf, ef = g['rp_factors']                        # 'rp': the factors come from the data, the loop is the plain one
+    res = orc.qphb_fit(dict(base, chrono_weight_factor=float(cf), eis_weight_factor=float(ef)))
+    assert res['n_outer'] == int(g['rp_n_outer']) and rel_err(res['x'], g['rp_cvx_x']) < 1e-8
+
+
 def test_coneqp_small_kat():
     """Known answer: min 1/2 x'x - c'x, x >= 0 has x = max(c, 0)."""
     c = np.array([1.0, -2.0, 0.5, -0.1])
