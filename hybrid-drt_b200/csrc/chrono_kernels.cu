@@ -53,11 +53,11 @@ using namespace hdrt;
 extern "C" int hdrt_filter_gather(const double* y, int n_sig, int nt, const int* idx, const int* seg_lo,
                                   const int* seg_len, const long long* woff, const int* lw, const double* taps, int m,
                                   double* out, void* stream) {
+    if (n_sig == 0) return HDRT_OK;        // an empty batch is a no-op (its buffers may be null)
     if (!y || !idx || !seg_lo || !seg_len || !woff || !lw || !taps || !out || n_sig < 0 || nt <= 0 || m <= 0) {
         set_error("hdrt_filter_gather: invalid argument");
         return HDRT_ERR_ARG;
     }
-    if (n_sig == 0) return HDRT_OK;
     int dev = 0, sms = 148;
     HDRT_CUDA_CHECK(cudaGetDevice(&dev));
     HDRT_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -558,11 +558,11 @@ extern "C" int hdrt_build_impedance(int mode, const double* freq, const double* 
                                     double eps, const double* re_x, const double* re_v, const double* im_x,
                                     const double* im_v, int grid_points, int quad_points, double* a_re, double* a_im,
                                     void* stream) {
+    if (n_grids == 0) return HDRT_OK;      // an empty batch is a no-op (its buffers may be null)
     if (!freq || !tau || !a_re || !a_im || n_grids < 0 || nf <= 0 || nb <= 0) {
         set_error("hdrt_build_impedance: invalid argument");
         return HDRT_ERR_ARG;
     }
-    if (n_grids == 0) return HDRT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == HDRT_MODE_INTERP) {
         if (!re_x || !re_v || !im_x || !im_v || grid_points < 2) { set_error("interp mode needs lookup tables"); return HDRT_ERR_ARG; }
@@ -608,11 +608,11 @@ extern "C" int hdrt_build_response(int mode, const double* times, const double* 
                                    const double* step_sizes, int n_grids, int nt, int nb, int n_steps, double eps,
                                    const double* td_x, const double* td_v, int grid_points, int quad_points,
                                    double* rm, void* stream) {
+    if (n_grids == 0) return HDRT_OK;
     if (!times || !tau || !step_times || !step_sizes || !rm || n_grids < 0 || nt <= 0 || nb <= 0 || n_steps <= 0) {
         set_error("hdrt_build_response: invalid argument");
         return HDRT_ERR_ARG;
     }
-    if (n_grids == 0) return HDRT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == HDRT_MODE_INTERP) {
         if (!td_x || !td_v || grid_points < 2) { set_error("interp mode needs the response lookup"); return HDRT_ERR_ARG; }
@@ -638,8 +638,8 @@ extern "C" int hdrt_build_response(int mode, const double* times, const double* 
 
 extern "C" int hdrt_build_penalty(const double* grid, int n_grids, int nb, double eps, int toeplitz, double* m,
                                   void* stream) {
-    if (!grid || !m || n_grids < 0 || nb <= 0) { set_error("hdrt_build_penalty: invalid argument"); return HDRT_ERR_ARG; }
     if (n_grids == 0) return HDRT_OK;
+    if (!grid || !m || n_grids < 0 || nb <= 0) { set_error("hdrt_build_penalty: invalid argument"); return HDRT_ERR_ARG; }
     const long long total = (long long)n_grids * 3 * nb * nb;
     penalty_kernel<<<grid_for(total, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(grid, n_grids, nb, eps, toeplitz, m);
     HDRT_CUDA_CHECK(cudaGetLastError());
@@ -648,8 +648,8 @@ extern "C" int hdrt_build_penalty(const double* grid, int n_grids, int nb, doubl
 
 extern "C" int hdrt_build_eis_vmm(const double* freq, int n_grids, int nf, double vmm_eps, double reim_cor, int uniform,
                                   double* vmm, void* stream) {
-    if (!freq || !vmm || n_grids < 0 || nf <= 0) { set_error("hdrt_build_eis_vmm: invalid argument"); return HDRT_ERR_ARG; }
     if (n_grids == 0) return HDRT_OK;
+    if (!freq || !vmm || n_grids < 0 || nf <= 0) { set_error("hdrt_build_eis_vmm: invalid argument"); return HDRT_ERR_ARG; }
     const long long rows = (long long)n_grids * 2 * nf;
     eis_vmm_kernel<<<grid_for(rows * 32, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(freq, n_grids, nf, vmm_eps,
                                                                                          reim_cor, uniform, vmm);

@@ -700,6 +700,42 @@ def test_hybrid_fit_options():
         drt.fit_hybrid(*args, hybrid_weight_factor_method='nonsense')
 
 
+def test_builder_and_filter_edges(eng, orc, lookup_golden):
+    """Empty and degenerate inputs of the L0 / L1 entry points: zero grids, a single frequency or basis function,
+    an odd number of entries per grid (the 16-byte store path), filter windows several times longer than the step
+    segment (repeated mirroring), an empty batch of traces."""
+    from hybdrt_b200 import engine as E
+    from oracle import chrono_oracle as co
+    eps = float(lookup_golden['eps'])
+    a_re, a_im = eng.build_impedance(np.zeros((0, 7)), np.zeros((0, 5)), eps, E.MODE_INTERP)
+    assert a_re.shape == (0, 7, 5)
+    for nf, nb in ((1, 1), (1, 9), (7, 1), (3, 5), (64, 33)):
+        freq = np.logspace(5, -1, nf)[None] if nf > 1 else np.array([[37.0]])
+        tau = np.logspace(-6, 1, nb)[None] if nb > 1 else np.array([[2e-3]])
+        a_re, a_im = eng.build_impedance(freq, tau, eps, E.MODE_INTERP)
+        assert rel_err(_np(a_re[0]), orc.impedance_matrix(freq[0], tau[0], eps, 'real', 'interp', lookup_golden)) < MAT_TOL
+        assert rel_err(_np(a_im[0]), orc.impedance_matrix(freq[0], tau[0], eps, 'imag', 'interp', lookup_golden)) < MAT_TOL
+    g3 = np.repeat(np.logspace(5, -1, 7)[None], 3, 0) * np.array([[1.0], [1.1], [1.2]])     # odd grid offsets: 7 x 5
+    t3 = np.repeat(np.logspace(-6, 1, 5)[None], 3, 0)
+    a_re, _ = eng.build_impedance(g3, t3, eps, E.MODE_INTERP)
+    for i in range(3):
+        assert rel_err(_np(a_re[i]), orc.impedance_matrix(g3[i], t3[i], eps, 'real', 'interp', lookup_golden)) < MAT_TOL
+    # filter: one 5-sample and one 40-sample segment, windows of 24 taps each side
+    y = np.random.default_rng(9).normal(size=(3, 45))
+    lw, w = 24, np.exp(-0.5 / 36.0 * np.arange(-24, 25) ** 2)      # sigma 6, truncate 4
+    w /= w.sum()
+    idx = np.array([0, 2, 4, 5, 20, 44])
+    plan = dict(idx=idx.astype(np.int32), seg_lo=np.where(idx < 5, 0, 5).astype(np.int32),
+                seg_len=np.where(idx < 5, 5, 40).astype(np.int32), lw=np.full(6, lw, np.int32),
+                woff=(np.arange(6) * 49).astype(np.int64), taps=np.tile(w, 6))
+    out = _np(eng.filter_gather(y, plan))
+    for b in range(3):
+        ref = np.concatenate([co.gaussian_filter1d_reflect(y[b, :5], 6.0), co.gaussian_filter1d_reflect(y[b, 5:], 6.0)])
+        assert rel_err(out[b], ref[idx]) < 1e-12
+    assert eng.filter_gather(np.zeros((0, 45)), plan).shape == (0, 6)
+    assert _np(eng.build_chrono_vmm(np.array([[0.0, 1.0]]), np.array([[0.5]]), 4.0)).shape == (1, 2, 2)
+
+
 def test_unsupported_options_raise():
     from hybdrt_b200.models import DRT
     c2 = load_golden('c2_eis.npz')
