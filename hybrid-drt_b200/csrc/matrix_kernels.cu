@@ -32,15 +32,16 @@ __device__ __forceinline__ double integrand(int kind, double y, double arg, doub
 
 // np.trapezoid(f(y), x=y) over y = linspace(-20, 20, quad_points); one warp cooperates.
 // For kind 0/1 `arg` is ln(omega tau); for kind 2 it is dt/tau.
+// sum_i (y_{i+1} - y_i) (f_{i+1} + f_i) / 2 regrouped by point -- f_i (y_{i+1} - y_{i-1}) / 2 with one-sided weights
+// at the two ends -- so that every integrand value (three exponentials) is computed once, not twice.
 __device__ double warp_trapz(int kind, double arg, double eps, int quad_points) {
     const int lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int i = lane; i < quad_points - 1; i += 32) {
-        const double y0 = linspace_at(-20.0, 20.0, quad_points, i);
-        const double y1 = linspace_at(-20.0, 20.0, quad_points, i + 1);
-        const double f0 = integrand(kind, y0, arg, eps);
-        const double f1 = integrand(kind, y1, arg, eps);
-        acc += (y1 - y0) * (f1 + f0) / 2.0;
+    for (int i = lane; i < quad_points; i += 32) {
+        const double y = linspace_at(-20.0, 20.0, quad_points, i);
+        const double ym = linspace_at(-20.0, 20.0, quad_points, max(i - 1, 0));
+        const double yp = linspace_at(-20.0, 20.0, quad_points, min(i + 1, quad_points - 1));
+        acc = fma(integrand(kind, y, arg, eps), (yp - ym) / 2.0, acc);
     }
     return warp_sum(acc);
 }
