@@ -1537,6 +1537,14 @@ class DRT:
             v_baseline = vb @ fp['v_baseline']
         return resp + v_baseline
 
+    def predict_r_inf(self):
+        """drt1d.py:3573-3581 (gaussian DOP basis: the ohmic resistance is R_inf itself)."""
+        return self.fit_parameters.get('R_inf', 0)
+
+    def predict_r_tot(self):
+        """drt1d.py:3583-3584"""
+        return self.predict_r_inf() + self.predict_r_p()
+
     def predict_r_p(self, absolute=False):
         """Polarisation resistance: sum of DRT coefficients times basis area (drt1d.py:3552-3590)."""
         x = self.fit_parameters['x']

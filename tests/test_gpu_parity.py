@@ -603,6 +603,8 @@ def test_predictions_away_from_the_fit_grids():
     assert rel_err(drt.get_tau_eval(20), g['tau_default']) < 1e-13
     assert rel_err(drt.predict_drt(), g['drt_default']) < FIT_TOL
     assert rel_err(drt.predict_drt(g['tau'], normalize=True), g['drt_norm']) < FIT_TOL
+    for name in ('r_inf', 'r_p', 'r_tot'):                  # drt1d.py:3552-3584
+        assert abs(getattr(drt, 'predict_' + name)() - float(g[name])) < FIT_TOL * abs(float(g[name]))
     freq, z = synth.make_eis_batch(3, seed=0)
     res = DRT().fit_eis_batch(freq, z)
     assert rel_err(res.predict_z(g['f_new']), g['b_z_new']) < FIT_TOL
