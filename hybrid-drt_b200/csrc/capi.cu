@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace hdrt {
@@ -30,7 +32,14 @@ extern "C" int hdrt_create(hdrt_handle** out, int device) {
     cudaDeviceProp prop;
     HDRT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    HDRT_CUDA_CHECK(cudaMalloc(&h->work_counter, sizeof(int)));
+    h->launches = 0;
+    h->mu = new std::mutex();
+    for (int i = 0; i < kLaunchSlots; ++i) {
+        hdrt_launch_slot& sl = h->slots[i];
+        sl.used = false;
+        HDRT_CUDA_CHECK(cudaMalloc(&sl.work_counter, sizeof(int)));
+        HDRT_CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
     *out = h;
     return HDRT_OK;
 }
@@ -38,7 +47,11 @@ extern "C" int hdrt_create(hdrt_handle** out, int device) {
 extern "C" int hdrt_destroy(hdrt_handle* h) {
     if (!h) return HDRT_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->work_counter);
+    for (int i = 0; i < kLaunchSlots; ++i) {
+        cudaFree(h->slots[i].work_counter);
+        cudaEventDestroy(h->slots[i].done);
+    }
+    delete static_cast<std::mutex*>(h->mu);
     delete h;
     return HDRT_OK;
 }

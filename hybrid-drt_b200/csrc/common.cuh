@@ -35,8 +35,21 @@ __device__ __forceinline__ double warp_max(double v) {
 
 }  // namespace hdrt
 
+// Per-launch resources of the fit kernel.  A handle owns a small ring of them so that fits launched on different
+// streams of one handle never share a work counter: launch i takes slot i % kLaunchSlots and, before reusing it, makes
+// its stream wait for the event recorded behind the previous launch that used the slot.
+constexpr int kLaunchSlots = 4;
+struct hdrt_launch_slot {
+    int* work_counter;      // device: the persistent CTAs pull spectrum indices from it
+    cudaEvent_t done;       // recorded behind the last launch that used the slot
+    bool used;
+};
+
 struct hdrt_handle {
     int device;
     int sm_count;
-    int* work_counter;  // device
+    hdrt_launch_slot slots[kLaunchSlots];
+    unsigned long long launches;        // guarded by mu
+    void* mu;                           // std::mutex*
 };
+

@@ -8,27 +8,25 @@
 // (drt1d.py:972).
 //
 // Data layout.  Every n x n symmetric / triangular matrix of the QP is cut into 8 x 8 tiles; tile (j, i), j >= i,
-// belongs to warp (j % W, i % W) of a W x W warp grid and lives in that warp's registers ("slot" (a, b) =
-// (j / W, i / W), b <= a) in the accumulator layout of mma.sync.m8n8k4.f64: lane (g, q) = (lane / 4, lane % 4)
-// holds [g][2q] and [g][2q + 1].  In that layout a tile is at the same time a valid A operand and a valid B^T
-// operand of the instruction (the k index is summed over, so the k permutation {2q} / {2q + 1} of the two issues
-// is immaterial):  D += X Z^T costs two DMMAs and no data movement.  Everything is phrased in that form:
+// of the (negated) QP matrix P belongs to warp (j % W, i % W) of a W x W warp grid and lives in that warp's registers
+// ("slot" (a, b) = (j / W, i / W), b <= a) in the accumulator layout of mma.sync.m8n8k4.f64: lane (g, q) =
+// (lane / 4, lane % 4) holds [g][2q] and [g][2q + 1].  In that layout a tile is at the same time a valid A operand
+// and a valid B^T operand of the instruction (the k index is summed over, so the k permutation {2q} / {2q + 1} of the
+// two issues is immaterial):  D += X Z^T costs two DMMAs and no data movement.  Everything is phrased in that form:
 //   Gram      P_ji = sum over 8-row chunks of rm^T_j diag(w^2) rm^T_i^T   (rm chunks staged transposed by cp.async)
-//   Cholesky  right-looking over tile columns k, fused with the inversion of the factor (Gauss-Jordan on the
-//             identity).  After step k the register tile (j, i) holds   -Schur_ji                     for i > k,
-//                                                      sum_{m <= k} L_jm (L^-1)_mi  (lower orient.)  for i <= k < j,
-//                                                      (L^-T)_ij  (upper orientation, final)         for j <= k.
-//             Step k: the owner of tile (k, k) factorises and inverts it with shuffles and publishes -L_kk^-1;
-//             the owners of column k (j > k) form L_jk = tile (-L_kk^-1)^T, the owners of row k (i < k) form
-//             (L^-T)_ik = tile^T (-L_kk^-1)^T; all of column k of [L^-T above; L below] is published to shared
-//             memory ("pan"), and every tile (j, i) with j > k gets  tile += pan_j pan_i^T.
-//   Solves    u = Y (Y^T b) with Y = L^-T straight from the register tiles (DFMA + shuffle reductions).
-// Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the negated P tiles of the current QP
-// (lower triangle, 512 B per tile in lane order), one tile column ("pan"), per-warp matvec partials, w[N], r2[N].
-// The Gram staging ring lives in the tile area (the tiles are written after the last chunk).
+//   Cholesky  H = P + diag(z / s) = L L^T per interior-point iteration, left-looking over tile columns: the tiles
+//             of P stay in registers for the whole QP (only the diagonal of H changes between iterations), the
+//             factor is written to shared memory in the same lane order.  See factor_chol.
+//   Solves    forward / backward sweeps over the tile rows of L; a vector block is the row of a tile, so that the
+//             products with L_jk, L_jk^T and the inverted diagonal tiles are DMMAs as well.  See sweep_forward.
+// Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the tiles of L (lower triangle, 512 B per tile
+// in lane order; the Gram pass leaves -P there for the QP to pick up), the transposed inverses of the diagonal tiles,
+// per-warp matvec partials, w[N], r2[N].  The Gram staging ring lives in the tile area as well.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 
@@ -88,9 +86,8 @@ struct Cfg {
     static constexpr int oRbuf = oRed + 2 * kRedSlots * kWarps;
     static constexpr int oUnion = oRbuf + 16;
     static constexpr int oPart = oUnion;                       // QP view: NPART x NV matvec partials
-    static constexpr int oBinv = oPart + NPART * NV;           //          -L_kk^-1 (64)
-    static constexpr int oPan = oBinv + 64;                    //          TMAX tiles: column k
-    static constexpr int oTiles = oPan + TMAX * 64;            // NTILE x 64 negated P tiles; Gram staging ring
+    static constexpr int oLinvT = oPart + NPART * NV;          //          TMAX tiles: -L_kk^-T
+    static constexpr int oTiles = oLinvT + TMAX * 64;          // NTILE x 64: -P (Gram output), then L; Gram staging ring
     static_assert(kStages * NV * kChunk <= NTILE * 64, "staging ring must fit in the tile area");
     static constexpr int oRows = oTiles + NTILE * 64;          // w[N], r2[N], aux[N]
     enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH };
@@ -98,12 +95,10 @@ struct Cfg {
     static __device__ __forceinline__ double* red() { return g_smem + oRed; }
     static __device__ __forceinline__ double* rbuf() { return g_smem + oRbuf; }
     static __device__ __forceinline__ double* part(int p) { return g_smem + oPart + p * NV; }
-    static __device__ __forceinline__ double* binv() { return g_smem + oBinv; }
-    static __device__ __forceinline__ double* pan() { return g_smem + oPan; }
+    static __device__ __forceinline__ double* linvt() { return g_smem + oLinvT; }
     static __device__ __forceinline__ double* tiles() { return g_smem + oTiles; }
     // per-row vectors w[N], r2[N] (each padded to a multiple of 8): derived from g_smem so that the
     // compiler emits shared-memory loads, not generic ones
-    static __device__ __forceinline__ int* flag() { return reinterpret_cast<int*>(g_smem + oRbuf + 8); }   // factorisation status
     static __device__ __forceinline__ double* roww() { return g_smem + oRows; }
     static __device__ __forceinline__ double* rowr2(int N) { return g_smem + oRows + ((N + 7) & ~7); }
     static __device__ __forceinline__ double* rowu(int N) { return g_smem + oRows + 2 * ((N + 7) & ~7); }   // outlier fits only
@@ -128,7 +123,7 @@ __host__ __device__ inline long long smem_doubles(int N, int n, int row_vectors 
 
 struct Ctx {
     int N, n, T, ns, nc, dop_a, dop_b, vz, vb_a, vb_b;
-    int wr, wc, lane, g, q;  // warp grid position, lane, accumulator-layout coordinates
+    int wr, wc, role, lane, g, q;  // warp grid position (role = W wr + wc), lane, accumulator-layout coordinates
     bool dv;                 // the diagonal slots (a, a) of this warp are inside the lower triangle (wc <= wr)
     const double* __restrict__ rm;
     const double* __restrict__ rv;
@@ -141,6 +136,7 @@ struct Ctx {
     double* vzcol;  // global, per spectrum
     double* vz0;    // global, per spectrum: vz_offset column frozen at the start of a continuation step, else NULL
     double* t_out;  // global, per spectrum: outlier_t (only with outlier_p)
+    unsigned tm;    // TMEM address (lane quadrant | first column) of this warp's tiles of -P
     double outlier_p;  // < 0: no outlier error structure
     double rv_scale;   // running data scale (solve_rp / update_scale): the data vector is rv * rv_scale
     double dop_cs;     // column scale of the DOP block of rm (solve_rp's DOP rescale), 1 otherwise
@@ -151,6 +147,16 @@ struct Ctx {
 __device__ __forceinline__ void tile_mma(double2& d, const double2& x, const double2& z) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d.x), "+d"(d.y) : "d"(x.x), "d"(z.x));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d.x), "+d"(d.y) : "d"(x.y), "d"(z.y));
+}
+
+// the two halves of tile_mma, for loops that issue the first halves of several independent tiles before the second ones
+__device__ __forceinline__ void mma_lo(double2& d, const double2& x, const double2& z) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d.x), "+d"(d.y) : "d"(x.x), "d"(z.x));
+}
+__device__ __forceinline__ void mma_hi(double2& d, const double2& x, const double2& z) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d.x), "+d"(d.y) : "d"(x.y), "d"(z.y));
 }
@@ -167,6 +173,22 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts2(double* p, const double2 v) { *reinterpret_cast<double2*>(p) = v; }
+// The same with 32-bit shared-window byte addresses: address arithmetic stays in one register and the loads are
+// issued where they are written (the factorisation and the sweeps order them by hand)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds2a(unsigned a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds1a(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts2a(unsigned a, const double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -402,64 +424,424 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
 }
 
 // ------------------------------------------------------------------------------------------------
-// Matrix-vector products on tiles in accumulator layout.  Lane (g, q) of a tile with row block R and column
-// block C holds t[g][2q], t[g][2q + 1]:
-//   "N" part:  out[8R + g]            += t[g][2q] v[8C + 2q] + t[g][2q + 1] v[8C + 2q + 1]   (reduce over q)
-//   "T" part:  out[8C + 2q (+1)]      += t[g][2q (+1)] v[8R + g]                               (reduce over g)
-// Warps that share a row block (same wr) or a column block (same wc) write separate partial vectors.
+// The QP matrix P (negated, lower-triangle tiles) lives in tensor memory (TMEM) for the duration of a QP.  It is loop
+// invariant (only the diagonal of the KKT matrix changes between interior-point iterations) and it is read once per
+// iteration, a tile column at a time, by the warp that owns the tiles (tile (j, i) belongs to warp (j % W, i % W),
+// as in the Gram pass) -- which is exactly what TMEM allows: a warp reaches the 32 TMEM lanes of its own quadrant
+// only, and with the 32x32b shape lane l of the warp reads / writes N consecutive 32-bit columns of TMEM lane l.
+// One 8 x 8 FP64 tile in accumulator layout (two doubles per lane) is four columns; slot (a, b) of a warp sits at
+// column 4 sidx(a, b) of the warp's column range.  tcgen05.mma has no FP64 kind, so nothing else uses the 256 KB;
+// holding P there frees the registers (the tiles used to be parked in them) and the shared memory (which holds the
+// factor), and a tile comes back in a few tens of cycles where an L2 round trip takes several hundred.
 // ------------------------------------------------------------------------------------------------
-// part[0 .. W) <- N parts (indexed by wc), part[W .. 2W) <- T parts (indexed by wr) of -P xs
 template <class C>
-__device__ __forceinline__ void matvec_p(const Ctx& c, const double* xs) {
-    const int T = c.T, g = c.g, q = c.q;
-    double2 accT[C::A];
+struct Tm {
+    static constexpr int kGroups = (C::kWarps + 3) / 4;        // warps per TMEM lane quadrant
+    static constexpr int kColsWarp = 4 * C::NSLOT;             // 32-bit columns per warp
+    static constexpr int kColsNeed = kGroups * kColsWarp;
+    static constexpr int kCols = kColsNeed <= 32 ? 32 : kColsNeed <= 64 ? 64 : kColsNeed <= 128 ? 128 : kColsNeed <= 256 ? 256 : 512;
+    static_assert(kColsNeed <= 512, "QP matrix does not fit in tensor memory");
+};
+
+__device__ __forceinline__ void tmem_st2(unsigned taddr, const double2 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// N tiles in one go: the loads are asynchronous, the wait sits in the same asm block so that nothing reads the
+// destination registers early
+template <int N>
+__device__ __forceinline__ void tmem_ld_tiles(const unsigned (&ta)[N], double2 (&out)[N]) {
+    static_assert(N >= 1 && N <= 4, "one to four tiles per block");
+    unsigned r[4 * N];
+    if constexpr (N == 1) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ta[0]) : "memory");
+    } else if constexpr (N == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%8];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%9];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(ta[0]), "r"(ta[1]) : "memory");
+    } else if constexpr (N == 3) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%12];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%13];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%14];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
+                     : "r"(ta[0]), "r"(ta[1]), "r"(ta[2]) : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%16];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [%17];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [%18];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [%19];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(ta[0]), "r"(ta[1]), "r"(ta[2]), "r"(ta[3]) : "memory");
+    }
 #pragma unroll
-    for (int b = 0; b < C::A; ++b) accT[b] = make_double2(0.0, 0.0);
-    const double* xr = xs + 8 * c.wr + g;
-    const double* xc = xs + 8 * c.wc + 2 * q;
+    for (int i = 0; i < N; ++i)
+        out[i] = make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+}
+
+// shared-memory tile area (where the Gram pass leaves -P) -> this warp's tiles in TMEM
+template <class C>
+__device__ __forceinline__ void store_p_tiles(const Ctx& c) {
+    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane;
 #pragma unroll
     for (int a = 0; a < C::A; ++a) {
         const int j = C::W * a + c.wr;
-        if (j < T) {
-            const double xg = xr[a * (8 * C::W)];
-            const double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * c.lane;
-            double accN = 0.0;
+        if (j < c.T) {     // warp uniform
+            const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
 #pragma unroll
-            for (int b = 0; b < a; ++b) {
-                const double2 p = lds2(trow + b * (C::W * 64));
-                const double2 xb = lds2(xc + b * (8 * C::W));
-                accN = fma(p.x, xb.x, accN);
-                accN = fma(p.y, xb.y, accN);
-                accT[b].x = fma(p.x, xg, accT[b].x);
-                accT[b].y = fma(p.y, xg, accT[b].y);
-            }
-            if (c.dv) {  // slot (a, a): a diagonal tile when wc == wr (N part only), else below the diagonal
-                const double2 p = lds2(trow + a * (C::W * 64));
-                const double2 xb = lds2(xc + a * (8 * C::W));
-                accN = fma(p.x, xb.x, accN);
-                accN = fma(p.y, xb.y, accN);
-                if (c.wc != c.wr) {
-                    accT[a].x = fma(p.x, xg, accT[a].x);
-                    accT[a].y = fma(p.y, xg, accT[a].y);
-                }
-            }
-            accN = reduce_q(accN);
-            if (q == 0) C::part(c.wc)[8 * j + g] = accN;
+            for (int b = 0; b <= a; ++b)
+                if (b < a || c.dv) tmem_st2(c.tm + 4 * C::sidx(a, b), lds2a(trow + b * (C::W * 512)));
         }
     }
+    tmem_wait_st();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Gaussian elimination on M = [C_kk | I] (8 x 16)
+// without row scaling: row g ends as [d_g Lt_g | Lt^-1_g] of C_kk = Lt D Lt^T (Lt unit lower); scaling row g by
+// d_g^-1/2 afterwards gives [L^T | L^-1] of the Cholesky factor.  Lane (g, q) keeps M[g][2q], M[g][2q + 1],
+// M[g][8 + 2q], M[g][9 + 2q] in registers -- the accumulator layout of both halves; row cc, its pivot and the
+// column-cc element of the own row travel by shuffles.  This runs on one warp while its block waits, and a lone
+// warp issues an instruction only every few cycles: the loop is rolled (it must stay in the instruction cache)
+// and carries as few instructions as possible (one reciprocal, one multiply, four FMAs, six shuffles).
+// Publishes -L^-1 (row-major = accumulator layout) to `binv` (this lane's shared-window address of the tile); returns Y_kk = L^-T in accumulator layout.  false
+// on breakdown (non-positive or non-finite pivot), uniformly over the warp.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {   // 1 / x, x positive and finite: 2^-22 seed + 2 Newton
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
+__device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, double2& ykk, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double m0 = -s.x, m1 = -s.y;
+    double m2 = (g == 2 * q) ? 1.0 : 0.0, m3 = (g == 2 * q + 1) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int cc = 0; cc < 7; ++cc) {
+        const int h = cc >> 1;
+        const double colv = (cc & 1) ? m1 : m0;                      // column cc of the own row, where q == h
+        const double agc = __shfl_sync(kFull, colv, 4 * g + h);      // M[g][cc]
+        const double piv = __shfl_sync(kFull, colv, 4 * cc + h);     // M[cc][cc]
+        const int src = 4 * cc + q;                                  // row cc
+        const double r0 = __shfl_sync(kFull, m0, src), r1 = __shfl_sync(kFull, m1, src);
+        const double r2 = __shfl_sync(kFull, m2, src), r3 = __shfl_sync(kFull, m3, src);
+        // f = -agc / piv with the reciprocal folded in: y0 = rcp seed, e = 1 - piv y0, 1 / piv = y0 (1 + e + e^2 + O(e^3))
+        double y0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(piv));
+        const double e = fma(-piv, y0, 1.0);
+        const double t = fma(e, e, e);
+        const double f0 = -agc * y0;
+        const double f = (g > cc) ? fma(f0, t, f0) : 0.0;
+        m0 = fma(f, r0, m0);
+        m1 = fma(f, r1, m1);
+        m2 = fma(f, r2, m2);
+        m3 = fma(f, r3, m3);
+    }
+    const double dg = __shfl_sync(kFull, (g & 1) ? m1 : m0, 4 * g + (g >> 1));   // d_g = M[g][g]
+    const bool ok = __all_sync(kFull, (dg > 0.0) && (dg < INFINITY));
+    const double rinv = fast_rsqrt(dg);
+    m2 *= rinv;
+    m3 *= rinv;
+    sts2a(binv, make_double2(-m2, -m3));
+    const int sx = 8 * q + (g >> 1);   // lane (2q, g / 2); lane (2q + 1, g / 2) is + 4
+    const double a2 = __shfl_sync(kFull, m2, sx), a3 = __shfl_sync(kFull, m3, sx);
+    const double b2 = __shfl_sync(kFull, m2, sx + 4), b3 = __shfl_sync(kFull, m3, sx + 4);
+    ykk = make_double2((g & 1) ? a3 : a2, (g & 1) ? b3 : b2);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H = P + diag(dsq) = L L^T and U = -L^-T, left-looking over tile columns.  -P is read from tensor memory; the
+// results go to the shared-memory tile area:  while the factorisation runs, tile (j, k) holds L_jk (j > k) and the
+// diagonal slot (k, k) holds -L_kk^-1;  at the end tile (j, k) holds the block U_kj (block row k, block column j) and
+// linvt(k) holds U_kk = -L_kk^-T.
+//
+// The warps with the same wc form a team that owns the tile columns k = wc (mod W), one at a time: its
+// accumulators start from -P_jk (from tensor memory; dsq joins on the diagonal tile) and collect  sum_m L_jm L_km^T  over
+// the columns m that are already published.  Step s finishes column s: the team adds the last term (m = s - 1), the warp
+// holding the diagonal tile factorises and inverts it (diag_factor), a team barrier publishes -L_ss^-1, every team
+// warp scales its tiles (L_js = C_js L_ss^-T, two DMMAs) and stores them; one block barrier per step publishes the
+// column.  Only one term per column sits on the critical path, which is
+// T x (one tile update + diag_factor + one tile scaling + two barriers).
+// The other teams spend the step catching up on the columns published so far, and every warp but the one busy with the
+// diagonal tile takes a share of turning row s - 1 of L, which no later column needs, into row s - 1 of the inverse
+// in place:
+//     U_i,s-1 = (linvt(i) L_s-1,i^T + sum_{i < m < s-1} U_i,m L_s-1,m^T) (-L_s-1,s-1^-1)^T,
+// the same accumulate-and-scale pattern as a column of L.  A predicated-off DMMA still occupies the FP64 pipe for its
+// 16 cycles, so the unrolled tile loops are instantiated per active-tile count and entered through a branch.
+// Returns false on breakdown (uniform across the block).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void team_barrier(int wc) {   // named barrier 1 + wc over the W warps of a team
+    static_assert(W <= 4, "one named barrier per team");
+    if (wc == 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory");
+    else if (wc == 1) asm volatile("bar.sync 2, %0;" ::"n"(32 * W) : "memory");
+    else if (wc == 2) asm volatile("bar.sync 3, %0;" ::"n"(32 * W) : "memory");
+    else asm volatile("bar.sync 4, %0;" ::"n"(32 * W) : "memory");
+}
+
+// The tile rows of a warp are indexed from the bottom of the matrix upwards: r = 0 is its last tile row, so that the
+// rows of a column that are still active are always r = 0 .. nv - 1.
+template <class C>
+struct RowMap {
+    int a_hi;                     // tile rows of this warp: j = W a + wr < T  <=>  a < a_hi
+    unsigned addr[C::A];          // this lane's byte address of tile (j_r, 0)
+    __device__ __forceinline__ int row(const Ctx& c, int r) const { return C::W * (a_hi - 1 - r) + c.wr; }
+};
+
+// tiles (j_r, kc), r < nv, of -P for this warp, from TMEM (slot (a, bc) with a = a_hi - 1 - r; the rows r >= nv read
+// a valid slot nobody uses)
+template <class C>
+__device__ __forceinline__ void load_column(const Ctx& c, const RowMap<C>& rm, double2 (&dst)[C::A], int bc) {
+    unsigned ta[C::A];
 #pragma unroll
-    for (int b = 0; b < C::A; ++b) {
-        const int i = C::W * b + c.wc;
-        const double v0 = reduce_g(accT[b].x), v1 = reduce_g(accT[b].y);
-        if (g == 0 && i < T) sts2(C::part(C::W + c.wr) + 8 * i + 2 * q, make_double2(v0, v1));
+    for (int r = 0; r < C::A; ++r) {
+        const int a = max(rm.a_hi - 1 - r, bc);
+        ta[r] = c.tm + 4 * (a * (a + 1) / 2 + bc);
+    }
+    constexpr int A = C::A;
+    {
+        constexpr int N0 = A < 4 ? A : 4;
+        unsigned t0[N0];
+        double2 o0[N0];
+#pragma unroll
+        for (int i = 0; i < N0; ++i) t0[i] = ta[i];
+        tmem_ld_tiles<N0>(t0, o0);
+#pragma unroll
+        for (int i = 0; i < N0; ++i) dst[i] = o0[i];
+    }
+    if constexpr (A > 4) {
+        constexpr int N1 = A - 4;
+        static_assert(N1 <= 4, "at most eight tile rows per warp");
+        unsigned t1[N1];
+        double2 o1[N1];
+#pragma unroll
+        for (int i = 0; i < N1; ++i) t1[i] = ta[4 + i];
+        tmem_ld_tiles<N1>(t1, o1);
+#pragma unroll
+        for (int i = 0; i < N1; ++i) dst[4 + i] = o1[i];
     }
 }
 
-// Solve H u = bs with the register tiles Y = L^-T of factor_invert:  u = Y (Y^T bs).  Slot (a, b) holds Y_ij
-// (row block i, column block j).  On return u[t] = sum_{p < W} part(W + p)[t].
-// part(wc)[8j + ..] <- this warp's contribution to Y^T bs ("T" part: reduce over g); sum over wc to finish
+template <class C, int N>
+__device__ __forceinline__ void catchup_body(double2 (&acc)[C::A], const unsigned (&rowaddr)[C::A], unsigned zaddr, int m0, int m1) {
+    // the operands of term m + 1 are requested before the DMMAs of term m are issued
+    double2 Z = lds2a(zaddr), X[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) X[r] = lds2a(rowaddr[r] + m0 * 512);
+#pragma unroll 1
+    for (int m = m0; m < m1; ++m) {
+        const int mn = min(m + 1, m1 - 1);
+        const double2 Zn = lds2a(zaddr + (mn - m0) * 512);
+        double2 Xn[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) Xn[r] = lds2a(rowaddr[r] + mn * 512);
+#pragma unroll
+        for (int r = 0; r < N; ++r) mma_lo(acc[r], X[r], Z);
+#pragma unroll
+        for (int r = 0; r < N; ++r) mma_hi(acc[r], X[r], Z);
+        Z = Zn;
+#pragma unroll
+        for (int r = 0; r < N; ++r) X[r] = Xn[r];
+    }
+}
+template <class C, int N>
+__device__ __forceinline__ void catchup(int nv, double2 (&acc)[C::A], const unsigned (&rowaddr)[C::A], unsigned zaddr, int m0, int m1) {
+    if (nv == N) catchup_body<C, N>(acc, rowaddr, zaddr, m0, m1);
+    else if constexpr (N > 1) catchup<C, N - 1>(nv, acc, rowaddr, zaddr, m0, m1);
+}
+
+// L_js = C_js L_ss^-T for the first ns accumulators (D = acc bn^T), stored to tile (j_r, s)
+template <class C, int N>
+__device__ __forceinline__ void scale_store(int ns, const double2 (&acc)[C::A], const unsigned (&rowaddr)[C::A], const double2 bn, int s) {
+    if (ns == N) {
+        double2 r2[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) { r2[r] = make_double2(0.0, 0.0); mma_lo(r2[r], acc[r], bn); }
+#pragma unroll
+        for (int r = 0; r < N; ++r) mma_hi(r2[r], acc[r], bn);
+#pragma unroll
+        for (int r = 0; r < N; ++r) sts2a(rowaddr[r] + s * 512, r2[r]);
+    } else if constexpr (N > 1) {
+        scale_store<C, N - 1>(ns, acc, rowaddr, bn, s);
+    }
+}
+
+// The inverse row is shared by all warps but the one that is busy with the diagonal tile of the step ("workers",
+// NWK = kWarps - 1 of them): worker wk takes the block columns i_e = wk + NWK e.
 template <class C>
-__device__ __forceinline__ void matvec_yt(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
+struct Inv {
+    static constexpr int NWK = C::kWarps - 1;
+    static constexpr int EI = (C::TMAX - 1 + NWK - 1) / NWK;      // block columns per worker
+};
+
+// one term of the inverse row: inv[e] += Xop_e Z^T for the n active columns i_e <= m of this worker
+template <class C, int N>
+__device__ __forceinline__ void invert_term(int n, double2 (&inv)[Inv<C>::EI], unsigned zaddr, unsigned mrow, unsigned lastaddr) {
+    if (n == N) {
+        const double2 Z = lds2a(zaddr);
+        double2 X[N];
+#pragma unroll
+        for (int e = 0; e < N - 1; ++e) X[e] = lds2a(mrow + e * (Inv<C>::NWK * 512));
+        X[N - 1] = lds2a(lastaddr);
+#pragma unroll
+        for (int e = 0; e < N; ++e) mma_lo(inv[e], X[e], Z);
+#pragma unroll
+        for (int e = 0; e < N; ++e) mma_hi(inv[e], X[e], Z);
+    } else if constexpr (N > 1) {
+        invert_term<C, N - 1>(n, inv, zaddr, mrow, lastaddr);
+    }
+}
+template <class C, int N>
+__device__ __forceinline__ void invert_store(int ne, const double2 (&inv)[Inv<C>::EI], const double2 bn, unsigned dst) {
+    if (ne == N) {
+        double2 r2[N];
+#pragma unroll
+        for (int e = 0; e < N; ++e) { r2[e] = make_double2(0.0, 0.0); mma_lo(r2[e], inv[e], bn); }
+#pragma unroll
+        for (int e = 0; e < N; ++e) mma_hi(r2[e], inv[e], bn);
+#pragma unroll
+        for (int e = 0; e < N; ++e) sts2a(dst + e * (Inv<C>::NWK * 512), r2[e]);
+    } else if constexpr (N > 1) {
+        invert_store<C, N - 1>(ne, inv, bn, dst);
+    }
+}
+
+// Row sr of L -> row sr of the inverse (blocks U_i,sr, i < sr, into the tiles (sr, i)), worker wk's share.
+template <class C>
+__device__ __forceinline__ void invert_row(int sr, int wk, unsigned tl, unsigned lt) {
+    constexpr int NWK = Inv<C>::NWK, EI = Inv<C>::EI;
+    const int ne = sr > wk ? (sr - wk + NWK - 1) / NWK : 0;      // block columns i_e = wk + NWK e < sr
+    const unsigned srow = tl + (sr * (sr + 1) / 2) * 512;         // tiles (sr, m)
+    double2 inv[EI];
+#pragma unroll
+    for (int e = 0; e < EI; ++e) inv[e] = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int m = wk; m < sr; ++m) {
+        const int n = (m - wk) / NWK + 1;                         // active columns: i_e <= m
+        const unsigned mrow = tl + (m * (m + 1) / 2 + wk) * 512;  // tiles (m, i_e) = U_(i_e, m), e = 0 ..
+        const bool diag = (m - wk) % NWK == 0;                    // i_(n-1) == m: the block is U_mm = linvt(m)
+        const unsigned lastaddr = diag ? lt + 512 * m : mrow + (n - 1) * (NWK * 512);
+        invert_term<C, EI>(n, inv, srow + m * 512, mrow, lastaddr);
+    }
+    asm volatile("bar.sync 5, %0;" ::"n"(32 * NWK) : "memory");   // every worker is done reading row sr of L
+    if (ne > 0) invert_store<C, EI>(ne, inv, lds2a(srow + sr * 512), srow + wk * 512);
+}
+
+template <class C>
+__device__ __noinline__ bool factor_chol(const Ctx& cref) {   // a function of its own: the caller's live values are
+    const Ctx c = cref;                                       // parked on its stack once per call, not in these loops
+    const int T = c.T, lane = c.lane;
+    constexpr int W = C::W;
+    PROF_DECL;
+    const unsigned tl = smem_u32(C::tiles()) + 16 * lane;   // this lane's element pair of tile 0 (byte address)
+    const unsigned lt = smem_u32(C::linvt()) + 16 * lane;
+    RowMap<C> rm;
+    rm.a_hi = T > c.wr ? (T - c.wr + W - 1) / W : 0;
+#pragma unroll
+    for (int r = 0; r < C::A; ++r) {
+        const int j = max(rm.row(c, r), 0);
+        rm.addr[r] = tl + (j * (j + 1) / 2) * 512;
+    }
+    const bool owner = c.wr == c.wc;             // this warp holds the diagonal tiles of its team's columns
+    double2 acc[C::A];
+    int kc = c.wc, bc = 0, mdone = 0;            // the team's current column, its slot column, terms collected
+    // active tile rows of column kc: slots a >= bc (+ 1 if the slot (bc, bc) lies above the diagonal), a < a_hi
+    int nv = max(rm.a_hi - (bc + (c.dv ? 0 : 1)), 0);
+    bool my_ok = true;
+    if (kc < T) load_column<C>(c, rm, acc, bc);
+    const double* dsq = C::vec(C::DSQ);
+    PROF_ADD(16);
+#pragma unroll 1
+    for (int s = 0; s <= T; ++s) {
+        const int ow = (s % W) * (W + 1);          // role of the warp that factorises the diagonal tile of this step
+        const bool crit = s < T && kc == s;        // this warp's team finishes its column in this step
+        if (crit && mdone < s) {                   // the critical path first: the last term(s) of column s
+            catchup<C, C::A>(nv, acc, rm.addr, tl + (kc * (kc + 1) / 2 + mdone) * 512, mdone, s);
+            mdone = s;
+        }
+        PROF_ADD(17);
+        if (s >= 1 && c.role != ow) {
+            invert_row<C>(s - 1, c.role - (c.role > ow ? 1 : 0), tl, lt);
+            PROF_ADD(21);
+        }
+        if (!crit && s < T && kc < T && mdone < s) {
+            catchup<C, C::A>(nv, acc, rm.addr, tl + (kc * (kc + 1) / 2 + mdone) * 512, mdone, s);
+            mdone = s;
+            PROF_ADD(17);
+        }
+        if (crit) {
+            const unsigned dslot = tl + (s * (s + 1) / 2 + s) * 512;
+            if (owner) {
+                double2 sk = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int r = 0; r < C::A; ++r) if (r == nv - 1) sk = acc[r];
+                const double d = dsq[8 * s + c.g];     // -(C_ss + diag(dsq))
+                if (c.g == 2 * c.q) sk.x -= d;
+                if (c.g == 2 * c.q + 1) sk.y -= d;
+                double2 ykk;
+                my_ok = diag_factor(sk, dslot, ykk, lane);
+                PROF_COUNT(24);
+                sts2a(lt + 512 * s, make_double2(-ykk.x, -ykk.y));
+                PROF_ADD(18);
+            }
+            team_barrier<W>(c.wc);
+            const int ns = nv - (owner ? 1 : 0);
+            if (ns > 0) scale_store<C, C::A>(ns, acc, rm.addr, lds2a(dslot), s);
+            kc += W;
+            ++bc;
+            mdone = 0;
+            nv = max(nv - 1, 0);
+            if (kc < T) load_column<C>(c, rm, acc, bc);
+            PROF_ADD(19);
+        }
+        const int all_ok = __syncthreads_and(my_ok);   // column s and inverse row s - 1 published
+        PROF_ADD(20);
+        if (!all_ok) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solves with U = -L^-T in the shared-memory tiles:  H^-1 b = U (U^T b).  Tile (j, i), j > i, holds the block U_ij
+// (block row i, block column j), linvt(j) the diagonal block U_jj; warp (wr, wc) of the grid takes the tiles
+// (j, i) = (W a + wr, W b + wc) as for P.  Lane (g, q) of a block holds u[g][2q], u[g][2q + 1]:
+//   (U^T b)_j [2q (+1)] += u[g][2q (+1)] b_i[g]          (reduce over g), partial per wc:  part(wc)
+//   (U t)_i [g]         += u[g][2q] t_j[2q] + u[g][2q + 1] t_j[2q + 1]   (reduce over q), partial per wr:  part(W + wr)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ void load_u_tiles(const Ctx& c, double2 (&S)[C::NSLOT]) {
+    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, lt = smem_u32(C::linvt()) + 16 * c.lane;
+#pragma unroll
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::W * a + c.wr;
+#pragma unroll
+        for (int b = 0; b <= a; ++b) S[C::sidx(a, b)] = make_double2(0.0, 0.0);
+        if (j < c.T) {
+            const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
+#pragma unroll
+            for (int b = 0; b < a; ++b) S[C::sidx(a, b)] = lds2a(trow + b * (C::W * 512));
+            if (c.dv) S[C::sidx(a, a)] = (c.wr == c.wc) ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512));
+        }
+    }
+}
+
+// part(wc)[8j + ..] <- this warp's contribution to U^T bs; sum over wc to finish
+template <class C>
+__device__ __forceinline__ void matvec_ut(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
     const int T = c.T, g = c.g, q = c.q;
     const double* bc = bs + 8 * c.wc + g;
     double bg[C::A];
@@ -481,233 +863,50 @@ __device__ __forceinline__ void matvec_yt(const Ctx& c, const double2 (&S)[C::NS
     }
 }
 
+// part(W + wr)[8i + ..] <- this warp's contribution to U t, t = sum_{p < W} part(p); sum over wr to finish
 template <class C>
-__device__ __forceinline__ void solve_phase(const Ctx& c, const double2 (&S)[C::NSLOT], const double* bs) {
+__device__ __forceinline__ void matvec_u(const Ctx& c, const double2 (&S)[C::NSLOT]) {
     const int T = c.T, g = c.g, q = c.q;
-    matvec_yt<C>(c, S, bs);
-    __syncthreads();
-    {   // u = Y t: N part (reduce over q), partial per wr
-        double acc[C::A];
+    double acc[C::A];
 #pragma unroll
-        for (int b = 0; b < C::A; ++b) acc[b] = 0.0;
-        const double* tr = C::part(0) + 8 * c.wr + 2 * q;
+    for (int b = 0; b < C::A; ++b) acc[b] = 0.0;
+    const double* tr = C::part(0) + 8 * c.wr + 2 * q;
 #pragma unroll
-        for (int a = 0; a < C::A; ++a) {
-            const int j = C::W * a + c.wr;
-            if (j < T) {
-                double2 tv = lds2(tr + a * (8 * C::W));
+    for (int a = 0; a < C::A; ++a) {
+        const int j = C::W * a + c.wr;
+        if (j < T) {
+            double2 tv = lds2(tr + a * (8 * C::W));
 #pragma unroll
-                for (int p = 1; p < C::W; ++p) {
-                    const double2 t = lds2(tr + p * C::NV + a * (8 * C::W));
-                    tv.x += t.x;
-                    tv.y += t.y;
-                }
+            for (int p = 1; p < C::W; ++p) {
+                const double2 t = lds2(tr + p * C::NV + a * (8 * C::W));
+                tv.x += t.x;
+                tv.y += t.y;
+            }
 #pragma unroll
-                for (int b = 0; b <= a; ++b) {
-                    acc[b] = fma(S[C::sidx(a, b)].x, tv.x, acc[b]);
-                    acc[b] = fma(S[C::sidx(a, b)].y, tv.y, acc[b]);
-                }
+            for (int b = 0; b <= a; ++b) {
+                acc[b] = fma(S[C::sidx(a, b)].x, tv.x, acc[b]);
+                acc[b] = fma(S[C::sidx(a, b)].y, tv.y, acc[b]);
             }
         }
+    }
 #pragma unroll
-        for (int b = 0; b < C::A; ++b) {
-            const int i = C::W * b + c.wc;
-            const double v = reduce_q(acc[b]);
-            if (q == 0 && i < T) C::part(C::W + c.wr)[8 * i + g] = v;
-        }
+    for (int b = 0; b < C::A; ++b) {
+        const int i = C::W * b + c.wc;
+        const double v = reduce_q(acc[b]);
+        if (q == 0 && i < T) C::part(C::W + c.wr)[8 * i + g] = v;
     }
-    __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Diagonal tile: s = -C_kk in accumulator layout (one warp).  Gaussian elimination on M = [C_kk | I] (8 x 16)
-// without row scaling: row g ends as [d_g Lt_g | Lt^-1_g] of C_kk = Lt D Lt^T (Lt unit lower); scaling row g by
-// d_g^-1/2 afterwards gives [L^T | L^-1] of the Cholesky factor.  Lane (g, q) keeps M[g][2q], M[g][2q + 1],
-// M[g][8 + 2q], M[g][9 + 2q] in registers -- the accumulator layout of both halves; row cc, its pivot and the
-// column-cc element of the own row travel by shuffles.  This runs on one warp while its block waits, and a lone
-// warp issues an instruction only every few cycles: the loop is rolled (it must stay in the instruction cache)
-// and carries as few instructions as possible (one reciprocal, one multiply, four FMAs, six shuffles).
-// Publishes -L^-1 (row-major = accumulator layout) to `binv`; returns Y_kk = L^-T in accumulator layout.  false
-// on breakdown (non-positive or non-finite pivot), uniformly over the warp.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_rcp(double x) {   // 1 / x, x positive and finite: 2^-22 seed + 2 Newton
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
-}
-
-__device__ __forceinline__ bool diag_factor(const double2 s, double* binv, double2& ykk, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    double m0 = -s.x, m1 = -s.y;
-    double m2 = (g == 2 * q) ? 1.0 : 0.0, m3 = (g == 2 * q + 1) ? 1.0 : 0.0;
-#pragma unroll 1
-    for (int cc = 0; cc < 7; ++cc) {
-        const int h = cc >> 1;
-        const double colv = (cc & 1) ? m1 : m0;                      // column cc of the own row, where q == h
-        const double agc = __shfl_sync(kFull, colv, 4 * g + h);      // M[g][cc]
-        const double piv = __shfl_sync(kFull, colv, 4 * cc + h);     // M[cc][cc]
-        const int src = 4 * cc + q;                                  // row cc
-        const double r0 = __shfl_sync(kFull, m0, src), r1 = __shfl_sync(kFull, m1, src);
-        const double r2 = __shfl_sync(kFull, m2, src), r3 = __shfl_sync(kFull, m3, src);
-        const double f = (g > cc) ? -agc * fast_rcp(piv) : 0.0;
-        m0 = fma(f, r0, m0);
-        m1 = fma(f, r1, m1);
-        m2 = fma(f, r2, m2);
-        m3 = fma(f, r3, m3);
-    }
-    const double dg = __shfl_sync(kFull, (g & 1) ? m1 : m0, 4 * g + (g >> 1));   // d_g = M[g][g]
-    const bool ok = __all_sync(kFull, (dg > 0.0) && (dg < INFINITY));
-    const double rinv = fast_rsqrt(dg);
-    m2 *= rinv;
-    m3 *= rinv;
-    sts2(binv + 2 * lane, make_double2(-m2, -m3));
-    const int sx = 8 * q + (g >> 1);   // lane (2q, g / 2); lane (2q + 1, g / 2) is + 4
-    const double a2 = __shfl_sync(kFull, m2, sx), a3 = __shfl_sync(kFull, m3, sx);
-    const double b2 = __shfl_sync(kFull, m2, sx + 4), b3 = __shfl_sync(kFull, m3, sx + 4);
-    ykk = make_double2((g & 1) ? a3 : a2, (g & 1) ? b3 : b2);
-    return ok;
-}
-
-// ------------------------------------------------------------------------------------------------
-// H = P + diag(dsq) -> register tiles Y = L^-T (H = L L^T).  See the header comment for the invariant.
-// Returns false on breakdown (uniform across the block).
-// ------------------------------------------------------------------------------------------------
+// H u = bs; on return u[t] = sum_{p < W} part(W + p)[t].  A function of its own, for the same reason as factor_chol.
 template <class C>
-__device__ __forceinline__ bool factor_invert(Ctx& c, double2 (&S)[C::NSLOT]) {
-    const int T = c.T, g = c.g, q = c.q, lane = c.lane;
-    constexpr int W = C::W;
-    PROF_DECL;
-    {
-        const double* dsq = C::vec(C::DSQ);
-#pragma unroll
-        for (int a = 0; a < C::A; ++a) {
-            const int j = W * a + c.wr;
-#pragma unroll
-            for (int b = 0; b <= a; ++b) S[C::sidx(a, b)] = make_double2(0.0, 0.0);
-            if (j < T) {
-                const double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * lane;
-#pragma unroll
-                for (int b = 0; b < a; ++b) S[C::sidx(a, b)] = lds2(trow + b * (W * 64));
-                if (c.dv) {
-                    double2 v = lds2(trow + a * (W * 64));
-                    if (c.wc == c.wr) {
-                        const double d = dsq[8 * j + g];
-                        if (g == 2 * q) v.x -= d;
-                        if (g == 2 * q + 1) v.y -= d;
-                    }
-                    S[C::sidx(a, a)] = v;
-                }
-            }
-        }
-    }
-    double* panr = C::pan() + 64 * c.wr + 2 * lane;   // tile j = W a + wr: + 64 W a
-    double* panc = C::pan() + 64 * c.wc + 2 * lane;
-    PROF_ADD(16);
-    // k = -1 is the prologue: only the look-ahead part runs (the diagonal tile of column 0 needs no update), so
-    // that the sweep holds a single instance of the diagonal-tile code
-#pragma unroll 1
-    for (int k = -1; k < T; ++k) {
-        const int kw = (k + W) % W, kd = k < 0 ? -1 : k / W;
-        const bool diag_owner = (kw == c.wr) && (kw == c.wc) && k >= 0;
-        if (k >= 0) {
-        PROF_ADD(17);
-        __syncthreads();  // (A) -L_kk^-1 published
-        PROF_ADD(18);
-        if (*C::flag() == 0) return false;
-        const double2 bn = lds2(C::binv() + 2 * lane);
-        if (diag_owner) {
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) if (a == kd) sts2(panr + a * (W * 64), S[C::sidx(a, a)]);
-        }
-        if (kw == c.wc) {  // column k: L_jk = C_jk L_kk^-T for j > k; the slot restarts from zero
-#pragma unroll
-            for (int b = 0; b < C::A; ++b) {
-                if (b == kd) {
-#pragma unroll
-                    for (int a = b; a < C::A; ++a) {
-                        const int j = W * a + c.wr;
-                        if (j < T && (a > b || c.wr > c.wc)) {
-                            double2 r2 = make_double2(0.0, 0.0);
-                            tile_mma(r2, S[C::sidx(a, b)], bn);
-                            sts2(panr + a * (W * 64), r2);
-                            S[C::sidx(a, b)] = make_double2(0.0, 0.0);
-                        }
-                    }
-                }
-            }
-        }
-        if (kw == c.wr) {  // row k: (L^-T)_ik = tile^T L_kk^-T for i < k, final.  The transposes go through the
-                           // tiles' own pan slots (free until barrier B): dump all, read back transposed, multiply.
-            const double* pant = C::pan() + 64 * c.wc + g;
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) {
-                if (a == kd) {
-                    const bool dlow = c.wc < c.wr;   // slot (a, a) is left of the diagonal tile
-#pragma unroll
-                    for (int b = 0; b < a; ++b) sts2(panc + b * (W * 64), S[C::sidx(a, b)]);
-                    if (dlow) sts2(panc + a * (W * 64), S[C::sidx(a, a)]);
-                    __syncwarp();
-                    double2 tt[C::A];
-#pragma unroll
-                    for (int b = 0; b <= a; ++b)
-                        tt[b] = make_double2(pant[b * (W * 64) + (2 * q) * 8], pant[b * (W * 64) + (2 * q + 1) * 8]);
-                    __syncwarp();
-#pragma unroll
-                    for (int b = 0; b <= a; ++b) {
-                        if (b < a || dlow) {
-                            double2 r2 = make_double2(0.0, 0.0);
-                            tile_mma(r2, tt[b], bn);
-                            sts2(panc + b * (W * 64), r2);
-                            S[C::sidx(a, b)] = r2;
-                        }
-                    }
-                }
-            }
-        }
-        PROF_ADD(19);
-        __syncthreads();  // (B) column k published
-        PROF_ADD(20);
-        }
-        if (k + 1 < T) {
-            // look-ahead: the owner of the next diagonal tile updates and factorises it before anything else
-            const int k1w = (k + 1) % W, k1d = (k + 1) / W;
-            const bool next_owner = (k1w == c.wr) && (k1w == c.wc);
-            if (next_owner) {
-                double2 sk = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int a = 0; a < C::A; ++a) {
-                    if (a == k1d) {
-                        if (k >= 0) tile_mma(S[C::sidx(a, a)], lds2(panr + a * (W * 64)), lds2(panc + a * (W * 64)));
-                        sk = S[C::sidx(a, a)];
-                    }
-                }
-                PROF_ADD(22);
-                double2 ykk;
-                const bool ok = diag_factor(sk, C::binv(), ykk, lane);
-                PROF_COUNT(24);
-#pragma unroll
-                for (int a = 0; a < C::A; ++a) if (a == k1d) S[C::sidx(a, a)] = ykk;
-                if (lane == 0) *C::flag() = ok ? 1 : 0;
-            }
-            PROF_ADD(17);
-            if (k >= 0) {
-#pragma unroll
-            for (int a = 0; a < C::A; ++a) {
-                const int j = W * a + c.wr;
-                if (j > k && j < T) {
-                    const double2 Fa = lds2(panr + a * (W * 64));
-#pragma unroll
-                    for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(panc + b * (W * 64)));
-                    if (c.dv && !(next_owner && a == k1d)) tile_mma(S[C::sidx(a, a)], Fa, lds2(panc + a * (W * 64)));
-                }
-            }
-            }
-            PROF_ADD(21);
-        }
-    }
-    return true;
+__device__ __noinline__ void solve_kkt(const Ctx& cref, const double* bs) {
+    const Ctx c = cref;
+    double2 S[C::NSLOT];
+    load_u_tiles<C>(c, S);
+    matvec_ut<C>(c, S, bs);
+    __syncthreads();
+    matvec_u<C>(c, S);
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -737,7 +936,6 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
     const int tid = threadIdx.x;
     const int n = c.n;
     const bool act = tid < n;
-    double* xs = C::vec(C::XS);
     double* bs = C::vec(C::BS);
     const double qi = act ? C::vec(C::QS)[tid] : 0.0;
     const double hi = act ? c.hvec[tid] : 0.0;
@@ -751,20 +949,20 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
         resx0 = fmax(1.0, sqrt(t2[0]));
         resz0 = fmax(1.0, sqrt(t2[1]));
     }
-    double2 S[C::NSLOT];
+    store_p_tiles<C>(c);      // -P to tensor memory (loop invariant: only the diagonal of the KKT matrix changes)
+    __syncthreads();          // the tile area now belongs to the factor
     PROF_DECL;
     double xi = 0.0, si = 1.0, zi = 1.0, di = 1.0, dinv = 1.0, lam = 1.0;
     double rxi = 0.0, rzi = 0.0, gap = 0.0, pcost = 0.0;
+    double pxi = 0.0;         // (P x)_i
     int iters;
     // iters == -1 is the initial point (W = I); 0.. are the interior-point iterations
 #pragma unroll 1
     for (iters = -1; iters <= kMaxIpm; ++iters) {
         if (iters >= 0) {
-            if (act) xs[tid] = xi;
-            __syncthreads();
-            matvec_p<C>(c, xs);
-            __syncthreads();
-            const double px = act ? -sum_parts<C>(0, C::NPART, tid) : 0.0;
+            // P x is carried along instead of recomputed: every solve H u = b of this loop has H = P + diag(dinv^2), so
+            // (P u)_i = b_i - dinv_i^2 u_i costs the owner of element i two operations and no communication
+            const double px = pxi;
             rxi = px + qi;
             const double f0p = act ? (xi * rxi + xi * qi) : 0.0;
             rxi -= zi;
@@ -796,7 +994,7 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
         if (act) C::vec(C::DSQ)[tid] = dinv * dinv;
         __syncthreads();
         PROF_ADD(8);
-        const bool fact_ok = factor_invert<C>(c, S);
+        const bool fact_ok = factor_chol<C>(c);
         PROF_ADD(9);
         if (!fact_ok) {
             out.status |= HDRT_ST_KKT_FAIL;
@@ -809,12 +1007,13 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
         const double lamsq = lam * lam;
         const double mu = gap / (double)n;
         double sigma = 0.0, step = 1.0;
-        double ws3 = 0.0, dxi = 0.0, dsi = 0.0, dzi = 0.0, zs = 0.0;
+        double ws3 = 0.0, dxi = 0.0, dsi = 0.0, dzi = 0.0, zs = 0.0, rhs = 0.0;
 #pragma unroll 1
         for (int pass = start ? 1 : 0; pass < 2; ++pass) {
             if (start) {
                 // solve [P+I] x = -q - h ; z = -x - h ; s = -z, shifted into the cone
-                if (act) bs[tid] = -qi - hi;
+                rhs = -qi - hi;
+                if (act) bs[tid] = rhs;
             } else {
                 dsi = 0.0;
                 if (pass == 1) dsi -= ws3;
@@ -825,13 +1024,15 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
                 dsi = dsi / lam;
                 dzi = dzi - di * dsi;
                 zs = dinv * dzi;
-                if (act) bs[tid] = dxi - dinv * zs;
+                rhs = dxi - dinv * zs;
+                if (act) bs[tid] = rhs;
             }
             __syncthreads();
-            solve_phase<C>(c, S, bs);
+            solve_kkt<C>(c, bs);
             dxi = act ? sum_parts<C>(C::W, C::W, tid) : 0.0;
             if (start) {
                 xi = dxi;
+                pxi = act ? rhs - xi : 0.0;          // (P + I) x = rhs
                 zi = -xi - hi;
                 si = -zi;
                 double t4[4] = {act ? si * si : 0.0, act ? -si : -INFINITY, act ? zi * zi : 0.0, act ? -zi : -INFINITY};
@@ -860,6 +1061,7 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
         }
         if (start) continue;
         PROF_ADD(10);
+        pxi = act ? fma(step, rhs - (dinv * dinv) * dxi, pxi) : 0.0;
         xi += step * dxi;
         dsi = step * dsi + 1.0;
         dzi = step * dzi + 1.0;
@@ -1228,10 +1430,10 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
 // ------------------------------------------------------------------------------------------------
 // Post-fit diagnostics for the mapping path (DRT.estimate_distribution_cov, drt1d.py:3063-3151, with
 // estimate_param_cov :4116-4138): diag(B P^-1 B^T) for the rows b_t of the evaluation matrix B, in the scaled
-// space (the host multiplies by coefficient_scale^2).  P = L L^T is factorised and inverted by the same tile
-// sweep as the QP's KKT matrices (its negated tiles are in shared memory after the calculate_pq Gram pass);
-// then diag_t = |Y^T b_t|^2 with Y = L^-T.  Returns false if P is not positive definite (the reference warns
-// 'Singular P matrix' and reports no covariance).
+// space (the host multiplies by coefficient_scale^2).  P = L L^T is factorised by the same tile sweep as the QP's
+// KKT matrices (its negated tiles are in shared memory after the calculate_pq Gram pass); then
+// diag_t = |U^T b_t|^2 with U = -L^-T.
+// Returns false if P is not positive definite (the reference warns 'Singular P matrix' and reports no covariance).
 // ------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __noinline__ bool postfit_variance(Ctx& cref, const double* __restrict__ eval_mat, int n_eval, double* out) {
@@ -1239,15 +1441,17 @@ __device__ __noinline__ bool postfit_variance(Ctx& cref, const double* __restric
     const int tid = threadIdx.x, n = c.n;
     double* bs = C::vec(C::BS);
     if (tid < C::NV) C::vec(C::DSQ)[tid] = 0.0;
+    store_p_tiles<C>(c);
     __syncthreads();
-    double2 S[C::NSLOT];
-    const bool ok = factor_invert<C>(c, S);
+    const bool ok = factor_chol<C>(c);
     if (ok) {
+        double2 S[C::NSLOT];
+        load_u_tiles<C>(c, S);
 #pragma unroll 1
         for (int t = 0; t < n_eval; ++t) {
             if (tid < n) bs[tid] = eval_mat[(size_t)t * n + tid];
             __syncthreads();
-            matvec_yt<C>(c, S, bs);
+            matvec_ut<C>(c, S, bs);
             __syncthreads();
             double v[1] = {0.0};
             if (tid < n) {
@@ -1630,6 +1834,7 @@ template <class C>
 __global__ void __launch_bounds__(C::kThreads, C::MINB)
 qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     __shared__ int s_work;
+    __shared__ unsigned s_tmem;
     Ctx c;
     c.N = p.n_rows; c.n = p.n_cols; c.ns = p.n_special; c.nc = p.n_chrono;
     c.dop_a = p.dop_start; c.dop_b = p.dop_end; c.vz = p.vz_index; c.vb_a = p.vb_start; c.vb_b = p.vb_end;
@@ -1637,10 +1842,22 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     c.T = (p.n_cols + 7) >> 3;
     c.lane = threadIdx.x & 31;
     c.g = c.lane >> 2; c.q = c.lane & 3;
+    // tensor memory for the QP matrix: one allocation per (persistent) CTA, by warp 0, released at the end
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(Tm<C>::kCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int wphys = threadIdx.x >> 5;     // the TMEM lane quadrant is a property of the physical warp
+        c.tm = s_tmem + ((unsigned)(32 * (wphys & 3)) << 16) + (unsigned)((wphys >> 2) * Tm<C>::kColsWarp);
+    }
     // tile-grid role of this warp, rotated per block so that the heavy roles (diagonal owners) of the blocks
     // sharing an SM land on different warp schedulers
     const int role = ((threadIdx.x >> 5) + blockIdx.x % 3) % C::kWarps;
-    c.wr = role / C::W; c.wc = role % C::W;
+    c.role = role; c.wr = role / C::W; c.wc = role % C::W;
     c.dv = c.wc <= c.wr;
     c.red_phase = 0;
 #ifdef HDRT_PROFILE
@@ -1663,6 +1880,9 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < 32) g_prof[threadIdx.x] += s_prof[threadIdx.x];
 #endif
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(Tm<C>::kCols) : "memory");
 }
 
 __global__ void fp64_probe_kernel(double* out, int iters) {
@@ -1702,9 +1922,19 @@ static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, 
     if (const char* e = getenv("HDRT_DEBUG_OCC")) { const int cap = atoi(e); if (cap > 0 && cap < occ) occ = cap; }  // dev knob
     int grid = h->sm_count * occ;
     if (grid > p.batch) grid = p.batch;
-    HDRT_CUDA_CHECK(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
-    qphb_kernel<C><<<grid, C::kThreads, smem, st>>>(p, h->work_counter);
-    HDRT_CUDA_CHECK(cudaGetLastError());
+    if (occ * Tm<C>::kCols > 512) { set_error("tensor memory: %d CTAs x %d columns per SM", occ, Tm<C>::kCols); return HDRT_ERR_UNSUPPORTED; }
+    // per-launch work counter: fits in flight on different streams of one handle do not share it
+    hdrt_launch_slot* sl;
+    {
+        std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(h->mu));
+        sl = &h->slots[h->launches++ % kLaunchSlots];
+        if (sl->used) HDRT_CUDA_CHECK(cudaStreamWaitEvent(st, sl->done, 0));
+        sl->used = true;
+        HDRT_CUDA_CHECK(cudaMemsetAsync(sl->work_counter, 0, sizeof(int), st));
+        qphb_kernel<C><<<grid, C::kThreads, smem, st>>>(p, sl->work_counter);
+        HDRT_CUDA_CHECK(cudaGetLastError());
+        HDRT_CUDA_CHECK(cudaEventRecord(sl->done, st));
+    }
     return HDRT_OK;
 }
 

@@ -62,7 +62,7 @@ for r in rows[2:]:
     tot += s
 src_cache = {}
 print(f'total samples {tot}')
-for key, s in per_line.most_common(45):
+for key, s in per_line.most_common(int(os.environ.get("NCU_LINES_TOP", "45"))):
     text = ''
     if key:
         fn = os.path.join(os.path.dirname(lib), '..', 'csrc', key[0])

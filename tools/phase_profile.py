@@ -40,10 +40,10 @@ lib.hdrt_debug_profile(buf, 0)
 v = np.array(list(buf), dtype=np.float64)
 grid = min(batch, 148 * 3)
 fits_block0 = int(np.ceil(batch / grid))  # approximately; the work queue decides
-names = {0: 'other(outer)', 1: 'gram', 2: 'qp total', 3: 'hyper', 4: 'weights', 8: 'qp: matvec+residual', 9: 'qp: factor_invert',
-         10: 'qp: solves+step', 16: 'fi: load', 17: 'fi: diag (owner)', 18: 'fi: wait A', 19: 'fi: finalize', 20: 'fi: wait B',
-         21: 'fi: update', 22: 'fi: look-ahead tile update (owner)', 5: 'gram: chunks', 6: 'gram: L2 add', 11: 'w: residual', 12: 'w: vmm', 13: 'hyper: s loop', 14: 'hyper: rho loop'}
+names = {0: 'other(outer)', 1: 'gram', 2: 'qp total', 3: 'hyper', 4: 'weights', 8: 'qp: matvec+residual', 9: 'qp: factor_chol',
+         10: 'qp: solves+step', 16: 'fc: load column 0', 17: 'fc: catch-up (updates)', 18: 'fc: diag tile (owner)', 19: 'fc: team barrier + scaling + next column', 20: 'fc: block barrier', 21: 'fc: inverse row (shadow team)',
+         5: 'gram: chunks', 6: 'gram: L2 add', 11: 'w: residual', 12: 'w: vmm', 13: 'hyper: s loop', 14: 'hyper: rho loop'}
 tot = v[0] + v[1] + v[2] + v[3] + v[4]
-print(f'block 0 total cycles {tot:.3e}  fits {v[25]:.0f}  diag calls (warp 0) {v[24]:.0f} -> {v[17] / max(v[24], 1):.0f} cycles each; per fit {tot / max(v[25], 1):.3e}')
+print(f'block 0 total cycles {tot:.3e}  fits {v[25]:.0f}  diag calls (warp 0) {v[24]:.0f} -> {v[18] / max(v[24], 1):.0f} cycles each; per fit {tot / max(v[25], 1):.3e}')
 for k in sorted(names):
     print(f'{names[k]:24s} {v[k]:.3e}  {100 * v[k] / tot:5.1f}%')
