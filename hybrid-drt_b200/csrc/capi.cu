@@ -32,6 +32,10 @@ extern "C" int hdrt_create(hdrt_handle** out, int device) {
     cudaDeviceProp prop;
     HDRT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    h->smem_reserved_per_cta = prop.reservedSharedMemPerBlock;
+    h->regs_per_sm = prop.regsPerMultiprocessor;
+    h->threads_per_sm = prop.maxThreadsPerMultiProcessor;
     h->launches = 0;
     h->mu = new std::mutex();
     for (int i = 0; i < kLaunchSlots; ++i) {

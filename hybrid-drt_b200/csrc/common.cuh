@@ -48,6 +48,8 @@ struct hdrt_launch_slot {
 struct hdrt_handle {
     int device;
     int sm_count;
+    size_t smem_per_sm, smem_reserved_per_cta;   // device limits the fit kernel sizes its grid with
+    int regs_per_sm, threads_per_sm;
     hdrt_launch_slot slots[kLaunchSlots];
     unsigned long long launches;        // guarded by mu
     void* mu;                           // std::mutex*

@@ -1916,13 +1916,21 @@ extern "C" long long hdrt_qphb_smem_bytes(int n_rows, int n_cols) {
 template <class C>
 static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, cudaStream_t st) {
     HDRT_CUDA_CHECK(cudaFuncSetAttribute(qphb_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    HDRT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qphb_kernel<C>, C::kThreads, smem));
+    // Resident CTAs per SM from the kernel's own resources: the occupancy API answers 1 for any kernel that allocates
+    // tensor memory, while the hardware co-schedules CTAs as long as their allocations fit in the 512 columns
+    // (tools/probes/tmem_probe.cu)
+    cudaFuncAttributes fa;
+    HDRT_CUDA_CHECK(cudaFuncGetAttributes(&fa, qphb_kernel<C>));
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * C::kThreads;
+    const size_t smem_per_cta = smem + fa.sharedSizeBytes + h->smem_reserved_per_cta;
+    int occ = (int)(h->smem_per_sm / smem_per_cta);
+    occ = occ < h->regs_per_sm / regs_per_cta ? occ : h->regs_per_sm / regs_per_cta;
+    occ = occ < 512 / Tm<C>::kCols ? occ : 512 / Tm<C>::kCols;
+    occ = occ < h->threads_per_sm / C::kThreads ? occ : h->threads_per_sm / C::kThreads;
     if (occ < 1) { set_error("kernel cannot be resident (smem %zu)", smem); return HDRT_ERR_UNSUPPORTED; }
     if (const char* e = getenv("HDRT_DEBUG_OCC")) { const int cap = atoi(e); if (cap > 0 && cap < occ) occ = cap; }  // dev knob
     int grid = h->sm_count * occ;
     if (grid > p.batch) grid = p.batch;
-    if (occ * Tm<C>::kCols > 512) { set_error("tensor memory: %d CTAs x %d columns per SM", occ, Tm<C>::kCols); return HDRT_ERR_UNSUPPORTED; }
     // per-launch work counter: fits in flight on different streams of one handle do not share it
     hdrt_launch_slot* sl;
     {
