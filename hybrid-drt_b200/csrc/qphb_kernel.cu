@@ -20,8 +20,7 @@
 //   Solves    u = U (U^T b): two passes over the tiles with DFMA and shuffle reductions.  See solve_kkt.
 //   P         the (negated) QP matrix itself lives in tensor memory (TMEM) between the Gram pass and the end of the QP.
 // Shared memory per CTA: a dozen length-NV vectors, reduction scratch, the tiles of L / L^-T (lower triangle, 512 B per
-// tile in lane order), the transposed inverses of the diagonal tiles, per-warp matvec partials, w[N], r2[N].  The
-// Gram staging ring lives in the tile area as well.
+// tile in lane order), per-warp matvec partials, w[N], r2[N].  The Gram staging ring lives in the tile area as well.
 // The design matrix rm, the variance-estimation matrix vmm and the penalty matrices are shared by the batch and
 // stay in global memory (L2 resident, read-only path).
 #include <stdlib.h>
@@ -81,13 +80,14 @@ struct Cfg {
     static constexpr int NPART = 2 * W;
     static constexpr int kChunk = 8;                  // rows of rm per Gram step (two DMMA k-steps)
     static constexpr int kStages = 4;                 // cp.async ring depth of the Gram (lives in the tile area)
+    static constexpr int RU = 4;    // rows per warp and pass of the row-wise matrix-vector loops: RU x 4
+                                                      // L2 loads in flight per lane
     // offsets
     static constexpr int oRed = kNumVec * NV;
     static constexpr int oRbuf = oRed + 2 * kRedSlots * kWarps;
     static constexpr int oUnion = oRbuf + 16;
     static constexpr int oPart = oUnion;                       // QP view: NPART x NV matvec partials
-    static constexpr int oLinvT = oPart + NPART * NV;          //          TMAX tiles: -L_kk^-T
-    static constexpr int oTiles = oLinvT + TMAX * 64;          // NTILE x 64: -P (Gram output), then L; Gram staging ring
+    static constexpr int oTiles = oPart + NPART * NV;          // NTILE x 64: L, then U = -L^-T; Gram staging ring
     static_assert(kStages * NV * kChunk <= NTILE * 64, "staging ring must fit in the tile area");
     static constexpr int oRows = oTiles + NTILE * 64;          // w[N], r2[N], aux[N]
     enum { XS = 0, BS, DSQ, QS, SV0, SV1, SV2, US0, US1, US2, XH };
@@ -95,7 +95,6 @@ struct Cfg {
     static __device__ __forceinline__ double* red() { return g_smem + oRed; }
     static __device__ __forceinline__ double* rbuf() { return g_smem + oRbuf; }
     static __device__ __forceinline__ double* part(int p) { return g_smem + oPart + p * NV; }
-    static __device__ __forceinline__ double* linvt() { return g_smem + oLinvT; }
     static __device__ __forceinline__ double* tiles() { return g_smem + oTiles; }
     // per-row vectors w[N], r2[N] (each padded to a multiple of 8): derived from g_smem so that the
     // compiler emits shared-memory loads, not generic ones
@@ -186,6 +185,8 @@ __device__ __forceinline__ double lds1a(unsigned a) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
     return v;
 }
+// a tile read transposed: lane (g, q) gets [2q][g] and [2q + 1][g]; `a` is the tile's address + (16 q + g) * 8
+__device__ __forceinline__ double2 lds2t(unsigned a) { return make_double2(lds1a(a), lds1a(a + 64)); }
 __device__ __forceinline__ void sts2a(unsigned a, const double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
@@ -543,7 +544,7 @@ __device__ __noinline__ void gram_phase(Ctx& cref, const L2Factors& fref, bool l
 // column-cc element of the own row travel by shuffles.  This runs on one warp while its block waits, and a lone
 // warp issues an instruction only every few cycles: the loop is rolled (it must stay in the instruction cache)
 // and carries as few instructions as possible (one reciprocal, one multiply, four FMAs, six shuffles).
-// Publishes -L^-1 (row-major = accumulator layout) to `binv` (this lane's shared-window address of the tile); returns Y_kk = L^-T in accumulator layout.  false
+// Publishes -L^-1 (row-major = accumulator layout) to `binv` (this lane's shared-window address of the tile).  false
 // on breakdown (non-positive or non-finite pivot), uniformly over the warp.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double x) {   // 1 / x, x positive and finite: 2^-22 seed + 2 Newton
@@ -554,7 +555,7 @@ __device__ __forceinline__ double fast_rcp(double x) {   // 1 / x, x positive an
     return y;
 }
 
-__device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, double2& ykk, int lane) {
+__device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, int lane) {
     const int g = lane >> 2, q = lane & 3;
     double m0 = -s.x, m1 = -s.y;
     double m2 = (g == 2 * q) ? 1.0 : 0.0, m3 = (g == 2 * q + 1) ? 1.0 : 0.0;
@@ -585,18 +586,14 @@ __device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, doub
     m2 *= rinv;
     m3 *= rinv;
     sts2a(binv, make_double2(-m2, -m3));
-    const int sx = 8 * q + (g >> 1);   // lane (2q, g / 2); lane (2q + 1, g / 2) is + 4
-    const double a2 = __shfl_sync(kFull, m2, sx), a3 = __shfl_sync(kFull, m3, sx);
-    const double b2 = __shfl_sync(kFull, m2, sx + 4), b3 = __shfl_sync(kFull, m3, sx + 4);
-    ykk = make_double2((g & 1) ? a3 : a2, (g & 1) ? b3 : b2);
     return ok;
 }
 
 // ------------------------------------------------------------------------------------------------
 // H = P + diag(dsq) = L L^T and U = -L^-T, left-looking over tile columns.  -P is read from tensor memory; the
 // results go to the shared-memory tile area:  while the factorisation runs, tile (j, k) holds L_jk (j > k) and the
-// diagonal slot (k, k) holds -L_kk^-1;  at the end tile (j, k) holds the block U_kj (block row k, block column j) and
-// linvt(k) holds U_kk = -L_kk^-T.
+// diagonal slot (k, k) holds -L_kk^-1;  at the end tile (j, k) holds the block U_kj (block row k, block column j); the
+// diagonal blocks U_kk = (-L_kk^-1)^T are the diagonal slots read transposed.
 //
 // The warps with the same wc form a team that owns the tile columns k = wc (mod W), one at a time: its
 // accumulators start from -P_jk (from tensor memory; dsq joins on the diagonal tile) and collect  sum_m L_jm L_km^T  over
@@ -608,7 +605,7 @@ __device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, doub
 // The other teams spend the step catching up on the columns published so far, and every warp but the one busy with the
 // diagonal tile takes a share of turning row s - 1 of L, which no later column needs, into row s - 1 of the inverse
 // in place:
-//     U_i,s-1 = (linvt(i) L_s-1,i^T + sum_{i < m < s-1} U_i,m L_s-1,m^T) (-L_s-1,s-1^-1)^T,
+//     U_i,s-1 = (U_ii L_s-1,i^T + sum_{i < m < s-1} U_i,m L_s-1,m^T) (-L_s-1,s-1^-1)^T,
 // the same accumulate-and-scale pattern as a column of L.  A predicated-off DMMA still occupies the FP64 pipe for its
 // 16 cycles, so the unrolled tile loops are instantiated per active-tile count and entered through a branch.
 // Returns false on breakdown (uniform across the block).
@@ -698,19 +695,19 @@ struct Inv {
 
 // one term of the inverse row: inv[e] += Xop_e Z^T for the n active columns i_e <= m of this worker
 template <class C, int N>
-__device__ __forceinline__ void invert_term(int n, double2 (&inv)[Inv<C>::EI], unsigned zaddr, unsigned mrow, unsigned lastaddr) {
+__device__ __forceinline__ void invert_term(int n, double2 (&inv)[Inv<C>::EI], unsigned zaddr, unsigned mrow, unsigned lastaddr, bool diag) {
     if (n == N) {
         const double2 Z = lds2a(zaddr);
         double2 X[N];
 #pragma unroll
         for (int e = 0; e < N - 1; ++e) X[e] = lds2a(mrow + e * (Inv<C>::NWK * 512));
-        X[N - 1] = lds2a(lastaddr);
+        X[N - 1] = diag ? lds2t(lastaddr) : lds2a(lastaddr);     // U_mm = (-L_mm^-1)^T: the diagonal slot read transposed
 #pragma unroll
         for (int e = 0; e < N; ++e) mma_lo(inv[e], X[e], Z);
 #pragma unroll
         for (int e = 0; e < N; ++e) mma_hi(inv[e], X[e], Z);
     } else if constexpr (N > 1) {
-        invert_term<C, N - 1>(n, inv, zaddr, mrow, lastaddr);
+        invert_term<C, N - 1>(n, inv, zaddr, mrow, lastaddr, diag);
     }
 }
 template <class C, int N>
@@ -730,7 +727,7 @@ __device__ __forceinline__ void invert_store(int ne, const double2 (&inv)[Inv<C>
 
 // Row sr of L -> row sr of the inverse (blocks U_i,sr, i < sr, into the tiles (sr, i)), worker wk's share.
 template <class C>
-__device__ __forceinline__ void invert_row(int sr, int wk, unsigned tl, unsigned lt) {
+__device__ __forceinline__ void invert_row(int sr, int wk, unsigned tl, unsigned tt) {
     constexpr int NWK = Inv<C>::NWK, EI = Inv<C>::EI;
     const int ne = sr > wk ? (sr - wk + NWK - 1) / NWK : 0;      // block columns i_e = wk + NWK e < sr
     const unsigned srow = tl + (sr * (sr + 1) / 2) * 512;         // tiles (sr, m)
@@ -741,9 +738,9 @@ __device__ __forceinline__ void invert_row(int sr, int wk, unsigned tl, unsigned
     for (int m = wk; m < sr; ++m) {
         const int n = (m - wk) / NWK + 1;                         // active columns: i_e <= m
         const unsigned mrow = tl + (m * (m + 1) / 2 + wk) * 512;  // tiles (m, i_e) = U_(i_e, m), e = 0 ..
-        const bool diag = (m - wk) % NWK == 0;                    // i_(n-1) == m: the block is U_mm = linvt(m)
-        const unsigned lastaddr = diag ? lt + 512 * m : mrow + (n - 1) * (NWK * 512);
-        invert_term<C, EI>(n, inv, srow + m * 512, mrow, lastaddr);
+        const bool diag = (m - wk) % NWK == 0;                    // i_(n-1) == m: the block is U_mm
+        const unsigned lastaddr = diag ? tt + (m * (m + 1) / 2 + m) * 512 : mrow + (n - 1) * (NWK * 512);
+        invert_term<C, EI>(n, inv, srow + m * 512, mrow, lastaddr, diag);
     }
     asm volatile("bar.sync 5, %0;" ::"n"(32 * NWK) : "memory");   // every worker is done reading row sr of L
     if (ne > 0) invert_store<C, EI>(ne, inv, lds2a(srow + sr * 512), srow + wk * 512);
@@ -756,7 +753,7 @@ __device__ __noinline__ bool factor_chol(const Ctx& cref) {   // a function of i
     constexpr int W = C::W;
     PROF_DECL;
     const unsigned tl = smem_u32(C::tiles()) + 16 * lane;   // this lane's element pair of tile 0 (byte address)
-    const unsigned lt = smem_u32(C::linvt()) + 16 * lane;
+    const unsigned tt = smem_u32(C::tiles()) + (16 * c.q + c.g) * 8;   // ... for a transposed tile read
     RowMap<C> rm;
     rm.a_hi = T > c.wr ? (T - c.wr + W - 1) / W : 0;
 #pragma unroll
@@ -783,7 +780,7 @@ __device__ __noinline__ bool factor_chol(const Ctx& cref) {   // a function of i
         }
         PROF_ADD(17);
         if (s >= 1 && c.role != ow) {
-            invert_row<C>(s - 1, c.role - (c.role > ow ? 1 : 0), tl, lt);
+            invert_row<C>(s - 1, c.role - (c.role > ow ? 1 : 0), tl, tt);
             PROF_ADD(21);
         }
         if (!crit && s < T && kc < T && mdone < s) {
@@ -800,10 +797,8 @@ __device__ __noinline__ bool factor_chol(const Ctx& cref) {   // a function of i
                 const double d = dsq[8 * s + c.g];     // -(C_ss + diag(dsq))
                 if (c.g == 2 * c.q) sk.x -= d;
                 if (c.g == 2 * c.q + 1) sk.y -= d;
-                double2 ykk;
-                my_ok = diag_factor(sk, dslot, ykk, lane);
+                my_ok = diag_factor(sk, dslot, lane);
                 PROF_COUNT(24);
-                sts2a(lt + 512 * s, make_double2(-ykk.x, -ykk.y));
                 PROF_ADD(18);
             }
             team_barrier<W>(c.wc);
@@ -825,14 +820,14 @@ __device__ __noinline__ bool factor_chol(const Ctx& cref) {   // a function of i
 
 // ------------------------------------------------------------------------------------------------
 // Solves with U = -L^-T in the shared-memory tiles:  H^-1 b = U (U^T b).  Tile (j, i), j > i, holds the block U_ij
-// (block row i, block column j), linvt(j) the diagonal block U_jj; warp (wr, wc) of the grid takes the tiles
+// (block row i, block column j), the diagonal slot (j, j) the transpose of U_jj; warp (wr, wc) of the grid takes the tiles
 // (j, i) = (W a + wr, W b + wc) as for P.  Lane (g, q) of a block holds u[g][2q], u[g][2q + 1]:
 //   (U^T b)_j [2q (+1)] += u[g][2q (+1)] b_i[g]          (reduce over g), partial per wc:  part(wc)
 //   (U t)_i [g]         += u[g][2q] t_j[2q] + u[g][2q + 1] t_j[2q + 1]   (reduce over q), partial per wr:  part(W + wr)
 // ------------------------------------------------------------------------------------------------
 template <class C>
 __device__ __forceinline__ void load_u_tiles(const Ctx& c, double2 (&S)[C::NSLOT]) {
-    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, lt = smem_u32(C::linvt()) + 16 * c.lane;
+    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, tt = smem_u32(C::tiles()) + (16 * c.q + c.g) * 8;
 #pragma unroll
     for (int a = 0; a < C::A; ++a) {
         const int j = C::W * a + c.wr;
@@ -842,7 +837,7 @@ __device__ __forceinline__ void load_u_tiles(const Ctx& c, double2 (&S)[C::NSLOT
             const unsigned trow = tl + (j * (j + 1) / 2 + c.wc) * 512;
 #pragma unroll
             for (int b = 0; b < a; ++b) S[C::sidx(a, b)] = lds2a(trow + b * (C::W * 512));
-            if (c.dv) S[C::sidx(a, a)] = (c.wr == c.wc) ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512));
+            if (c.dv) S[C::sidx(a, a)] = (c.wr == c.wc) ? lds2t(tt + (j * (j + 1) / 2 + j) * 512) : lds2a(trow + a * (C::W * 512));
         }
     }
 }
@@ -911,7 +906,7 @@ __device__ __forceinline__ void matvec_u(const Ctx& c, const double2 (&S)[C::NSL
 template <class C>
 __device__ __forceinline__ void solve_kkt(const Ctx& c, const double* bs) {
     const int T = c.T, g = c.g, q = c.q;
-    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, lt = smem_u32(C::linvt()) + 16 * c.lane;
+    const unsigned tl = smem_u32(C::tiles()) + 16 * c.lane, tt = smem_u32(C::tiles()) + (16 * c.q + c.g) * 8;
     const bool dg = c.wr == c.wc;
     {   // part(wc) <- U^T bs (this warp's tiles)
         const double* bc = bs + 8 * c.wc + g;
@@ -926,7 +921,7 @@ __device__ __forceinline__ void solve_kkt(const Ctx& c, const double* bs) {
                 double2 t[C::A];
 #pragma unroll
                 for (int b = 0; b < a; ++b) t[b] = lds2a(trow + b * (C::W * 512));
-                t[a] = c.dv ? (dg ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
+                t[a] = c.dv ? (dg ? lds2t(tt + (j * (j + 1) / 2 + j) * 512) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
                 double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int b = 0; b <= a; ++b) {
@@ -952,7 +947,7 @@ __device__ __forceinline__ void solve_kkt(const Ctx& c, const double* bs) {
                 double2 t[C::A];
 #pragma unroll
                 for (int b = 0; b < a; ++b) t[b] = lds2a(trow + b * (C::W * 512));
-                t[a] = c.dv ? (dg ? lds2a(lt + 512 * j) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
+                t[a] = c.dv ? (dg ? lds2t(tt + (j * (j + 1) / 2 + j) * 512) : lds2a(trow + a * (C::W * 512))) : make_double2(0.0, 0.0);
                 double2 tv = lds2(tr + a * (8 * C::W));
 #pragma unroll
                 for (int p = 1; p < C::W; ++p) {
@@ -1178,7 +1173,7 @@ __device__ __noinline__ void hyper_block(Ctx& cref, const BlockHyp& hpref, int s
     if (act) {
         const double inv2s0 = 1.0 / (2.0 * hp.sigma[0] * hp.sigma[0]);
         const double* __restrict__ pcol = c.pen + (start * n + gi);  // symmetric: read column-wise (coalesced)
-        // rows in batches of four: the twelve loads (L2 hits, several hundred cycles each) are issued together
+        // rows in batches of eight: the 24 loads (L2 hits, several hundred cycles each) are issued together
 #pragma unroll 1
         for (int j0 = 0; j0 < len; j0 += 4) {
             double mm[4][3];
@@ -1288,13 +1283,13 @@ __device__ __noinline__ void hyper_block(Ctx& cref, const BlockHyp& hpref, int s
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rows rb + u kWarps (u < 4) of vmm @ uin for one warp; uin is a per-row vector in shared memory.  vmm is block
+// Rows rb + u kWarps (u < RU) of vmm @ uin for one warp; uin is a per-row vector in shared memory.  vmm is block
 // diagonal: chrono rows x chrono columns (dense, or NULL = uniform: the caller substitutes the mean), EIS rows x
 // EIS columns.  The sums are warp-reduced (valid in every lane).
 // ------------------------------------------------------------------------------------------------
 template <class C>
-__device__ __forceinline__ void vmm_rows(const Ctx& c, const double* uin, int rb, double (&sh)[4]) {
-    constexpr int RU = 4, CU = (C::NV + 31) / 32;
+__device__ __forceinline__ void vmm_rows(const Ctx& c, const double* uin, int rb, double (&sh)[C::RU]) {
+    constexpr int RU = C::RU, CU = (C::NV + 31) / 32;
     const int lane = threadIdx.x & 31;
     const int N = c.N, nc = c.nc;
 #pragma unroll
@@ -1371,7 +1366,7 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     PROF_DECL;
     // residuals: one warp per row, four rows per pass.  All loads of a pass (L2 hits, several hundred cycles
     // each) are issued before the first use: row / column indices are clamped instead of branched around.
-    constexpr int RU = 4, CU = (C::NV + 31) / 32;
+    constexpr int RU = C::RU, CU = (C::NV + 31) / 32;
     double xw[CU];     // this lane's coefficients (DOP ones with the column rescale of solve_rp folded in)
 #pragma unroll
     for (int w = 0; w < CU; ++w) {
@@ -1995,6 +1990,17 @@ static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, 
     occ = occ < h->threads_per_sm / C::kThreads ? occ : h->threads_per_sm / C::kThreads;
     if (occ < 1) { set_error("kernel cannot be resident (smem %zu)", smem); return HDRT_ERR_UNSUPPORTED; }
     if (const char* e = getenv("HDRT_DEBUG_OCC")) { const int cap = atoi(e); if (cap > 0 && cap < occ) occ = cap; }  // dev knob
+    {   // no more shared memory than the resident CTAs need: the rest of the unified array is L1, where the stack lives
+        // (the supported carve-outs of sm_100 are 0, 8, 16, 32, 64, 100, 132, 164, 196 and 228 KB; the hint is a
+        // percentage of the largest and is rounded to the nearest one, so aim at the smallest that fits)
+        static const int kCarve[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = (size_t)occ * smem_per_cta;
+        int kb = 228;
+        for (int i = 8; i >= 0; --i) if ((size_t)kCarve[i] * 1024 >= need) kb = kCarve[i];
+        const int pct = (100 * kb + 227) / 228;
+        if (!getenv("HDRT_NO_CARVE"))
+        HDRT_CUDA_CHECK(cudaFuncSetAttribute(qphb_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     int grid = h->sm_count * occ;
     if (grid > p.batch) grid = p.batch;
     // per-launch work counter: fits in flight on different streams of one handle do not share it
