@@ -1008,18 +1008,23 @@ class DRT:
                                           rp_eis ** 0.75 / (rp_chrono ** 0.25 * rp_tot ** 0.5)], axis=1))
         vz_index = sp['vz_offset']['index'] if 'vz_offset' in sp else -1
         vb_range = self.get_special_indices('v_baseline') if 'vz_offset' in sp else (-1, -1)
-        raw = eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
-                                 vmm_eis=plan['vmm_eis'], vmm_chrono=plan['vmm_chrono'], n_chrono=nc, dop_range=dop_range,
-                                 vz_index=vz_index, vb_range=vb_range, vz_strength=plan.get('vz_strength'),
-                                 hybrid=(plan['data_type'] == 'hybrid'), hypers=self._c_hypers(opts),
-                                 want_pq=want_pq, eval_mat=self._eval_matrix(plan, diag_tau),
-                                 want_resid=diag_tau is not None, pfrt=pfrt, weight_factor_vec=wf_vec,
-                                 hybrid_wf=hybrid_wf)
-        plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
+        # host copies of the (small, shared) impedance matrices for predict_z: fetched before the fit is launched, so
+        # that nothing between the launch and the caller's first read of a result waits for the fit kernel
         if nf and not plan.get('multi'):
             plan['zm_drt_host'] = (plan['a_re'] + 1j * plan['a_im']).cpu().numpy()
             if self.fit_dop:
                 plan['zm_dop_host'] = plan['zm_dop_dev'].cpu().numpy()
+        c_hyp, eval_mat = self._c_hypers(opts), self._eval_matrix(plan, diag_tau)
+
+        def launch(out=None):
+            return eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
+                                      vmm_eis=plan['vmm_eis'], vmm_chrono=plan['vmm_chrono'], n_chrono=nc,
+                                      dop_range=dop_range, vz_index=vz_index, vb_range=vb_range,
+                                      vz_strength=plan.get('vz_strength'), hybrid=(plan['data_type'] == 'hybrid'),
+                                      hypers=c_hyp, want_pq=want_pq, eval_mat=eval_mat, want_resid=diag_tau is not None,
+                                      pfrt=pfrt, weight_factor_vec=wf_vec, hybrid_wf=hybrid_wf, out=out)
+        raw = launch()
+        plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         copied.synchronize()        # the pinned staging buffer may be refilled by the next call from here on
         rv_host = rv.copy() if want_pq else None
         if opts['solve_rp'] or opts['update_scale']:
@@ -1035,7 +1040,8 @@ class DRT:
             scales['dop_column_scale'] = sf[:, 2]          # dop_scale_vector /= dop_rescale_factor (drt1d.py:589-592)
             if rv_host is not None:
                 rv_host *= tot[:, None]
-        res = BatchFit(plan, raw, scales, dict(rv=rv_host, h2d_bytes=rv.nbytes))
+        # 'relaunch' repeats the fit kernel on the inputs already resident in HBM (bench.py times it)
+        res = BatchFit(plan, raw, scales, dict(rv=rv_host, h2d_bytes=rv.nbytes, relaunch=launch))
         self.last_batch = res
         self.fit_type = f"qphb_{plan['data_type']}"
         return res
