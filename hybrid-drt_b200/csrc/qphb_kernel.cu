@@ -1946,6 +1946,12 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(Tm<C>::kCols) : "memory");
 }
 
+}  // namespace hdrt
+
+#include "qphb_warp.cuh"
+
+namespace hdrt {
+
 __global__ void fp64_probe_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double m = 1.0000001, b = 1e-9;
@@ -2018,6 +2024,35 @@ static int launch_qphb(hdrt_handle* h, const hdrt_qphb_problem& p, size_t smem, 
     return HDRT_OK;
 }
 
+// Warp-per-spectrum form (qphb_warp.cuh): one CTA of four independent warps per SM.
+static constexpr size_t kMaxDynSmem = 227 * 1024;
+static bool warp_path_eligible(const hdrt_qphb_problem& p, bool ext) {
+    if (ext || p.n_cols > wk::NV || p.vz_index >= 0) return false;
+    if (const char* e = getenv("HDRT_QPHB_PATH")) { if (e[0] == 'c') return false; }      // dev knob: force the CTA kernel
+    return (size_t)wk::warp_doubles(p.n_rows) * 8 * 4 + 512 <= kMaxDynSmem;
+}
+
+static int launch_qphb_warp(hdrt_handle* h, const hdrt_qphb_problem& p, cudaStream_t st) {
+    const int stride = wk::warp_doubles(p.n_rows);
+    const size_t smem = (size_t)stride * 8 * 4;
+    HDRT_CUDA_CHECK(cudaFuncSetAttribute(wk::qphb_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HDRT_CUDA_CHECK(cudaFuncSetAttribute(wk::qphb_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int grid = h->sm_count;
+    if (grid > (p.batch + 3) / 4) grid = (p.batch + 3) / 4;
+    hdrt_launch_slot* sl;
+    {
+        std::lock_guard<std::mutex> lock(*static_cast<std::mutex*>(h->mu));
+        sl = &h->slots[h->launches++ % kLaunchSlots];
+        if (sl->used) HDRT_CUDA_CHECK(cudaStreamWaitEvent(st, sl->done, 0));
+        sl->used = true;
+        HDRT_CUDA_CHECK(cudaMemsetAsync(sl->work_counter, 0, sizeof(int), st));
+        wk::qphb_warp_kernel<<<grid, 128, smem, st>>>(p, sl->work_counter, stride);
+        HDRT_CUDA_CHECK(cudaGetLastError());
+        HDRT_CUDA_CHECK(cudaEventRecord(sl->done, st));
+    }
+    return HDRT_OK;
+}
+
 extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob, void* stream) {
     if (!h || !prob) { set_error("null handle or problem"); return HDRT_ERR_ARG; }
     const hdrt_qphb_problem& p = *prob;
@@ -2059,6 +2094,7 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
         set_error("init_weights_separately cannot be combined with outlier_p / solve_rp");
         return HDRT_ERR_UNSUPPORTED;
     }
+    if (warp_path_eligible(p, ext)) return launch_qphb_warp(h, p, st);
     if (small_cfg(p.n_cols)) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
     return ext ? launch_qphb<CfgLX>(h, p, (size_t)smem, st) : launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }
