@@ -203,7 +203,7 @@ def run_gpu(args):
 
     def step_resident():
         eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
-                           vmm_eis=plan['vmm_eis'], hypers=hyp, out=out)
+                           vmm_eis=plan['vmm_eis'], hypers=hyp, out=out, pen_hint=plan.get('pen_hint'))
 
     def step_e2e():
         r = drt.fit_eis_batch(freq, z)

@@ -21,15 +21,30 @@ void set_error(const char* fmt, ...);
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// 64-bit shuffles, low word first: the toolkit's double overloads move the high word first, which lands the halves in
+// the wrong registers of the destination pair and costs three LOP3 (an xor swap) per shuffle.
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(kFull, lo, m);
+    hi = __shfl_xor_sync(kFull, hi, m);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_idx_d(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(kFull, lo, src);
+    hi = __shfl_sync(kFull, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
     return v;
 }
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_xor_d(v, o));
     return v;
 }
 

@@ -201,14 +201,14 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ double reduce_q(double v) {
-    v += __shfl_xor_sync(kFull, v, 1);
-    v += __shfl_xor_sync(kFull, v, 2);
+    v += shfl_xor_d(v, 1);
+    v += shfl_xor_d(v, 2);
     return v;
 }
 __device__ __forceinline__ double reduce_g(double v) {
-    v += __shfl_xor_sync(kFull, v, 4);
-    v += __shfl_xor_sync(kFull, v, 8);
-    v += __shfl_xor_sync(kFull, v, 16);
+    v += shfl_xor_d(v, 4);
+    v += shfl_xor_d(v, 8);
+    v += shfl_xor_d(v, 16);
     return v;
 }
 
@@ -563,11 +563,11 @@ __device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, int 
     for (int cc = 0; cc < 7; ++cc) {
         const int h = cc >> 1;
         const double colv = (cc & 1) ? m1 : m0;                      // column cc of the own row, where q == h
-        const double agc = __shfl_sync(kFull, colv, 4 * g + h);      // M[g][cc]
-        const double piv = __shfl_sync(kFull, colv, 4 * cc + h);     // M[cc][cc]
+        const double agc = shfl_idx_d(colv, 4 * g + h);      // M[g][cc]
+        const double piv = shfl_idx_d(colv, 4 * cc + h);     // M[cc][cc]
         const int src = 4 * cc + q;                                  // row cc
-        const double r0 = __shfl_sync(kFull, m0, src), r1 = __shfl_sync(kFull, m1, src);
-        const double r2 = __shfl_sync(kFull, m2, src), r3 = __shfl_sync(kFull, m3, src);
+        const double r0 = shfl_idx_d(m0, src), r1 = shfl_idx_d(m1, src);
+        const double r2 = shfl_idx_d(m2, src), r3 = shfl_idx_d(m3, src);
         // f = -agc / piv with the reciprocal folded in: y0 = rcp seed, e = 1 - piv y0, 1 / piv = y0 (1 + e + e^2 + O(e^3))
         double y0;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(piv));
@@ -580,7 +580,7 @@ __device__ __forceinline__ bool diag_factor(const double2 s, unsigned binv, int 
         m2 = fma(f, r2, m2);
         m3 = fma(f, r3, m3);
     }
-    const double dg = __shfl_sync(kFull, (g & 1) ? m1 : m0, 4 * g + (g >> 1));   // d_g = M[g][g]
+    const double dg = shfl_idx_d((g & 1) ? m1 : m0, 4 * g + (g >> 1));   // d_g = M[g][g]
     const bool ok = __all_sync(kFull, (dg > 0.0) && (dg < INFINITY));
     const double rinv = fast_rsqrt(dg);
     m2 *= rinv;

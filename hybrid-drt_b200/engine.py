@@ -60,6 +60,7 @@ class Problem(C.Structure):
         ('n_pfrt', C.c_int), ('pfrt_max_iter', C.c_int), ('pfrt_min_iter', C.c_int), ('pfrt_factors', _P),
         ('pfrt_x', _P), ('pfrt_llh', _P), ('pfrt_p', _P), ('pfrt_iters', _P), ('hybrid_wf_in', _P), ('hybrid_wf_out', _P), ('x_overfit_eis', _P),
         ('weight_factor_vec', _P), ('vz_scratch', _P),
+        ('pen_toeplitz', _P), ('pen_band', C.c_int),
     ]
 
 
@@ -310,7 +311,7 @@ class Engine:
     def qphb_fit_batch(self, rm, rv, pen, h, l1, n_special, vmm_eis=None, vmm_chrono=None, n_chrono=0,
                        dop_range=None, vz_index=-1, vb_range=(-1, -1), vz_strength=None, hybrid=False,
                        hypers=None, want_pq=False, out=None, eval_mat=None, want_resid=False, pfrt=None,
-                       weight_factor_vec=None, hybrid_wf=None):
+                       weight_factor_vec=None, hybrid_wf=None, pen_hint=None):
         """Launch the batched QPHB solver.  All inputs are device float64 tensors.
 
         rm [N,n] (shared) or [B,N,n]; rv [B,N]; pen [3,n,n] or [B,3,n,n]; h, l1 [n].
@@ -345,6 +346,10 @@ class Engine:
         if vmm_chrono is not None:
             p.vmm_chrono, p.vmm_chrono_stride = _ptr(vmm_chrono), (n_chrono ** 2 if vmm_chrono.dim() == 3 else 0)
         p.pen, p.pen_stride = _ptr(pen), (3 * n * n if pen.dim() == 4 else 0)
+        if pen_hint is not None and pen.dim() == 3:     # (first rows [3, n - n_special], band) from penalty_hint
+            tz, band = pen_hint
+            assert tz.is_cuda and tz.dtype == torch.float64 and tz.is_contiguous() and tuple(tz.shape) == (3, n - int(n_special))
+            p.pen_toeplitz, p.pen_band = _ptr(tz), int(band)
         p.h, p.l1 = _ptr(h), _ptr(l1)
         p.vz_strength = _ptr(vz_strength)
         p.hyp = hyp
@@ -404,6 +409,24 @@ class Engine:
         self._check(self.lib.hdrt_qphb_fit_batch(self.handle, C.byref(p), self._stream()))
         self.launches += 1
         return o
+
+    def penalty_hint(self, pen, n_special):
+        """Structure hint for the fit kernel (pen_toeplitz / pen_band of the ABI): when the DRT block of every penalty
+        matrix in `pen` [3, n, n] is an exactly symmetric Toeplitz matrix, returns (first rows [3, nb] on the device,
+        band), band = the largest |i - j| whose entry reaches 1e-45 of the largest one; otherwise None."""
+        if pen.dim() != 3:
+            return None
+        blk = pen[:, n_special:, n_special:]
+        nb = blk.shape[-1]
+        if nb < 2:
+            return None
+        toep = bool(torch.equal(blk[:, 1:, 1:], blk[:, :-1, :-1])) and bool(torch.equal(blk, blk.transpose(1, 2)))
+        if not toep:
+            return None
+        tz = blk[:, 0, :].contiguous()
+        a = tz.abs().cpu().numpy()
+        big = np.nonzero(a >= 1e-45 * a.max(axis=1, keepdims=True))[1]
+        return tz, int(big.max()) if len(big) else 0
 
     def probe_fp64(self):
         """Achieved DFMA TFLOP/s of this GPU (register-resident FMA loop on every SM)."""

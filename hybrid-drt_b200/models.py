@@ -649,6 +649,7 @@ class DRT:
             m_dop = eng.build_penalty(self.basis_nu[None], self.nu_epsilon, is_uniform(self.basis_nu))[0]
             pen[:, dop_a:dop_b, dop_a:dop_b] = m_dop
         plan['pen'] = pen
+        plan['pen_hint'] = eng.penalty_hint(pen, ns) if not self.fit_dop else None
         plan['rm'] = rm
 
         # ---- variance-estimation matrices, drt1d.py:614-636
@@ -1022,7 +1023,8 @@ class DRT:
                                       dop_range=dop_range, vz_index=vz_index, vb_range=vb_range,
                                       vz_strength=plan.get('vz_strength'), hybrid=(plan['data_type'] == 'hybrid'),
                                       hypers=c_hyp, want_pq=want_pq, eval_mat=eval_mat, want_resid=diag_tau is not None,
-                                      pfrt=pfrt, weight_factor_vec=wf_vec, hybrid_wf=hybrid_wf, out=out)
+                                      pfrt=pfrt, weight_factor_vec=wf_vec, hybrid_wf=hybrid_wf, out=out,
+                                      pen_hint=plan.get('pen_hint'))
         raw = launch()
         plan['diag_tau'] = None if diag_tau is None else np.asarray(diag_tau, dtype=float)
         copied.synchronize()        # the pinned staging buffer may be refilled by the next call from here on

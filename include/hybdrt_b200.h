@@ -231,6 +231,13 @@ typedef struct hdrt_qphb_problem {
     double* vz_scratch;         /* [batch][N] work buffer: the vz_offset column a continuation step starts from
                                                           (drt1d.py:1296-1302); required iff n_pfrt > 1 and
                                                           vz_index >= 0                                            */
+    const double* pen_toeplitz; /* optional hint, [3][n_cols - n_special], shared by the batch: when the DRT block of every
+                                   m_k is an exactly symmetric Toeplitz matrix (a uniform ln(tau) grid of Gaussians builds
+                                   them that way, mat1d.py:125-209, basis.py:382-395) these are its first rows, and
+                                   pen_band is the distance |i - j| beyond which every entry is below 1e-45 of the
+                                   largest one.  The kernel may then take the entries of the block from these rows
+                                   instead of from pen (which must still be complete).  NULL = no hint.            */
+    int pen_band;
 } hdrt_qphb_problem;
 
 /* Fills `hyp` with the reference defaults (qphb.py:208-255 eff_hp=True, drt1d.py:102-137). */
