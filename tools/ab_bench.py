@@ -27,7 +27,7 @@ for rep in range(2):
         hyp = drt._c_hypers(plan['opts'])
         out = {}
         def step():
-            eng.qphb_fit_batch(plan['rm'], rv, plan['pen'], plan['h'], plan['l1'], plan['n_special'], vmm_eis=plan['vmm_eis'], hypers=hyp, out=out)
+            eng.qphb_fit_batch(plan['rm'], rv, plan['pen'], plan['h'], plan['l1'], plan['n_special'], vmm_eis=plan['vmm_eis'], hypers=hyp, out=out, pen_hint=plan.get('pen_hint'))
         step(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
