@@ -99,22 +99,88 @@ def _cpu_init(freq):
 
 def _cpu_fit(z):
     res = _WORKER['prep'].fit(z)
-    return res['n_outer'], int(res['ipm_iters'].sum())
+    return res['n_outer'], int(res['ipm_iters'].sum()), np.asarray(res['x'], dtype=np.float64)
+
+
+def parity_summary(cpu_out, x_gpu, n_outer_gpu, n_ipm_gpu):
+    """The CPU oracle against the kernel on the same spectra (scaled space): fraction of spectra whose coefficient
+    vector agrees within 1e-6 (norm-wise relative, SURVEY.md section 7 hard part 1), outer / interior-point iteration
+    count mismatches, and the offenders."""
+    n = len(cpu_out)
+    rel = np.empty(n)
+    out_mis, ipm_mis = [], []
+    for i, (no, ni, x) in enumerate(cpu_out):
+        rel[i] = np.max(np.abs(x_gpu[i] - x)) / np.max(np.abs(x))
+        if int(no) != int(n_outer_gpu[i]):
+            out_mis.append(i)
+        if int(ni) != int(n_ipm_gpu[i]):
+            ipm_mis.append(i)
+    worst = np.argsort(-rel)[:5]
+    return {'n': n, 'frac_x_within_1e-6': float(np.mean(rel <= 1e-6)), 'n_outer_mismatch': len(out_mis),
+            'n_ipm_mismatch': len(ipm_mis), 'worst_rel': float(rel.max()), 'median_rel': float(np.median(rel)),
+            'worst_spectra': [{'index': int(i), 'rel': float(rel[i])} for i in worst if rel[i] > 1e-6],
+            'outer_mismatch_spectra': out_mis[:10], 'ipm_mismatch_spectra': ipm_mis[:10],
+            'against': 'oracle/drt_oracle.py (numpy restatement + coneqp restatement) on the first n spectra of the batch'}
+
+
+REF_ROOT = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def _ref_init(freq):
+    """Worker of the reference arm: the UNMODIFIED reference package installed under baseline/_ref (pip --no-deps),
+    imported on top of oracle/refshim.py (stubs for its absent plotting / file-format dependencies; cvxopt.solvers.qp
+    -> the coneqp restatement).  One DRT() per worker, as BASELINE.md section 3 prescribes."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import refshim
+    refshim.install(REF_ROOT)
+    t0 = time.perf_counter()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints while it builds its lookup tables
+        from hybdrt.models import DRT
+        drt = DRT()
+    _WORKER['ref_drt'] = drt
+    _WORKER['ref_freq'] = np.asarray(freq, dtype=float)
+    _WORKER['ref_setup_s'] = time.perf_counter() - t0
+
+
+def _ref_fit(z):
+    drt = _WORKER['ref_drt']
+    drt.fit_eis(_WORKER['ref_freq'], z)
+    hist = drt.qphb_history
+    return (len(hist), int(sum(e['cvx_result']['iterations'] for e in hist)),
+            np.asarray(drt.cvx_result['x'], dtype=np.float64).ravel())
+
+
+def _ref_setup(_):
+    return _WORKER['ref_setup_s']
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_ROOT, 'hybdrt'))
 
 
 class CpuPool:
     """One worker process per core, each holding its own EisPrep (lookup tables built once per worker, as
     DRT() construction does in the reference; excluded from the timing)."""
 
-    def __init__(self, freq, cores):
+    def __init__(self, freq, cores, reference=False):
         import multiprocessing as mp
         self.cores = cores
-        self.pool = mp.get_context('spawn').Pool(cores, initializer=_cpu_init, initargs=(freq,))
+        self.fit = _ref_fit if reference else _cpu_fit
+        self.pool = mp.get_context('spawn').Pool(cores, initializer=_ref_init if reference else _cpu_init, initargs=(freq,))
+        self.setup_s = float(np.mean(self.pool.map(_ref_setup, range(cores)))) if reference else None
 
     def fits_per_second(self, z):
-        self.pool.map(_cpu_fit, list(z[:self.cores]))      # touch every worker (imports, tables)
+        self.pool.map(self.fit, list(z[:self.cores]))      # touch every worker (imports, tables)
         t0 = time.perf_counter()
-        out = self.pool.map(_cpu_fit, list(z), chunksize=max(1, len(z) // (self.cores * 8)))
+        out = self.pool.map(self.fit, list(z), chunksize=max(1, len(z) // (self.cores * 8)))
         dt = time.perf_counter() - t0
         return len(z) / dt, dt, out
 
@@ -131,35 +197,166 @@ def host_cores():
 
 
 def run_reference(args):
+    """CPU arm.  The unmodified reference (baseline/_ref, under the import shim) on every host core when it is
+    installed; the oracle port otherwise.  Every step fits the same fixed sample: the first n spectra of the seeded
+    C2 batch the GPU arm fits."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from hybdrt_b200 import synth
     cores = host_cores()
-    n_sample = int(min(BATCH_PER_GPU, max(64, 64 * cores)))
+    use_ref = reference_available() and not args.port
+    n_sample = int(min(BATCH_PER_GPU, max(64, (16 if use_ref else 64) * cores)))
     freq, z = synth.make_eis_batch(BATCH_PER_GPU, seed=0)
     z = z[:n_sample]
     vals = []
-    pool = CpuPool(freq, cores)
+    pool = CpuPool(freq, cores, reference=use_ref)
+    out = []
     for i in range(args.warmup + args.steps):
-        v, dt, _ = pool.fits_per_second(z)
+        v, dt, out = pool.fits_per_second(z)
         if i >= args.warmup:
             vals.append((v, dt))
+    setup_s = pool.setup_s
     pool.close()
     value = float(np.mean([v for v, _ in vals]))
+    if use_ref:
+        kind = 'reference'
+        how = (f'the unmodified reference package (baseline/_ref, pip --no-deps) under oracle/refshim.py: DRT().fit_eis per '
+               f'spectrum, one DRT() per worker process ({setup_s:.2f} s construction incl. lookup tables, not timed), BLAS '
+               f'threads = 1; cvxopt is not installable here: cvxopt.solvers.qp = the coneqp restatement (oracle/coneqp.py)')
+    else:
+        kind = 'port'
+        how = ('numpy oracle (oracle/drt_oracle.py), one process per core, BLAS threads = 1; QP = coneqp restatement '
+               '(cvxopt not installable)')
     line = {
         'impl': 'reference', 'metric': 'DRT fits/sec (70f x 101 basis, hierarchical-Bayes, FP64)', 'value': value,
         'unit': 'fits/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': float(np.mean([dt for _, dt in vals]) * 1e3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'C2: 10,000 synthetic 2-ZARC EIS spectra, 70 freqs x 101 RBF basis, DRT() defaults',
-                   'sample': f'{n_sample} of the 10,000 spectra per step'},
-        'cpu_baseline': {'value': value, 'unit': 'fits/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{n_sample} spectra of the same batch; numpy oracle (oracle/drt_oracle.py), one process '
-                                   f'per core, BLAS threads = 1; QP = coneqp restatement (cvxopt not installable)'},
+                   'sample': f'the first {n_sample} of the 10,000 spectra, every step',
+                   'mean_outer_iters': float(np.mean([o[0] for o in out])), 'mean_ipm_iters': float(np.mean([o[1] for o in out]))},
+        'cpu_baseline': {'value': value, 'unit': 'fits/s', 'cores': cores, 'kind': kind,
+                         'sample': f'first {n_sample} spectra of the seeded C2 batch; {how}'},
         'e2e': {'value': value, 'unit': 'fits/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
+
+
+def other_configs(eng, fp64_peak, flush):
+    """BASELINE configs C3 (hybrid) and C4 (DRT+DOP) at full size: the fit kernel re-launched on the inputs already
+    resident in HBM (the launch the public API made), CUDA events, FP64 roofline fraction from the same flop model."""
+    import torch
+    from hybdrt_b200 import synth
+    from hybdrt_b200.models import DRT
+    res = {}
+
+    def measure(name, fit, workload):
+        r = fit()
+        torch.cuda.synchronize()
+        relaunch, raw = r.extra['relaunch'], {}
+        relaunch(raw)
+        ms = []
+        for k in range(3):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            relaunch(raw)
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        n_outer = raw['n_outer'].cpu().numpy().astype(np.float64)
+        n_ipm = raw['n_ipm'].cpu().numpy().astype(np.float64)
+        plan = r.plan
+        flops = fit_flops(plan['n_rows'], plan['n'], plan['n'] - plan['n_special'], n_outer, n_ipm)
+        sec = float(np.mean(ms)) * 1e-3
+        nb = len(n_outer)
+        res[name] = {'workload': workload, 'fits_per_s': nb / sec, 'ms_per_launch': sec * 1e3, 'n_rows': plan['n_rows'],
+                     'n_cols': plan['n'], 'mean_outer_iters': float(n_outer.mean()), 'mean_ipm_iters': float(n_ipm.mean()),
+                     'frac_converged': float(np.mean((raw['status'].cpu().numpy() & 1) > 0)),
+                     'roofline': {'bound': 'fp64', 'achieved': flops / sec / 1e12, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                                  'frac': flops / sec / 1e12 / fp64_peak, 'flops_per_launch': flops}}
+
+    times, i_sig, v, freq3, z3 = synth.make_hybrid_batch(4096, seed=1)
+    d3 = DRT()
+    measure('C3', lambda: d3.fit_hybrid_batch(times, i_sig, v, freq3, z3),
+            '4096 hybrid fits: 2000-sample chrono step response + 30 high-frequency EIS points each')
+    del d3
+    freq4, z4 = synth.make_dop_batch(10000, seed=2)
+    d4 = DRT(fit_dop=True)
+    measure('C4', lambda: d4.fit_eis_batch(freq4, z4), '10000 DRT+DOP fits, 70 frequencies')
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# C5: the 256 x 256 map through DRTMD, sharded over the ranks (strong scaling), result gather inside the timed region
+# ---------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as graft
+    graft.build()
+    from hybdrt_b200 import engine as E, synth
+    from hybdrt_b200.mapping import DRTMD
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    eng = E.get_engine(local)
+    rows = cols = args.map_size
+    freq, z = synth.make_map_batch(rows, cols, seed=3)
+    psi = np.array([(r, c) for r in range(rows) for c in range(cols)], dtype=float)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        md = DRTMD(tau_supergrid=np.logspace(-8, 3, 111), psi_dim_names=['row', 'col'], print_progress=False, device=local)
+        md.add_observations(psi, freq, z)
+        md.fit_all(ignore_errors=True, shard=world > 1)       # every rank ends with the full map (all-gather over NCCL)
+        return md
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        md = step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = eng.launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        md = step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=eng.device)
+    launches = eng.launches - launches0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    total_s = float(dt.item())
+    n_obs = rows * cols
+    value = n_obs * args.steps / total_s
+    if rank == 0:
+        per_obs = (md.obs_x.shape[-1] + md.obs_drt_var.shape[-1] + 6) * 8
+        line = {
+            'metric': 'DRT fits/sec (70f x 101 basis, hierarchical-Bayes, FP64)', 'value': value, 'unit': 'fits/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_s / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'C5: {rows} x {cols} map of synthetic 2-ZARC spectra through DRTMD.fit_all (fit + '
+                                   f'distribution variance + llh + rss per observation), interleaved shards, results '
+                                   f'all-gathered over NCCL inside the timed region', 'observations': n_obs,
+                       'fitted': int(md.obs_fit_status.sum()), 'mean_outer_iters': float(md.obs_outer_iterations.mean()),
+                       'timing': 'host wall clock around fit_all + barrier, max over ranks (host buffers in, host arrays out)'},
+            'e2e': {'value': value, 'unit': 'fits/s', 'h2d_bytes_per_step': int(z.shape[1] * 16 * n_obs // world),
+                    'd2h_bytes_per_step': int(per_obs * n_obs // world)},
+            'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -205,9 +402,13 @@ def run_gpu(args):
         eng.qphb_fit_batch(plan['rm'], rv_dev, plan['pen'], plan['h'], plan['l1'], plan['n_special'],
                            vmm_eis=plan['vmm_eis'], hypers=hyp, out=out, pen_hint=plan.get('pen_hint'))
 
+    from hybdrt_b200 import sharding
+
     def step_e2e():
         r = drt.fit_eis_batch(freq, z)
         fp = r.fit_parameters()                             # D2H of x and weights + unscaling on the host
+        if world > 1:                                       # the path's only collective: results to rank 0 (NCCL)
+            sharding.gather_results({'x': r.raw['x'], 'weights': r.raw['weights']}, world * B, dst=0)
         return r, fp
 
     for _ in range(args.warmup):
@@ -328,16 +529,28 @@ def run_gpu(args):
             except Exception:
                 traffic = None
 
-        cpu = None
+        cpu = parity = None
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()
-            n_sample = int(min(B, max(64, 48 * cores)))
+            n_sample = int(min(B, max(1024, 96 * cores)))
             pool = CpuPool(freq, cores)
-            v, dt, _ = pool.fits_per_second(z[:n_sample])
+            v, dt, cpu_out = pool.fits_per_second(z[:n_sample])
             pool.close()
             cpu = {'value': v, 'unit': 'fits/s', 'cores': cores, 'kind': 'port',
                    'sample': f'first {n_sample} spectra of the same batch ({dt:.1f} s); numpy oracle, one process per core, '
                              f'BLAS threads = 1; QP = coneqp restatement (cvxopt not installable here)'}
+            parity = parity_summary(cpu_out, out['x'][:n_sample].cpu().numpy(), n_outer[:n_sample], n_ipm[:n_sample])
+            if reference_available():      # second figure: the unmodified reference under the import shim, small sample
+                n_ref = int(min(B, 8 * cores))
+                rpool = CpuPool(freq, cores, reference=True)
+                rv_, rdt, rout = rpool.fits_per_second(z[:n_ref])
+                rpool.close()
+                rpar = parity_summary(rout, out['x'][:n_ref].cpu().numpy(), n_outer[:n_ref], n_ipm[:n_ref])
+                cpu['reference_shim'] = {'value': rv_, 'unit': 'fits/s', 'cores': cores, 'kind': 'reference',
+                                         'sample': f'first {n_ref} spectra ({rdt:.1f} s): unmodified reference package '
+                                                   f'(baseline/_ref) under oracle/refshim.py, one DRT() per worker',
+                                         'parity_vs_kernel': {k: rpar[k] for k in ('n', 'frac_x_within_1e-6', 'n_outer_mismatch',
+                                                                                    'worst_rel')}}
 
         achieved = flops / kernel_s / 1e12
         line = {
@@ -354,7 +567,10 @@ def run_gpu(args):
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / fp64_peak, 'traffic': traffic, 'kernel': 'qphb_kernel (DMMA.8x8x4 + DFMA)',
+                         'frac': achieved / fp64_peak, 'traffic': traffic,
+                         'traffic_source': 'static: ncu dram bytes per fit of profiles/qphb_traffic.json x this batch '
+                                           '(not a same-run counter)',
+                         'kernel': 'qphb_warp_kernel (DMMA.8x8x4 + DFMA, one warp per spectrum)',
                          'peak_source': 'measured in this run: register-resident DFMA loop on every SM '
                                         '(MEASURED_PEAKS.json has no FP64 entry)',
                          'flops_per_launch': flops},
@@ -369,6 +585,8 @@ def run_gpu(args):
                                        'workload': f'{n_tr} raw traces x {len(rt)} samples -> {len(dec)} kept samples each '
                                                    f'(downsample_data, decimation_interval=8, factor 2)'},
             'cpu_baseline': cpu,
+            'parity': parity,
+            'configs': other_configs(eng, fp64_peak, flush) if (world == 1 and not args.no_configs) else None,
         }
         print(json.dumps(line))
     if world > 1:
@@ -383,11 +601,18 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='spectra per GPU (default: the C2 workload)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--port', action='store_true', help='--impl reference: time the oracle port even if baseline/_ref exists')
+    ap.add_argument('--no-configs', action='store_true', help='skip the C3 / C4 measurements of the default line')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c5'],
+                    help='c2: weak-scaled batch of 10,000 spectra per GPU (default); c5: 256 x 256 map, strong scaling')
+    ap.add_argument('--map-size', type=int, default=256)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 'c5':
+        run_c5(args)
     else:
         run_gpu(args)
 

@@ -889,3 +889,153 @@ def test_full_size_c3_c4_c5_properties():
     md2.fit_all()
     assert np.array_equal(md2.obs_x, md.obs_x[pick])
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# Parity at scale (hard part 1): the kernel against the CPU oracle on >= 1,024 C2 spectra and
+# on >= 64 spectra of the hybrid (C3) and DRT + DOP (C4) configurations -- fraction of spectra within 1e-6, outer and
+# interior-point iteration counts per spectrum, offenders listed by index.  The oracle runs in a process pool on
+# the matrices of the kernel's own plan (the matrices themselves are pinned at 1e-10 above).
+# ---------------------------------------------------------------------------------------------------
+_POOL = {}
+
+
+def _pool_init(prob):
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    _POOL['prob'] = prob
+
+
+def _pool_fit(rv):
+    from oracle import drt_oracle
+    prob = dict(_POOL['prob'])
+    prob['rv'] = rv
+    res = drt_oracle.qphb_fit(prob, prob.pop('hypers', None))
+    return res['n_outer'], int(np.sum(res['ipm_iters'])), np.asarray(res['x'], dtype=float)
+
+
+def _oracle_pool_fits(prob, rvs):
+    import multiprocessing as mp
+    import os
+    cores = max(1, min(32, len(os.sched_getaffinity(0))))
+    with mp.get_context('spawn').Pool(cores, initializer=_pool_init, initargs=(prob,)) as pool:
+        return pool.map(_pool_fit, list(rvs), chunksize=max(1, len(rvs) // (cores * 4)))
+
+
+def _parity_report(ref, h, tag, min_frac=1.0):
+    rel = np.array([np.max(np.abs(h['x'][i] - r[2])) / np.max(np.abs(r[2])) for i, r in enumerate(ref)])
+    outer_bad = [i for i, r in enumerate(ref) if int(r[0]) != int(h['n_outer'][i])]
+    ipm_bad = [i for i, r in enumerate(ref) if int(r[1]) != int(h['n_ipm'][i])]
+    frac = float(np.mean(rel <= FIT_TOL))
+    print(f'{tag}: n = {len(ref)}, fraction within 1e-6 = {frac:.4f}, worst rel = {rel.max():.3e} (spectrum {int(np.argmax(rel))}), '
+          f'outer-iteration mismatches {outer_bad[:10]}, interior-point mismatches {ipm_bad[:10]}')
+    assert not outer_bad, (tag, 'outer iteration counts differ', outer_bad[:10])
+    assert not ipm_bad, (tag, 'interior-point iteration counts differ', ipm_bad[:10])
+    assert frac >= min_frac, (tag, frac, [(int(i), float(rel[i])) for i in np.argsort(-rel)[:5]])
+
+
+def test_parity_at_scale_c2():
+    from hybdrt_b200 import synth
+    from hybdrt_b200.models import DRT
+    n = 1024
+    freq, z = synth.make_eis_batch(10000, seed=0)
+    drt = DRT()
+    res = drt.fit_eis_batch(freq, z[:n])
+    h = res.host(['x', 'n_outer', 'n_ipm'])
+    plan = res.plan
+    prob = dict(rm=_np(plan['rm']), vmm=_np(plan['vmm_eis']), pen=list(_np(plan['pen'])), h=_np(plan['h']), l1=_np(plan['l1']),
+                n_special=plan['n_special'])
+    zs = z[:n] / res.scales['coefficient_scale'][:, None]
+    ref = _oracle_pool_fits(prob, np.concatenate([zs.real, zs.imag], axis=1))
+    _parity_report(ref, h, 'C2 (70 f x 101 basis)')
+
+
+def test_parity_at_scale_c3_c4():
+    from hybdrt_b200 import synth
+    from hybdrt_b200.models import DRT
+    n = 64
+    # ---- C3: hybrid fits, 2,000 chrono samples + 30 frequencies, vz_offset column rewritten every iteration
+    t, i_sig, v, f, z = synth.make_hybrid_batch(n, seed=1)
+    drt = DRT()
+    res = drt.fit_hybrid_batch(t, i_sig, v, f, z)
+    h = res.host(['x', 'n_outer', 'n_ipm'])
+    plan = res.plan
+    nc = plan['n_chrono']
+    sp = plan['special_qp_params']
+    hyp = drt._c_hypers(plan['opts'])
+    prob = dict(rm=_np(plan['rm']), vmm=dict(n_chrono=nc, chrono=None, eis=_np(plan['vmm_eis'])), pen=list(_np(plan['pen'])),
+                h=_np(plan['h']), l1=_np(plan['l1']), n_special=plan['n_special'], n_chrono=nc,
+                vz_index=sp['vz_offset']['index'], vb_range=drt.get_special_indices('v_baseline'),
+                vz_strength=plan['vz_strength_host'], chrono_weight_factor=float(hyp.chrono_weight_factor),
+                eis_weight_factor=float(hyp.eis_weight_factor))
+    prob['rm'][:, prob['vz_index']] = 0.0
+    ref = _oracle_pool_fits(prob, _np(res.extra['rv_dev']))
+    _parity_report(ref, h, 'C3 (hybrid, N = 2060)')
+    # ---- C4: DRT + DOP, n = 153
+    f4, z4 = synth.make_dop_batch(n, seed=2)
+    dd = DRT(fit_dop=True)
+    res = dd.fit_eis_batch(f4, z4)
+    h = res.host(['x', 'n_outer', 'n_ipm'])
+    plan = res.plan
+    prob = dict(rm=_np(plan['rm']), vmm=_np(plan['vmm_eis']), pen=list(_np(plan['pen'])), h=_np(plan['h']), l1=_np(plan['l1']),
+                n_special=plan['n_special'], dop_range=dd.get_special_indices('x_dop'))
+    zs = z4 / res.scales['coefficient_scale'][:, None]
+    ref = _oracle_pool_fits(prob, np.concatenate([zs.real, zs.imag], axis=1))
+    _parity_report(ref, h, 'C4 (DRT + DOP, n = 153)')
+
+
+# ---------------------------------------------------------------------------------------------------
+# Multi-GPU: a map fitted through DRTMD.fit_all(shard=True) on two ranks (NCCL gather of the results) equals the
+# single-rank result.  Needs two GPUs; the host logic alone is covered with gloo in tests/test_sharding.py.
+# ---------------------------------------------------------------------------------------------------
+def _map_worker(rank, ws, port, q):
+    import os
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=ws, device_id=torch.device('cuda', rank))
+    try:
+        from hybdrt_b200 import synth
+        from hybdrt_b200.mapping import DRTMD
+        rows, cols = 12, 11
+        f, z = synth.make_map_batch(rows, cols, seed=3)
+        psi = np.array([(r, c) for r in range(rows) for c in range(cols)], dtype=float)
+        md = DRTMD(tau_supergrid=np.logspace(-8, 3, 111), psi_dim_names=['row', 'col'], print_progress=False, device=rank)
+        md.add_observations(psi, f, z)
+        md.fit_all(shard=True)
+        q.put((rank, md.obs_x.copy(), md.obs_drt_var.copy(), md.obs_llh.copy(), md.obs_outer_iterations.copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_map_on_two_gpus_equals_single_rank():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (run with gpurun --gpus 2)')
+    import socket
+    import torch.multiprocessing as mp
+    from hybdrt_b200 import synth
+    from hybdrt_b200.mapping import DRTMD
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_map_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+    rows, cols = 12, 11
+    f, z = synth.make_map_batch(rows, cols, seed=3)
+    psi = np.array([(r, c) for r in range(rows) for c in range(cols)], dtype=float)
+    md = DRTMD(tau_supergrid=np.logspace(-8, 3, 111), psi_dim_names=['row', 'col'], print_progress=False)
+    md.add_observations(psi, f, z)
+    md.fit_all()
+    for rank, x, var, llh, outer in got:
+        assert np.array_equal(x, md.obs_x) and np.array_equal(var, md.obs_drt_var), rank
+        assert np.array_equal(llh, md.obs_llh) and np.array_equal(outer, md.obs_outer_iterations), rank
