@@ -1806,6 +1806,28 @@ __device__ __forceinline__ void fit_one(const hdrt_qphb_problem& p, int b, Ctx& 
             // ---- outputs of the fit proper (before the optional calculate_pq pass rescales c.w)
             if (p.weights) for (int r = tid; r < N; r += C::kThreads) p.weights[(size_t)b * N + r] = C::roww()[r];
             if (p.resid_ss && !cont) {   // sum of squared residuals of the final x per domain (evaluate_rss / evaluate_llh)
+                if (c.vz >= 0) {
+                    // the reference evaluates them with the design matrix whose vz_offset column has already been
+                    // rewritten from this x (drt1d.py:972-979, 4433-4496); the last weights pass used the previous column
+                    const int lane = tid & 31, warp = tid >> 5;
+                    const double* xs = C::vec(C::XS);
+                    __syncthreads();
+                    for (int r = warp; r < N; r += C::kWarps) {
+                        const double* __restrict__ src = c.rm + (size_t)r * n;
+                        double acc = 0.0;
+                        for (int col = lane; col < n; col += 32) {
+                            double xv = xs[col];
+                            if (C::EXT && col >= c.dop_a && col < c.dop_b) xv *= c.dop_cs;
+                            acc += ((col == c.vz) ? c.vzcol[r] : src[col]) * xv;
+                        }
+                        acc = warp_sum(acc);
+                        if (lane == 0) {
+                            const double resid = acc - (C::EXT ? c.rv[r] * c.rv_scale : c.rv[r]);
+                            C::rowr2(c.N)[r] = resid * resid;
+                        }
+                    }
+                    __syncthreads();
+                }
                 double t2[2] = {0.0, 0.0};
                 for (int r = tid; r < N; r += C::kThreads) {
                     if (r < c.nc) t2[0] += C::rowr2(c.N)[r]; else t2[1] += C::rowr2(c.N)[r];

@@ -295,8 +295,9 @@ class DRTMD:
         good = members[~bad]
         self.obs_x[good] = 0.0
         self.obs_x[good, ..., left:right] = out['x'][~bad]
-        for key in sp_keys:
-            self.obs_special[key][good] = out['sp_' + key][~bad]
+        for key in sp_keys:       # a vector parameter of size one (v_baseline with a single step) is stored as a scalar per observation
+            val = out['sp_' + key][~bad]
+            self.obs_special[key][good] = val.reshape((len(val), *self.special_param_shape(key)))
         dv = out['drt_var'][~bad]                               # of the initial fit; one row per factor (drtmd.py:270)
         self.obs_drt_var[good] = dv[:, None, :] if self.fit_type == 'pfrt' else dv
         self.obs_llh[good] = out['llh'][~bad]

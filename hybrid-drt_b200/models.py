@@ -657,7 +657,9 @@ class DRT:
         if times is not None and kw['chrono_error_structure'] != 'uniform':
             if kw['chrono_error_structure'] is not None:
                 raise ValueError(f"Invalid error structure {kw['chrono_error_structure']}")
-            plan['vmm_chrono'] = eng.build_chrono_vmm(times[None], self.step_times[None],
+            # the decorrelation blocks follow the NON-consecutive steps (drt1d.py:616): a finite-rise step made of
+            # consecutive samples is one block, not several
+            plan['vmm_chrono'] = eng.build_chrono_vmm(times[None], np.asarray(self.nonconsec_step_times, dtype=float)[None],
                                                       kw['chrono_vmm_epsilon'])[0]
         if frequencies is not None:
             es = kw['eis_error_structure']

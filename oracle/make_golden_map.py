@@ -38,6 +38,8 @@ def main():
     for key, val in md.obs_special.items():
         out['special_' + key] = np.asarray(val)
     path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_small.npz')
+    if '--hybrid-only' in sys.argv:
+        return hybrid_map(supergrid)
     if '--pfrt-only' not in sys.argv:
         np.savez_compressed(path, **out)
         print('wrote', path, {k: np.shape(v) for k, v in out.items()})
@@ -55,6 +57,26 @@ def main():
     path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_pfrt.npz')
     np.savez_compressed(path, **outp)
     print('wrote', path, {k: np.shape(v) for k, v in outp.items()})
+    hybrid_map(supergrid)
+
+
+def hybrid_map(supergrid):
+    """Hybrid observations (chrono + EIS): obs_llh / obs_rss are evaluated with the design matrix whose vz_offset column
+    has been rewritten from the final coefficients (drt1d.py:972-979, 4433-4496)."""
+    times = np.concatenate([np.linspace(-0.01, -1e-4, 25), np.logspace(-4, 0, 220)])
+    t, i_sig, v, freq, z = synth.make_hybrid_batch(3, times=times, seed=11)
+    mh = DRTMD(tau_supergrid=supergrid, psi_dim_names=['k'], print_progress=False)
+    for b in range(3):
+        mh.add_observation([float(b)], (t, i_sig, v[b]), (freq, z[b]))
+    mh.fit_all()
+    assert mh.obs_fit_status.all()
+    outh = dict(times=t, i_signal=i_sig, v=v, freq=freq, z=z, tau_supergrid=supergrid, obs_x=mh.obs_x,
+                obs_tau_indices=np.array(mh.obs_tau_indices), obs_drt_var=mh.obs_drt_var, obs_llh=mh.obs_llh, obs_rss=mh.obs_rss)
+    for key, val in mh.obs_special.items():
+        outh['special_' + key] = np.asarray(val)
+    path = os.path.join(ROOT, 'tests', 'golden', 'drtmd_hybrid.npz')
+    np.savez_compressed(path, **outh)
+    print('wrote', path, {k: np.shape(v) for k, v in outh.items()})
 
 
 if __name__ == '__main__':

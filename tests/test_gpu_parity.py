@@ -1039,3 +1039,32 @@ def test_sharded_map_on_two_gpus_equals_single_rank():
     for rank, x, var, llh, outer in got:
         assert np.array_equal(x, md.obs_x) and np.array_equal(var, md.obs_drt_var), rank
         assert np.array_equal(llh, md.obs_llh) and np.array_equal(outer, md.obs_outer_iterations), rank
+
+
+def test_consecutive_steps_and_hybrid_map_against_the_reference():
+    """(1) Finite-rise current steps with chrono_error_structure=None: the decorrelation blocks of the variance
+    matrix follow the non-consecutive step times (drt1d.py:616).  (2) A hybrid map: obs_llh / obs_rss are evaluated
+    with the vz_offset column rewritten from the final coefficients (drt1d.py:972-979, 4433-4496)."""
+    from hybdrt_b200.models import DRT
+    from hybdrt_b200.mapping import DRTMD
+    g = load_golden('consec_steps.npz')
+    drt = DRT()
+    drt.fit_chrono(g['times'], g['i_signal'], g['v_signal'], error_structure=None)
+    assert rel_err(drt.step_times, g['step_times']) < 1e-12 and rel_err(drt.nonconsec_step_times, g['nonconsec_step_times']) < 1e-12
+    assert len(drt.step_times) > len(drt.nonconsec_step_times)
+    assert drt.qphb_params['n_outer'] == int(g['n_outer']) and drt.qphb_params['n_ipm'] == int(g['ipm'])
+    assert rel_err(drt.cvx_result['x'], g['cvx_x']) < FIT_TOL
+    assert rel_err(drt.qphb_params['est_weights'], g['est_weights']) < FIT_TOL
+    assert rel_err(drt.predict_response(), g['v_pred']) < FIT_TOL
+    h = load_golden('drtmd_hybrid.npz')
+    md = DRTMD(tau_supergrid=h['tau_supergrid'], psi_dim_names=['k'], print_progress=False)
+    for b in range(3):
+        md.add_observation([float(b)], (h['times'], h['i_signal'], h['v'][b]), (h['freq'], h['z'][b]))
+    md.fit_all()
+    assert md.obs_fit_status.all() and np.array_equal(np.array(md.obs_tau_indices), h['obs_tau_indices'])
+    for b in range(3):
+        assert rel_err(md.obs_x[b], h['obs_x'][b]) < FIT_TOL
+        assert rel_err(md.obs_drt_var[b], h['obs_drt_var'][b]) < 1e-5
+    for key in ('R_inf', 'inductance', 'v_baseline', 'vz_offset'):
+        assert rel_err(md.obs_special[key], h['special_' + key]) < FIT_TOL, key
+    assert rel_err(md.obs_rss, h['obs_rss']) < FIT_TOL and rel_err(md.obs_llh, h['obs_llh']) < FIT_TOL
