@@ -2129,25 +2129,26 @@ extern "C" int hdrt_debug_profile(unsigned long long* out32, int reset) {
 }
 #endif
 
-extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host) {
+extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host, void* stream) {
     if (!h || !tflops_host) { set_error("null argument"); return HDRT_ERR_ARG; }
     HDRT_CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
     const int blocks = h->sm_count * 8, threads = 256, iters = 20000;
     double* out = nullptr;
-    HDRT_CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    HDRT_CUDA_CHECK(cudaMallocAsync(&out, sizeof(double) * blocks * threads, st));
     cudaEvent_t e0, e1;
     HDRT_CUDA_CHECK(cudaEventCreate(&e0));
     HDRT_CUDA_CHECK(cudaEventCreate(&e1));
-    fp64_probe_kernel<<<blocks, threads>>>(out, iters);
-    HDRT_CUDA_CHECK(cudaEventRecord(e0));
-    fp64_probe_kernel<<<blocks, threads>>>(out, iters);
-    HDRT_CUDA_CHECK(cudaEventRecord(e1));
+    fp64_probe_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    HDRT_CUDA_CHECK(cudaEventRecord(e0, st));
+    fp64_probe_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    HDRT_CUDA_CHECK(cudaEventRecord(e1, st));
     HDRT_CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
     HDRT_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     *tflops_host = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(out);
+    HDRT_CUDA_CHECK(cudaFreeAsync(out, st));
     return HDRT_OK;
 }

@@ -101,7 +101,7 @@ def load_library():
     lib.hdrt_qphb_smem_bytes.argtypes = [C.c_int, C.c_int]
     lib.hdrt_qphb_smem_bytes.restype = C.c_longlong
     lib.hdrt_qphb_fit_batch.argtypes = [_P, C.POINTER(Problem), _P]
-    lib.hdrt_probe_fp64.argtypes = [_P, C.POINTER(C.c_double)]
+    lib.hdrt_probe_fp64.argtypes = [_P, C.POINTER(C.c_double), _P]
     _lib = lib
     return lib
 
@@ -140,6 +140,7 @@ class Engine:
         self._lookups = {}
         self._pinned = {}
         self.launches = 0           # kernels launched through this engine (bench.py reports it)
+        self.max_pinned_shapes = 8
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -172,9 +173,13 @@ class Engine:
     def pinned(self, *shape, dtype=torch.float64):
         """Page-locked host staging buffer, cached per shape (reused across calls)."""
         key = (tuple(shape), dtype)
-        if key not in self._pinned:
-            self._pinned[key] = torch.empty(*shape, dtype=dtype, pin_memory=True)
-        return self._pinned[key]
+        buf = self._pinned.pop(key, None)
+        if buf is None:
+            buf = torch.empty(*shape, dtype=dtype, pin_memory=True)
+        self._pinned[key] = buf                       # most recently used last
+        while len(self._pinned) > self.max_pinned_shapes:     # maps with many group sizes: do not hoard page-locked memory
+            self._pinned.pop(next(iter(self._pinned)))
+        return buf
 
     # -- L0 --------------------------------------------------------------------------------------
     def filter_gather(self, y, plan):
@@ -431,7 +436,7 @@ class Engine:
     def probe_fp64(self):
         """Achieved DFMA TFLOP/s of this GPU (register-resident FMA loop on every SM)."""
         v = C.c_double()
-        self._check(self.lib.hdrt_probe_fp64(self.handle, C.byref(v)))
+        self._check(self.lib.hdrt_probe_fp64(self.handle, C.byref(v), self._stream()))
         self.launches += 2
         return v.value
 

@@ -245,9 +245,10 @@ class DRTMD:
                 np.zeros((0, len(chrono0[0])))
         drt = self.drt1d
         if len(local) or ws > 1:
-            # every rank builds the plan (cheap) so that special_qp_params / basis_tau agree everywhere
-            zz = z if (z is None or len(z)) else np.ones((1, z.shape[1]), dtype=complex)
-            vv = v if (v is None or len(v)) else np.ones((1, v.shape[1]))
+            # every rank builds the plan (cheap) so that special_qp_params / basis_tau agree everywhere; a rank whose
+            # shard of the group is empty fits the group's first spectrum (a benign stand-in whose result is dropped)
+            zz = z if (z is None or len(z)) else np.asarray(eis0[1])[None]
+            vv = v if (v is None or len(v)) else np.asarray(chrono0[2], dtype=float)[None]
             if self.fit_type == 'pfrt':
                 # drtmd.py:1339-1342 calls DRT._pfrt_fit_core(*chrono, *eis, **fit_kw): the factors are those of
                 # fit_kw (default logspace(-1, 1, 11)); DRTMD.pfrt_factors only sizes the containers
@@ -287,7 +288,9 @@ class DRTMD:
         for key in sp_keys:
             if key not in self.obs_special:
                 self.obs_special[key] = np.zeros([self.num_obs, *self.special_param_shape(key)])
-        bad = (out['status'] & (_engine.ST_NAN | _engine.ST_KKT_FAIL)) != 0
+        # a singular P (ST_COV_FAIL) makes the reference's estimate_distribution_cov fail, which fit_observation reports
+        # as a fit error of the observation (drtmd.py:256-287)
+        bad = (out['status'] & (_engine.ST_NAN | _engine.ST_KKT_FAIL | _engine.ST_COV_FAIL)) != 0
         bad |= ~np.all(np.isfinite(out['x']).reshape(len(out['x']), -1), axis=1)
         if bad.any() and not ignore_errors:
             raise ValueError(f'Error encountered at obs_index {int(members[np.argmax(bad)])}: '

@@ -149,7 +149,8 @@ def estimate_rp_batch(times, step_times, step_sizes, response, z):
                 mins.append(np.full(response.shape[0], np.nan))
                 maxs.append(np.full(response.shape[0], np.nan))
                 continue
-            r = (response[:, start:end] - response[:, start - 1:start]) / step_sizes[i]
+            prev = response[:, start - 1:start] if start > 0 else 0.0        # a step at the first sample: no pre-step value
+            r = (response[:, start:end] - prev) / step_sizes[i]
             mins.append(np.min(r, axis=1))
             maxs.append(np.max(r, axis=1))
         r_min = np.nanmean(np.array(mins), axis=0)
@@ -1386,7 +1387,15 @@ class DRT:
             'n_outer': int(h['n_outer'][0]), 'n_ipm': int(h['n_ipm'][0]), 'status': st,
             'outlier_t': h['outlier_t'][0] if 'outlier_t' in h else np.ones(pl['n_rows']),
         }
-        self.qphb_history = None    # per-iteration history is not exported by the batched kernel
+        # qphb.iterate_qphb appends one entry per outer iteration (qphb.py:950-966).  The kernel keeps the iterates on
+        # chip, so only the LAST entry is populated (what the reference's own callers read: qphb_history[-1]['x'],
+        # drt1d.py:1517, 4161, 4447; len(qphb_history) = outer iterations); the earlier ones are None.
+        n_out = int(h['n_outer'][0])
+        last = {'x': h['x'][0].copy(), 's_vectors': [h['s_vectors'][0, k].copy() for k in range(3)],
+                'rho_vector': h['rho'][0].copy(), 'dop_rho_vector': h['dop_rho'][0].copy() if 'dop_rho' in h else None,
+                'weights': None,            # the reference stores the weights that ENTERED the iteration; not exported
+                'outlier_t': self.qphb_params['outlier_t'], 'fun': float(h['fun'][0]), 'cvx_result': self.cvx_result}
+        self.qphb_history = [None] * max(n_out - 1, 0) + ([last] if n_out > 0 else [])
 
     # ------------------------------------------------------------------------------------------------
     # prediction (drt1d.py:3363-3542); matrices are rebuilt on the GPU for the requested grid

@@ -249,9 +249,9 @@ long long hdrt_qphb_smem_bytes(int n_rows, int n_cols);
 /* One persistent CTA per spectrum in flight; spectra are pulled from a device-side work counter. */
 int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob, void* stream);
 
-/* FP64 FMA probe: runs a register-resident DFMA loop on every SM and returns achieved TFLOP/s
- * (host-synchronous; used by bench.py for the FP64 roofline denominator). */
-int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host);
+/* FP64 FMA probe: runs a register-resident DFMA loop on every SM, on `stream`, and returns achieved TFLOP/s
+ * (host-synchronous on that stream; used by bench.py for the FP64 roofline denominator). */
+int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -259,6 +259,11 @@ def test_model_fit_eis_golden():
     assert rel_err(drt.qphb_params['rm'], c1['rm']) < MAT_TOL
     assert rel_err(drt.qphb_params['vmm'], c1['vmm']) < MAT_TOL
     assert rel_err(drt.basis_tau, c1['basis_tau']) < 1e-14
+    # qphb_history (qphb.py:950-966): one entry per outer iteration, the last one populated
+    hist = drt.qphb_history
+    assert len(hist) == int(c1['n_outer']) and rel_err(hist[-1]['x'], c1['hist_x'][-1]) < FIT_TOL
+    assert rel_err(hist[-1]['rho_vector'], c1['hist_rho'][-1]) < FIT_TOL and rel_err(np.array(hist[-1]['s_vectors']), c1['hist_s'][-1]) < 1e-5
+    assert abs(hist[-1]['fun'] - float(c1['hist_fun'][-1])) < 1e-6 * abs(float(c1['hist_fun'][-1]))
     with pytest.raises(ValueError):
         drt.fit_eis(c1['freq'], c1['z'], not_a_hyper=1)
 
