@@ -134,26 +134,45 @@ __global__ void impedance_interp_global_kernel(const double* __restrict__ freq, 
 // + Toeplitz fill, mat1d.py:341-372), the two differ at the 1e-16 level.
 // A work item is `rows_per_item` rows of one grid; stores are 16-byte, streaming (the output is not re-read).
 struct SmemTable {
-    const double* x;
-    const double* v;
-    const double* s;
-    double x0, xn, inv_dx, v0, vn;
+    const double* x;      // knots
+    const double2* sc;    // per interval: slope, intercept (v_j - slope x_j): the interpolant is fma(slope, x, intercept)
+    double x0, xn, inv_dx, pos0, v0, vn;
     bool uniform;   // every knot within 1e-9 of a spacing of the uniform grid: the index guess can be trusted
 };
-// Exact numpy.interp semantics (same interval as numpy's binary search, slope * (x - x_j) + v_j, edge values
-// outside the span).  Common path: no loop and no branch -- the interval index comes from the uniform-grid guess,
-// which is provably right when x is further than 1e-6 of a spacing from a knot; otherwise (or for a non-uniform
-// table) the two loops move the index to where the binary search lands.
+// numpy.interp semantics: piecewise linear between the knots, the edge values outside the span.
+// Uniform table (the lookup tables are linspace grids): x is clamped to the span, the interval index is the floor of
+// (x - x0) / dx taken by adding 2^52 + 2^51 (the low word of the sum is the rounded integer: one DADD instead of a
+// double -> int conversion on the quarter-rate pipe), and the value is one fma on a 16-byte shared load.  At a knot
+// the guess may fall on either neighbouring interval: the interpolant is continuous, both give the knot value to the
+// last bit or two.  Against slope * (x - x_j) + v_j the fma form differs at the 1e-16 level of the table scale.
+// A non-uniform table takes the search loop.
+template <bool UNIFORM, bool CHECK = true>
 __device__ __forceinline__ double interp_smem(double x, const SmemTable& t, int npts) {
-    const double pos = (x - t.x0) * t.inv_dx;
-    const int jr = __double2int_rd(pos);          // floor, saturating; NaN -> 0
-    const double frac = pos - (double)jr;         // in [0, 1) also for x outside the span (|pos| < 2^31)
-    int j = max(0, min(jr, npts - 2));
-    if (!(frac > 1e-6 && frac < 1.0 - 1e-6 && t.uniform)) {   // rare: x at a knot, NaN, or an odd table
-        while (j > 0 && t.x[j] > x) --j;
-        while (j < npts - 2 && t.x[j + 1] <= x) ++j;
+    if (UNIFORM && !CHECK) {      // the caller has bounded |x| for the whole work item: no branch at all
+        const double big = fma(x, t.inv_dx, t.pos0) + 6755399441055744.0;
+        const int j = max(-1, min(__double2loint(big), npts - 1));
+        const double2 sc = t.sc[j + 1];
+        return fma(sc.x, x, sc.y);
     }
-    double r = __dadd_rn(__dmul_rn(t.s[j], x - t.x[j]), t.v[j]);   // NaN x gives NaN
+    if (UNIFORM) {
+        // sc[0] and sc[npts] are flat sentinel intervals (slope 0, the edge value): an x outside the span needs no
+        // comparison, its index clamps onto them.  fmin / fmax on doubles cost eight instructions each on this target.
+        const double pos = fma(x, t.inv_dx, t.pos0);                      // (x - x0) / dx - 0.5
+        const double big = pos + 6755399441055744.0;                      // 2^52 + 2^51: low word = round(pos)
+        if ((unsigned)(__double2hiint(pos) & 0x7fffffff) < 0x41d00000u) { // |pos| < 2^30 (always, for finite frequencies)
+            const int j = max(-1, min(__double2loint(big), npts - 1));
+            const double2 sc = t.sc[j + 1];
+            return fma(sc.x, x, sc.y);
+        }
+        return (x != x) ? x : (x < t.x0 ? t.v0 : t.vn);                   // +-inf (f = 0), NaN
+    }
+    int j = 0;
+    {
+        int lo = 0, hi = npts - 1;                            // binary search: x[j] <= x < x[j + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (t.x[mid] <= x) lo = mid; else hi = mid; }
+        j = lo;
+    }
+    double r = fma(t.sc[j + 1].x, x, t.sc[j + 1].y);
     r = (x >= t.xn) ? t.vn : r;
     r = (x < t.x0) ? t.v0 : r;
     return r;
@@ -161,37 +180,72 @@ __device__ __forceinline__ double interp_smem(double x, const SmemTable& t, int 
 
 constexpr int kIThreads = 512;
 
+// The entries of one work item that belong to this thread: fixed column, every `groups`-th row; four rows in flight.
+template <bool UNIFORM, bool CHECK>
+__device__ __forceinline__ void interp_tile(const double* s_lt, const double* s_lw, double* __restrict__ o_re,
+                                            double* __restrict__ o_im, const SmemTable& tr, const SmemTable& ti, int npts,
+                                            int nb, int rows, int col0, int rg, int groups) {
+    const size_t step = (size_t)groups * nb;
+    for (int col = col0; col < nb; col += kIThreads) {
+        const double lt = s_lt[col];
+        double* __restrict__ pr = o_re + (size_t)rg * nb + col;
+        double* __restrict__ pi = o_im + (size_t)rg * nb + col;
+        int rr = rg;
+        for (; rr + 3 * groups < rows; rr += 4 * groups, pr += 4 * step, pi += 4 * step) {
+            double vr[4], vi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double x = s_lw[rr + u * groups] + lt;
+                vr[u] = interp_smem<UNIFORM, CHECK>(x, tr, npts);
+                vi[u] = interp_smem<UNIFORM, CHECK>(x, ti, npts);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                __stcs(pr + u * step, vr[u]);
+                __stcs(pi + u * step, vi[u]);
+            }
+        }
+        for (; rr < rows; rr += groups, pr += step, pi += step) {
+            const double x = s_lw[rr] + lt;
+            __stcs(pr, interp_smem<UNIFORM, CHECK>(x, tr, npts));
+            __stcs(pi, interp_smem<UNIFORM, CHECK>(x, ti, npts));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kIThreads, 2)
 impedance_interp_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int n_grids, int nf, int nb,
                         const double* __restrict__ re_x, const double* __restrict__ re_v,
                         const double* __restrict__ im_x, const double* __restrict__ im_v, int npts,
                         double* __restrict__ a_re, double* __restrict__ a_im, int rows_per_item, int tiles_per_grid) {
     extern __shared__ __align__(16) double sm[];
-    double* t_rx = sm;
-    double* t_rv = t_rx + npts;
-    double* t_rs = t_rv + npts;
-    double* t_ix = t_rs + npts;
-    double* t_iv = t_ix + npts;
-    double* t_is = t_iv + npts;
-    double* s_vec = t_is + npts;                      // two buffers of [nb ln tau | rows_per_item ln omega]
+    double2* t_rsc = reinterpret_cast<double2*>(sm);          // [npts + 1] (slope, intercept), real table; see interp_smem
+    double2* t_isc = t_rsc + npts + 1;                        // imaginary table
+    double* t_rx = reinterpret_cast<double*>(t_isc + npts + 1);
+    double* t_ix = t_rx + npts;
+    double* s_vec = t_ix + npts;                              // two buffers of [nb ln tau | rows_per_item ln omega]
     const int vlen = nb + rows_per_item;
     const int tid = threadIdx.x;
-    for (int i = tid; i < npts; i += kIThreads) {
-        t_rx[i] = __ldg(re_x + i); t_rv[i] = __ldg(re_v + i);
-        t_ix[i] = __ldg(im_x + i); t_iv[i] = __ldg(im_v + i);
+    for (int i = tid; i < npts; i += kIThreads) { t_rx[i] = __ldg(re_x + i); t_ix[i] = __ldg(im_x + i); }
+    for (int i = tid; i < npts - 1; i += kIThreads) {         // interval i = [x_i, x_i+1) sits at index i + 1
+        const double sr = (__ldg(re_v + i + 1) - __ldg(re_v + i)) / (__ldg(re_x + i + 1) - __ldg(re_x + i));
+        const double si = (__ldg(im_v + i + 1) - __ldg(im_v + i)) / (__ldg(im_x + i + 1) - __ldg(im_x + i));
+        t_rsc[i + 1] = make_double2(sr, fma(-sr, __ldg(re_x + i), __ldg(re_v + i)));
+        t_isc[i + 1] = make_double2(si, fma(-si, __ldg(im_x + i), __ldg(im_v + i)));
     }
-    __syncthreads();
-    for (int i = tid; i < npts - 1; i += kIThreads) {
-        t_rs[i] = (t_rv[i + 1] - t_rv[i]) / (t_rx[i + 1] - t_rx[i]);
-        t_is[i] = (t_iv[i + 1] - t_iv[i]) / (t_ix[i + 1] - t_ix[i]);
+    if (tid == 0) {
+        t_rsc[0] = make_double2(0.0, __ldg(re_v)); t_rsc[npts] = make_double2(0.0, __ldg(re_v + npts - 1));
+        t_isc[0] = make_double2(0.0, __ldg(im_v)); t_isc[npts] = make_double2(0.0, __ldg(im_v + npts - 1));
     }
     __shared__ int s_nonuniform[2];
     if (tid < 2) s_nonuniform[tid] = 0;
     SmemTable tr, ti;
-    tr.x = t_rx; tr.v = t_rv; tr.s = t_rs; tr.x0 = t_rx[0]; tr.xn = t_rx[npts - 1]; tr.v0 = t_rv[0]; tr.vn = t_rv[npts - 1];
-    ti.x = t_ix; ti.v = t_iv; ti.s = t_is; ti.x0 = t_ix[0]; ti.xn = t_ix[npts - 1]; ti.v0 = t_iv[0]; ti.vn = t_iv[npts - 1];
+    tr.x = t_rx; tr.sc = t_rsc; tr.x0 = __ldg(re_x); tr.xn = __ldg(re_x + npts - 1); tr.v0 = __ldg(re_v); tr.vn = __ldg(re_v + npts - 1);
+    ti.x = t_ix; ti.sc = t_isc; ti.x0 = __ldg(im_x); ti.xn = __ldg(im_x + npts - 1); ti.v0 = __ldg(im_v); ti.vn = __ldg(im_v + npts - 1);
     tr.inv_dx = (double)(npts - 1) / (tr.xn - tr.x0);
     ti.inv_dx = (double)(npts - 1) / (ti.xn - ti.x0);
+    tr.pos0 = -tr.x0 * tr.inv_dx - 0.5;
+    ti.pos0 = -ti.x0 * ti.inv_dx - 0.5;
     __syncthreads();
     for (int i = tid; i < npts; i += kIThreads) {
         if (fabs((t_rx[i] - tr.x0) * tr.inv_dx - (double)i) > 1e-9) s_nonuniform[0] = 1;
@@ -200,6 +254,9 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
     __syncthreads();
     tr.uniform = s_nonuniform[0] == 0;
     ti.uniform = s_nonuniform[1] == 0;
+    const bool fast = tr.uniform && ti.uniform;
+    // |x| = |ln tau + ln omega| <= 2 half_xmax keeps |pos| below 2^30 for both tables
+    const double half_xmax = 0.5 * fmin((1073741824.0 - fabs(tr.pos0)) / tr.inv_dx, (1073741824.0 - fabs(ti.pos0)) / ti.inv_dx);
     // thread -> (column, row group): the column of a thread is fixed, so ln(tau) sits in a register and the row loop
     // carries no index arithmetic; consecutive threads write consecutive columns (coalesced 8-byte stores)
     const int groups = nb <= kIThreads ? kIThreads / nb : 1;
@@ -207,30 +264,51 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
     const int rg = nb <= kIThreads ? tid / nb : 0;
     const bool active = rg < groups;
     const long long items = (long long)n_grids * tiles_per_grid;
+    // ln(tau) / ln(omega) of the NEXT work item are fetched while the current one is computed (one element per thread,
+    // nb + rows_per_item <= kIThreads for every shape the host sends here), so that an item starts without a global
+    // round trip in front of it
+    auto fetch = [&](long long item) -> double {
+        if (item >= items || tid >= vlen) return 1.0;
+        const int g = (int)(item / tiles_per_grid);
+        const int r0 = (int)(item - (long long)g * tiles_per_grid) * rows_per_item;
+        if (tid < nb) return tau[(size_t)g * nb + tid];
+        const int rr = r0 + tid - nb;
+        return rr < nf ? freq[(size_t)g * nf + rr] * (2.0 * 3.141592653589793) : 1.0;     // 2 pi f
+    };
+    const bool prefetch = vlen <= kIThreads;
     int buf = 0;
+    if (prefetch) {
+        const double v0 = fetch(blockIdx.x);
+        if (tid < vlen) s_vec[tid] = log(v0);
+    }
     for (long long item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
         const int g = (int)(item / tiles_per_grid);
         const int r0 = (int)(item - (long long)g * tiles_per_grid) * rows_per_item;
         const int rows = min(rows_per_item, nf - r0);
         double* s_lt = s_vec + buf * vlen;
         double* s_lw = s_lt + nb;
-        for (int i = tid; i < nb + rows; i += kIThreads) {
-            if (i < nb) s_lt[i] = log(tau[(size_t)g * nb + i]);
-            else s_lw[i - nb] = log(freq[(size_t)g * nf + r0 + (i - nb)] * 2.0 * 3.141592653589793);  // 2 pi f
+        double nextv = 1.0;
+        if (prefetch) {
+            nextv = fetch(item + gridDim.x);
+        } else {
+            for (int i = tid; i < nb + rows; i += kIThreads) {
+                if (i < nb) s_lt[i] = log(tau[(size_t)g * nb + i]);
+                else s_lw[i - nb] = log(freq[(size_t)g * nf + r0 + (i - nb)] * 2.0 * 3.141592653589793);
+            }
         }
-        __syncthreads();   // also orders the slope table on the first pass; the other buffer is free by now
+        // the barrier also orders the tables on the first pass (the other buffer is free by now), and tells whether every
+        // ln(tau) / ln(omega) of this item is small enough for the index arithmetic of the branch-free path
+        bool mine_ok = true;
+        if (prefetch && tid < vlen) mine_ok = fabs(s_vec[buf * vlen + tid]) < half_xmax;
+        const bool bounded = __syncthreads_and(mine_ok) && prefetch;
         double* __restrict__ o_re = a_re + ((size_t)g * nf + r0) * nb;
         double* __restrict__ o_im = a_im + ((size_t)g * nf + r0) * nb;
         if (active) {
-            for (int col = col0; col < nb; col += kIThreads) {
-                const double lt = s_lt[col];
-                for (int rr = rg; rr < rows; rr += groups) {
-                    const double x = s_lw[rr] + lt;
-                    __stcs(o_re + (size_t)rr * nb + col, interp_smem(x, tr, npts));
-                    __stcs(o_im + (size_t)rr * nb + col, interp_smem(x, ti, npts));
-                }
-            }
+            if (fast && bounded) interp_tile<true, false>(s_lt, s_lw, o_re, o_im, tr, ti, npts, nb, rows, col0, rg, groups);
+            else if (fast) interp_tile<true, true>(s_lt, s_lw, o_re, o_im, tr, ti, npts, nb, rows, col0, rg, groups);
+            else interp_tile<false, true>(s_lt, s_lw, o_re, o_im, tr, ti, npts, nb, rows, col0, rg, groups);
         }
+        if (prefetch && tid < vlen) s_vec[(buf ^ 1) * vlen + tid] = log(nextv);    // published by the next barrier
     }
 }
 
@@ -576,7 +654,7 @@ extern "C" int hdrt_build_impedance(int mode, const double* freq, const double* 
         int rows_per_item = nf;
         while (rows_per_item > 4 && (long long)n_grids * ((nf + rows_per_item - 1) / rows_per_item) < ctas) rows_per_item = (rows_per_item + 1) / 2;
         const int tiles = (nf + rows_per_item - 1) / rows_per_item;
-        const size_t smem = sizeof(double) * (6 * (size_t)grid_points + 2 * (size_t)(nb + rows_per_item));
+        const size_t smem = sizeof(double) * (6 * (size_t)grid_points + 4 + 2 * (size_t)(nb + rows_per_item));
         if (smem <= 110 * 1024) {
             HDRT_CUDA_CHECK(cudaFuncSetAttribute(impedance_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const long long items = (long long)n_grids * tiles;
