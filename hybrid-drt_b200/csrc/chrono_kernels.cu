@@ -30,18 +30,7 @@ __global__ void filter_gather_kernel(const double* __restrict__ y, int n_sig, in
             const int c = i - lo;
             double acc = 0.0;
             if (c - r >= 0 && c + r < len) {          // window inside the segment: no mirroring
-                // four independent tap / sample load pairs in flight per lane (the kernel is bound by the number of
-                // HBM requests in flight, not by arithmetic)
-                double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int k = -r + lane;
-                for (; k + 96 <= r; k += 128) {
-                    const double w0 = w[k], w1 = w[k + 32], w2 = w[k + 64], w3 = w[k + 96];
-                    const double y0 = ys[i + k], y1 = ys[i + k + 32], y2 = ys[i + k + 64],
-                                 y3 = ys[i + k + 96];
-                    acc = fma(w0, y0, acc); a1 = fma(w1, y1, a1); a2 = fma(w2, y2, a2); a3 = fma(w3, y3, a3);
-                }
-                for (; k <= r; k += 32) acc = fma(w[k], ys[i + k], acc);
-                acc = (acc + a1) + (a2 + a3);
+                for (int k = -r + lane; k <= r; k += 32) acc = fma(w[k], ys[i + k], acc);
             } else {
                 const int p2 = 2 * len;
                 for (int k = -r + lane; k <= r; k += 32) {
