@@ -1971,6 +1971,7 @@ qphb_kernel(const hdrt_qphb_problem p, int* work_counter) {
 }  // namespace hdrt
 
 #include "qphb_warp.cuh"
+#include "resolve_kernel.cuh"
 
 namespace hdrt {
 
@@ -2150,5 +2151,35 @@ extern "C" int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host, void* stream
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     HDRT_CUDA_CHECK(cudaFreeAsync(out, st));
+    return HDRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-observation resolve (resolve_kernel.cuh)
+// ------------------------------------------------------------------------------------------------
+static int resolve_grid(const hdrt_handle* h, int n_windows) { return n_windows < h->sm_count ? n_windows : h->sm_count; }
+
+extern "C" long long hdrt_resolve_work_bytes(const hdrt_handle* h, int n_windows, int nr, int nc) {
+    if (!h || n_windows < 0 || nr <= 0 || nc <= 0 || nr * nc > rs::kMaxN) return -1;
+    return (long long)resolve_grid(h, n_windows) * rs::work_doubles(nr * nc) * 8;
+}
+
+extern "C" int hdrt_resolve_qp_batch(hdrt_handle* h, const hdrt_resolve_problem* prob, void* work, void* stream) {
+    if (!h || !prob) { set_error("null handle or problem"); return HDRT_ERR_ARG; }
+    const hdrt_resolve_problem& p = *prob;
+    if (p.n_windows == 0) return HDRT_OK;
+    if (p.n_windows < 0 || p.nr <= 0 || p.nc <= 0 || !p.p || !p.q || !p.first_obs || !p.my || !p.param_scale || !p.h || !p.x || !work) {
+        set_error("hdrt_resolve_qp_batch: invalid argument");
+        return HDRT_ERR_ARG;
+    }
+    const int n = p.nr * p.nc;
+    if (n > rs::kMaxN) { set_error("resolve window of %d unknowns > %d unsupported", n, rs::kMaxN); return HDRT_ERR_UNSUPPORTED; }
+    const size_t smem = rs::smem_bytes(n);
+    if (smem > 227 * 1024) { set_error("resolve window does not fit in shared memory"); return HDRT_ERR_UNSUPPORTED; }
+    HDRT_CUDA_CHECK(cudaSetDevice(h->device));
+    HDRT_CUDA_CHECK(cudaFuncSetAttribute(rs::resolve_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = resolve_grid(h, p.n_windows);
+    rs::resolve_qp_kernel<<<grid, rs::kThreads, smem, (cudaStream_t)stream>>>(p, (double*)work, rs::work_doubles(n));
+    HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }

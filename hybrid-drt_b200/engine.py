@@ -64,6 +64,12 @@ class Problem(C.Structure):
     ]
 
 
+class ResolveProblem(C.Structure):
+    """struct hdrt_resolve_problem"""
+    _fields_ = [('n_windows', C.c_int), ('nr', C.c_int), ('nc', C.c_int), ('p', _P), ('q', _P), ('first_obs', _P),
+                ('my', _P), ('param_scale', _P), ('h', _P), ('x', _P), ('iters', _P), ('status', _P)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -102,6 +108,9 @@ def load_library():
     lib.hdrt_qphb_smem_bytes.restype = C.c_longlong
     lib.hdrt_qphb_fit_batch.argtypes = [_P, C.POINTER(Problem), _P]
     lib.hdrt_probe_fp64.argtypes = [_P, C.POINTER(C.c_double), _P]
+    lib.hdrt_resolve_qp_batch.argtypes = [_P, C.POINTER(ResolveProblem), _P, _P]
+    lib.hdrt_resolve_work_bytes.argtypes = [_P, C.c_int, C.c_int, C.c_int]
+    lib.hdrt_resolve_work_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 
@@ -109,7 +118,8 @@ def load_library():
 EXPORTED_SYMBOLS = [
     'hdrt_version', 'hdrt_last_error', 'hdrt_create', 'hdrt_destroy', 'hdrt_sm_count', 'hdrt_build_lookup',
     'hdrt_build_impedance', 'hdrt_build_response', 'hdrt_build_penalty', 'hdrt_build_eis_vmm', 'hdrt_build_chrono_vmm', 'hdrt_build_dop_z', 'hdrt_build_dop_v', 'hdrt_filter_gather',
-    'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64',
+    'hdrt_default_hypers', 'hdrt_qphb_smem_bytes', 'hdrt_qphb_fit_batch', 'hdrt_probe_fp64', 'hdrt_resolve_qp_batch',
+    'hdrt_resolve_work_bytes',
 ]
 
 
@@ -432,6 +442,30 @@ class Engine:
         a = tz.abs().cpu().numpy()
         big = np.nonzero(a >= 1e-45 * a.max(axis=1, keepdims=True))[1]
         return tz, int(big.max()) if len(big) else 0
+
+    def resolve_qp_batch(self, p, q, first_obs, my, param_scale, h, nr):
+        """Batched cross-observation resolve QP (hdrt_resolve_qp_batch).  p [n_obs, nc, nc], q [n_obs, nc] device;
+        first_obs [W] int; my [W, nr, nr]; param_scale [W, nc]; h [nc].  Returns dict(x [W, nr, nc], iters, status)."""
+        p, q = p.contiguous(), q.contiguous()
+        nc = q.shape[1]
+        fo = self.dev(np.asarray(first_obs, dtype=np.int32), dtype=torch.int32)
+        my_d, ps_d, h_d = self.dev(np.asarray(my, dtype=float)), self.dev(np.asarray(param_scale, dtype=float)), self.dev(np.asarray(h, dtype=float))
+        nw = int(fo.numel())
+        assert p.is_cuda and p.dtype == torch.float64 and tuple(p.shape[1:]) == (nc, nc) and tuple(my_d.shape) == (nw, nr, nr)
+        x = self.empty(nw, nr, nc)
+        iters = self.empty(nw, dtype=torch.int32)
+        status = self.empty(nw, dtype=torch.int32)
+        wb = int(self.lib.hdrt_resolve_work_bytes(self.handle, nw, nr, nc))
+        if wb < 0:
+            raise EngineError(f'resolve window of {nr} x {nc} unknowns is not supported')
+        work = self.empty(max(wb // 8, 1))
+        pr = ResolveProblem()
+        pr.n_windows, pr.nr, pr.nc = nw, int(nr), int(nc)
+        pr.p, pr.q, pr.first_obs, pr.my, pr.param_scale, pr.h = _ptr(p), _ptr(q), _ptr(fo), _ptr(my_d), _ptr(ps_d), _ptr(h_d)
+        pr.x, pr.iters, pr.status = _ptr(x), _ptr(iters), _ptr(status)
+        self._check(self.lib.hdrt_resolve_qp_batch(self.handle, C.byref(pr), _ptr(work), self._stream()))
+        self.launches += 1
+        return dict(x=x, iters=iters, status=status, _keep=(fo, my_d, ps_d, h_d, work))
 
     def probe_fp64(self):
         """Achieved DFMA TFLOP/s of this GPU (register-resident FMA loop on every SM)."""

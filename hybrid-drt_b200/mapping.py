@@ -22,6 +22,7 @@ Not mirrored (outside SURVEY.md section 8): file readers, resolve / filter / bad
 helpers.
 """
 import time
+import warnings
 
 import numpy as np
 
@@ -37,7 +38,7 @@ class DRTMD:
                  normalize_dop=True, nu_basis_type='gaussian', nu_epsilon=None, time_precision=10,
                  input_signal_precision=10, frequency_precision=10, fit_kw=None, fit_type='drt',
                  pfrt_factors=None, print_diagnostics=False, print_progress=True, warn=False, llh_kw=None,
-                 rss_kw=None, device=0):
+                 rss_kw=None, device=0, keep_pq=False):
         for kw_dict in (llh_kw, rss_kw):
             if kw_dict and (kw_dict.get('normalize', True) is not True or kw_dict.get('weights', 'uniform') != 'uniform'):
                 raise NotImplementedError('hybdrt_b200: llh_kw / rss_kw other than the DRTMD defaults')
@@ -59,6 +60,9 @@ class DRTMD:
         self.fit_type = fit_type
         self.fit_kw = dict({'nonneg': True}, **(fit_kw or {}))
         self.print_progress, self.warn, self.print_diagnostics = print_progress, warn, print_diagnostics
+        # keep_pq: every fit also returns its P matrix / q vector (qphb.calculate_pq), kept on the device per fit group;
+        # resolve_observations / resolve_group need them (the reference restores them from obs_fit_attr, drtmd.py:366-377)
+        self.keep_pq = bool(keep_pq)
         self.clear_obs()
 
     # ---- containers (drtmd.py:101-142, 379-430) ------------------------------------------------------
@@ -81,6 +85,11 @@ class DRTMD:
         self.obs_drt_var = np.zeros((n, *self.drt_param_shape()))
         self.obs_llh, self.obs_rss = np.zeros(n), np.zeros(n)
         self.obs_special = None
+        self._pq_store, self._pq_ref = [], {}                # fit groups' (p, q, plan scalars) on the device; obs -> (store, row)
+        self.obs_scales = {}                                 # coefficient_scale, response_signal_scale, ... per observation
+        self.obs_resolve_status = np.zeros(n, dtype=bool)
+        self.obs_x_resolved = np.zeros((n, *self.drt_param_shape()))
+        self.obs_special_resolved = None
         self.obs_outer_iterations = np.zeros(n, dtype=int)   # not in the reference: iteration count per fit
         self.obs_status = np.zeros(n, dtype=int)             # HDRT_ST_* bits per fit
 
@@ -256,12 +265,12 @@ class DRTMD:
                                                eis0[0], zz if eis0[0] is not None else None,
                                                diag_tau=self.tau_supergrid, **self.fit_kw)
             elif chrono0[0] is None:
-                res = drt.fit_eis_batch(eis0[0], zz, diag_tau=self.tau_supergrid, **self.fit_kw)
+                res = drt.fit_eis_batch(eis0[0], zz, diag_tau=self.tau_supergrid, want_pq=self.keep_pq, **self.fit_kw)
             elif eis0[0] is None:
-                res = drt.fit_chrono_batch(chrono0[0], chrono0[1], vv, diag_tau=self.tau_supergrid, **self.fit_kw)
+                res = drt.fit_chrono_batch(chrono0[0], chrono0[1], vv, diag_tau=self.tau_supergrid, want_pq=self.keep_pq, **self.fit_kw)
             else:
                 res = drt.fit_hybrid_batch(chrono0[0], chrono0[1], vv, eis0[0], zz, diag_tau=self.tau_supergrid,
-                                           **self.fit_kw)
+                                           want_pq=self.keep_pq, **self.fit_kw)
         if self.fit_type == 'pfrt':
             step_x = res.pfrt_result()['step_x']
             if step_x.shape[1] != len(self.pfrt_factors):
@@ -280,6 +289,19 @@ class DRTMD:
         sp_keys = list(drt.special_qp_params.keys())
         for key in sp_keys:
             out['sp_' + key] = np.asarray(fp[key])[:nloc]
+        if self.keep_pq and self.fit_type != 'pfrt':
+            if ws > 1:
+                raise NotImplementedError('hybdrt_b200: keep_pq with shard=True (the P matrices stay on the rank that fitted them)')
+            self._ensure_len()
+            pl = res.plan
+            self._pq_store.append(dict(p=res.raw['p_matrix'], q=res.raw['q_vector'], special=dict(drt.special_qp_params),
+                                       v_baseline_scale=pl.get('v_baseline_scale'), inductance_scale=pl['inductance_scale'],
+                                       capacitance_scale=pl['capacitance_scale']))
+            for row, i in enumerate(members):
+                self._pq_ref[int(i)] = (len(self._pq_store) - 1, row)
+            for key in ('coefficient_scale', 'response_signal_scale', 'scaled_response_offset'):
+                if key in res.scales:
+                    self.obs_scales.setdefault(key, np.zeros(self._n))[members] = np.asarray(res.scales[key])[:nloc]
         if ws > 1:
             out = _sharding.gather_results(out, len(members), interleave=True)
         # ---- scatter into the observation arrays (drtmd.py:256-287)
@@ -314,3 +336,203 @@ class DRTMD:
             self.obs_fit_status[i] = False
             self.obs_ignore_flag[i] = True
             self.obs_fit_errors[i] = ValueError('Rank(A) < p or Rank([P; A; G]) < n')
+
+    # ---- cross-observation resolve (drtmd.py:432-560, mapping/resolve.py) ----------------------------------------
+    def _ensure_len(self):
+        """The resolve containers and per-observation scales follow num_obs (they are allocated lazily)."""
+        n = self._n
+        if len(self.obs_x_resolved) != n:
+            keep = min(len(self.obs_x_resolved), n)
+            new = np.zeros((n, *self.drt_param_shape()))
+            new[:keep] = self.obs_x_resolved[:keep]
+            self.obs_x_resolved = new
+            st = np.zeros(n, dtype=bool)
+            st[:keep] = self.obs_resolve_status[:keep]
+            self.obs_resolve_status = st
+        for key, arr in list(self.obs_scales.items()):
+            if len(arr) != n:
+                new = np.zeros(n)
+                new[:min(len(arr), n)] = arr[:n]
+                self.obs_scales[key] = new
+        if self.obs_special is not None:
+            if self.obs_special_resolved is None:
+                self.obs_special_resolved = {}
+            for key, arr in self.obs_special.items():                  # drtmd.py:1160-1166
+                cur = self.obs_special_resolved.get(key)
+                if cur is None or len(cur) != n:
+                    new = np.zeros_like(arr)
+                    if cur is not None:
+                        new[:min(len(cur), n)] = cur[:n]
+                    self.obs_special_resolved[key] = new
+
+    def get_group_index(self, group_id):
+        """drtmd.py:1194-1210 (unsorted)"""
+        gids = np.array(self.obs_group_id, dtype=object)
+        if isinstance(group_id, str) or group_id is None:
+            return np.where(np.array([g == group_id for g in gids]))[0]
+        return np.where(np.array([g in group_id for g in gids]))[0]
+
+    def _sorted(self, obs_index, psi_sort_dims, psi_distance_dims=None):
+        dims = psi_sort_dims if psi_sort_dims is not None else psi_distance_dims
+        if dims is None:
+            return obs_index
+        vals = [self.obs_psi[obs_index, self.psi_dim_names.index(d)] for d in dims][::-1]
+        return obs_index[np.lexsort(vals)]
+
+    def _resolve_windows(self, windows, truncate, sigma, lambda_psi):
+        """The QPs of `windows` (lists of nr observation indices each) in one launch.  Returns, per window,
+        (x_drt [nr, n_tau], x_special dict, tau_indices), unpacked as resolve.unpack_resolved_x does."""
+        from scipy.ndimage import gaussian_filter1d, median_filter
+        if truncate:
+            raise NotImplementedError('hybdrt_b200: resolve with truncate=True')
+        if self.fit_dop:
+            raise NotImplementedError('hybdrt_b200: resolve of DRT + DOP fits')
+        eng = self.drt1d.engine
+        nr = len(windows[0])
+        flat = np.concatenate(windows)
+        missing = [int(i) for i in flat if int(i) not in self._pq_ref]
+        if missing:
+            raise ValueError(f'observation {missing[0]} has no stored P matrix: construct DRTMD(keep_pq=True) before fitting')
+        st0 = self._pq_store[self._pq_ref[int(flat[0])][0]]
+        sp = st0['special']
+        removed = [k for k in ('v_baseline', 'vz_offset') if k in sp]
+        if removed != ['v_baseline', 'vz_offset'] or sp['v_baseline']['index'] != 0:
+            # resolve.get_offset_pq indexes both keys (resolve.py:24-25): the reference resolves hybrid fits only
+            raise KeyError('vz_offset' if 'v_baseline' in sp else 'v_baseline')
+        k_rm = sum(sp[k].get('size', 1) for k in removed)
+        special_dict = {k: dict(v, index=v['index'] - k_rm) for k, v in sp.items() if k not in removed}     # resolve.py:138-164
+        so = sum(v.get('size', 1) for v in special_dict.values())
+        # ---- per (window, observation): trimmed P / q, resized to the window's tau range (resolve.py:11-135)
+        import torch
+        p_rows, q_rows, xrem = [], [], []
+        tau_win = []
+        for w in windows:
+            lo = min(self.obs_tau_indices[i][0] for i in w)
+            hi = max(self.obs_tau_indices[i][1] for i in w)
+            tau_win.append((lo, hi))
+        nc = so + max(hi - lo for lo, hi in tau_win)
+        if any(so + hi - lo != nc for lo, hi in tau_win):
+            raise NotImplementedError('hybdrt_b200: resolve windows with different tau ranges in one call')
+        cs = self.obs_scales['coefficient_scale']
+        rs_, ro_ = self.obs_scales['response_signal_scale'], self.obs_scales['scaled_response_offset']
+        p_res = torch.zeros(len(flat), nc, nc, dtype=torch.float64, device=eng.device)
+        q_res = torch.zeros(len(flat), nc, dtype=torch.float64, device=eng.device)
+        for pos, (w, (lo, hi)) in enumerate(zip(windows, tau_win)):
+            for r, i in enumerate(w):
+                sid, row = self._pq_ref[int(i)]
+                st = self._pq_store[sid]
+                vb = np.atleast_1d(np.asarray(self.obs_special['v_baseline'][i], dtype=float)) / rs_[i]
+                vb[0] += ro_[i]
+                vb = vb * np.atleast_1d(st['v_baseline_scale'])
+                x_rm = eng.dev(np.concatenate([vb, [float(self.obs_special['vz_offset'][i])]]))
+                p_full, q_full = st['p'][row], st['q'][row]
+                p_t, q_t = p_full[k_rm:, k_rm:], q_full[k_rm:] + x_rm @ p_full[:k_rm, k_rm:]
+                tl, tr_ = self.obs_tau_indices[i]
+                a, b = so + (tl - lo), nc + (tr_ - hi)                      # expand (resolve.py:84-100)
+                dst = pos * nr + r
+                p_res[dst, :so, :so], q_res[dst, :so] = p_t[:so, :so], q_t[:so]
+                p_res[dst, a:b, a:b], q_res[dst, a:b] = p_t[so:, so:], q_t[so:]
+                p_res[dst, a:b, :so], p_res[dst, :so, a:b] = p_t[so:, :so], p_t[:so, so:]
+        # ---- coupling and parameter scales per window (resolve.py:223-273)
+        my = np.zeros((len(windows), nr, nr))
+        pscale = np.ones((len(windows), nc))
+        ly = gaussian_filter1d(np.eye(nr), sigma=sigma, mode='reflect', order=2)
+        for pos, w in enumerate(windows):
+            scale_vec = cs[w]
+            smooth = gaussian_filter1d(median_filter(scale_vec, 3), 2)
+            lys = ly @ np.diag(scale_vec / smooth)
+            my[pos] = (lys.T @ lys) * lambda_psi
+            if 'R_inf' in special_dict:
+                x_inf = self.obs_special['R_inf'][w] / scale_vec
+                pscale[pos, special_dict['R_inf']['index']] = (5 * np.std(x_inf)) ** -2
+        h = np.zeros(nc) if self.fit_kw['nonneg'] else 10.0 * np.ones(nc)
+        for v in special_dict.values():
+            if v['nonneg']:
+                h[v['index']:v['index'] + v.get('size', 1)] = 0.0
+        out = eng.resolve_qp_batch(p_res, q_res, np.arange(len(windows)) * nr, my, pscale, h, nr)
+        x_all = out['x'].cpu().numpy()
+        self.last_resolve = dict(iters=out['iters'].cpu().numpy(), status=out['status'].cpu().numpy())
+        results = []
+        for pos, (w, tw) in enumerate(zip(windows, tau_win)):
+            x = x_all[pos]
+            scale_vec = cs[w]
+            x_special = {}
+            for key, info in special_dict.items():                       # resolve.unpack_resolved_x :344-375
+                xk = x[:, info['index']:info['index'] + info.get('size', 1)] * scale_vec[:, None]
+                if key == 'inductance':
+                    xk = xk * self._pq_store[self._pq_ref[int(w[0])][0]]['inductance_scale']
+                elif key == 'C_inv':
+                    xk = xk * self._pq_store[self._pq_ref[int(w[0])][0]]['capacitance_scale']
+                x_special[key] = xk.flatten() if info.get('size', 1) == 1 else xk
+            results.append((x[:, so:] * scale_vec[:, None], x_special, tw))
+        return results
+
+    def _insert_resolved(self, obs_index, x_drt, x_special, tau_indices):
+        self.obs_x_resolved[obs_index, tau_indices[0]:tau_indices[1]] = x_drt
+        for key, val in x_special.items():
+            self.obs_special_resolved[key][obs_index] = val
+        self.obs_resolve_status[obs_index] = True
+
+    def resolve_observations(self, obs_index, psi_sort_dims=None, psi_distance_dims=None, truncate=False, sigma=1,
+                             lambda_psi=1, tau_filter_sigma=0, special_filter_sigma=0):
+        """drtmd.py:432-484"""
+        if tau_filter_sigma or special_filter_sigma:
+            raise NotImplementedError('hybdrt_b200: resolve with tau_filter_sigma / special_filter_sigma')
+        self._ensure_len()
+        obs_index = np.asarray(obs_index)
+        obs_index = obs_index[self.obs_fit_status[obs_index] & ~self.obs_ignore_flag[obs_index]]
+        if psi_sort_dims is not None:
+            obs_index = self._sorted(obs_index, psi_sort_dims)
+        if len(obs_index) == 1:
+            warnings.warn('Only one observation included in resolution group; raw parameters will be copied')
+            ti = self.obs_tau_indices[obs_index[0]]
+            self._insert_resolved(obs_index, self.obs_x[obs_index, ti[0]:ti[1]],
+                                  {k: v[obs_index] for k, v in self.obs_special.items()}, ti)
+        elif len(obs_index) > 1:
+            (x_drt, x_special, ti), = self._resolve_windows([obs_index], truncate, sigma, lambda_psi)
+            self._insert_resolved(obs_index, x_drt, x_special, ti)
+        else:
+            warnings.warn('No valid observations included in resolution group')
+
+    def resolve_group(self, group_id, batch_size=7, overlap=2, psi_sort_dims=None, psi_distance_dims=None,
+                      truncate=False, sigma=1, lambda_psi=1, tau_filter_sigma=0, special_filter_sigma=0):
+        """drtmd.py:486-560: windows of batch_size observations with `overlap` shared neighbours, every window one QP
+        (all of them in ONE launch here), the overlapping solutions averaged with margin weights."""
+        if tau_filter_sigma or special_filter_sigma:
+            raise NotImplementedError('hybdrt_b200: resolve with tau_filter_sigma / special_filter_sigma')
+        self._ensure_len()
+        obs_index = self.get_group_index(group_id)
+        obs_index = obs_index[self.obs_fit_status[obs_index] & ~self.obs_ignore_flag[obs_index]]
+        obs_index = self._sorted(obs_index, psi_sort_dims, psi_distance_dims)
+        self.obs_x_resolved[obs_index] = 0
+        num_obs = len(obs_index)
+        if num_obs < 2:
+            return self.resolve_observations(obs_index, psi_sort_dims, psi_distance_dims, truncate, sigma, lambda_psi)
+        batch_size = min(batch_size, num_obs)
+        stride = max(batch_size - overlap, 1)
+        spans = []
+        for start in range(0, num_obs, stride):
+            if num_obs - start < batch_size:
+                start = max(0, num_obs - batch_size)                       # a full batch for the last one
+            spans.append((start, start + batch_size))
+            if start + batch_size >= num_obs:
+                break
+        results = self._resolve_windows([obs_index[a:b] for a, b in spans], truncate, sigma, lambda_psi)
+        nb = len(spans)
+        x_batch = np.zeros((nb, *self.obs_x_resolved[obs_index].shape))
+        x_special = {k: np.zeros((nb, *v[obs_index].shape)) for k, v in self.obs_special_resolved.items()}
+        margins = np.full((nb, num_obs), -1.0)
+        for i, ((a, b), (x_drt, xs, ti)) in enumerate(zip(spans, results)):
+            self._insert_resolved(obs_index[a:b], x_drt, xs, ti)
+            x_batch[i, a:b] = self.obs_x_resolved[obs_index[a:b]]
+            for key in self.obs_special_resolved:
+                x_special[key][i, a:b] = self.obs_special_resolved[key][obs_index[a:b]]
+            margins[i, a:b] = np.minimum(np.arange(batch_size), np.arange(batch_size)[::-1])
+        if overlap > 0 and num_obs > 1:
+            wts = margins + 0.1
+            wts[wts < 0] = 0
+            xw = np.moveaxis(np.tile(wts, (x_batch.shape[-1], 1, 1)), 0, -1)
+            self.obs_x_resolved[obs_index] = np.average(x_batch, axis=0, weights=xw)
+            for key, val in x_special.items():
+                kw_ = np.moveaxis(np.tile(wts, (val.shape[-1], 1, 1)), 0, -1) if np.ndim(val) > 2 else wts
+                self.obs_special_resolved[key][obs_index] = np.average(val, axis=0, weights=kw_)

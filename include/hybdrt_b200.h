@@ -249,6 +249,37 @@ long long hdrt_qphb_smem_bytes(int n_rows, int n_cols);
 /* One persistent CTA per spectrum in flight; spectra are pulled from a device-side work counter. */
 int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Cross-observation resolve (reference: hybdrt/mapping/resolve.py resolve_observations :176-341, reached from
+ * DRTMD.resolve_observations / resolve_group, mapping/drtmd.py:432-560): one QP per window of `nr` consecutive
+ * observations, n = nr * nc unknowns,
+ *     minimise 1/2 x'Px + q'x,  -x <= h,    P = blockdiag(P_1 .. P_nr) + My (x) diag(param_scale),
+ * solved by the same interior-point iteration as cvxopt.solvers.qp (resolve.py:334).  The caller supplies, per
+ * observation, the fit's P / q with the data-dependent parameters folded away and resized to the window's common tau
+ * range (resolve.get_offset_pq :11-62, resize_pq :65-135).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hdrt_resolve_problem {
+    int n_windows;
+    int nr;                    /* observations per window                                                   */
+    int nc;                    /* parameters per observation; nr * nc <= 1024                               */
+    const double* p;           /* [n_obs][nc][nc] per-observation P (symmetric, row-major)                  */
+    const double* q;           /* [n_obs][nc]                                                               */
+    const int* first_obs;      /* [n_windows] first observation of the window (its nr observations are
+                                  consecutive in p / q)                                                     */
+    const double* my;          /* [n_windows][nr][nr]  lambda_psi * My (resolve.py:223-273)                 */
+    const double* param_scale; /* [n_windows][nc]      (resolve.py:236-262)                                 */
+    const double* h;           /* [nc] rhs of -x <= h for one observation (resolve.py:318-329)              */
+    double* x;                 /* [n_windows][nr][nc]  res['x'] of every window                             */
+    int* iters;                /* [n_windows] interior-point iterations (optional)                          */
+    int* status;               /* [n_windows] HDRT_ST_QP_MAXITERS / HDRT_ST_KKT_FAIL bits (optional)        */
+} hdrt_resolve_problem;
+
+/* Bytes of device scratch hdrt_resolve_qp_batch needs for this shape (the Cholesky factors of the windows in flight). */
+long long hdrt_resolve_work_bytes(const hdrt_handle* h, int n_windows, int nr, int nc);
+
+/* One CTA per window; `work` is a device buffer of hdrt_resolve_work_bytes bytes. */
+int hdrt_resolve_qp_batch(hdrt_handle* h, const hdrt_resolve_problem* prob, void* work, void* stream);
+
 /* FP64 FMA probe: runs a register-resident DFMA loop on every SM, on `stream`, and returns achieved TFLOP/s
  * (host-synchronous on that stream; used by bench.py for the FP64 roofline denominator). */
 int hdrt_probe_fp64(hdrt_handle* h, double* tflops_host, void* stream);

@@ -1073,3 +1073,35 @@ def test_consecutive_steps_and_hybrid_map_against_the_reference():
     for key in ('R_inf', 'inductance', 'v_baseline', 'vz_offset'):
         assert rel_err(md.obs_special[key], h['special_' + key]) < FIT_TOL, key
     assert rel_err(md.obs_rss, h['obs_rss']) < FIT_TOL and rel_err(md.obs_llh, h['obs_llh']) < FIT_TOL
+
+
+def test_cross_observation_resolve_against_the_reference():
+    """mapping/resolve.py:176-341 through DRTMD.resolve_observations / resolve_group (drtmd.py:432-560): one window of
+    seven hybrid observations, then a group of nine in windows of seven with two shared neighbours (margin-weighted
+    averaging).  Interior-point iteration counts identical to the reference's, resolved parameters within 1e-6."""
+    from hybdrt_b200.mapping import DRTMD
+    g = load_golden('drtmd_resolve.npz')
+    md = DRTMD(tau_supergrid=g['tau_supergrid'], psi_dim_names=['k'], print_progress=False, keep_pq=True)
+    for b in range(9):
+        md.add_observation([float(b)], (g['times'], g['i_signal'], g['v'][b]), (g['freq'], g['z'][b]), group_id='g')
+    md.fit_all()
+    assert md.obs_fit_status.all()
+    for b in range(9):
+        assert rel_err(md.obs_x[b], g['obs_x'][b]) < FIT_TOL
+    md.resolve_observations(np.arange(7), psi_sort_dims=['k'], sigma=1, lambda_psi=1)
+    assert md.last_resolve['iters'].tolist() == g['win_ipm'].tolist() and not md.last_resolve['status'].any()
+    assert md.obs_resolve_status[:7].all() and not md.obs_resolve_status[7:].any()
+    for b in range(7):
+        assert rel_err(md.obs_x_resolved[b], g['win_x_resolved'][b]) < FIT_TOL, b
+    for key in ('R_inf', 'inductance'):
+        assert rel_err(md.obs_special_resolved[key][:7], g['win_special_' + key]) < FIT_TOL, key
+    md.resolve_group('g', batch_size=7, overlap=2, psi_sort_dims=['k'], sigma=1, lambda_psi=1)
+    assert md.last_resolve['iters'].tolist() == g['grp_ipm'].tolist()
+    assert md.obs_resolve_status.all()
+    for b in range(9):
+        assert rel_err(md.obs_x_resolved[b], g['grp_x_resolved'][b]) < FIT_TOL, b
+    for key in ('R_inf', 'inductance'):
+        assert rel_err(md.obs_special_resolved[key], g['grp_special_' + key]) < FIT_TOL, key
+    assert np.all(np.isfinite(md.obs_x_resolved)) and md.obs_x_resolved.min() > -1e-6
+    with pytest.raises(ValueError):
+        DRTMD(tau_supergrid=g['tau_supergrid'], print_progress=False)._resolve_windows([np.arange(2)], False, 1, 1)

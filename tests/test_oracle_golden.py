@@ -317,3 +317,28 @@ def test_coneqp_small_kat():
     res = coneqp_orthant(np.eye(4), -c, np.zeros(4))
     assert res['status'] == 'optimal'
     assert np.allclose(res['x'], np.maximum(c, 0), atol=1e-6)
+
+
+def test_resolve_oracle_against_the_reference_fixture():
+    """mapping/resolve.py through DRTMD.resolve_observations (one window of seven hybrid observations)."""
+    from oracle import resolve_oracle as ro
+    g = load_golden('drtmd_resolve.npz')
+    names = [str(s) for s in g['special_names']]
+    assert names == ['v_baseline', 'vz_offset', 'R_inf', 'inductance']
+    p_list, q_list = [], []
+    match = (int(g['obs_tau_indices'][:7, 0].min()), int(g['obs_tau_indices'][:7, 1].max()))
+    for i in range(7):
+        xr = np.concatenate([ro.scaled_v_baseline(g['fit_v_baseline'][i], g['fit_response_signal_scale'][i],
+                                                  g['fit_scaled_response_offset'][i], g['fit_v_baseline_scale'][i]),
+                             [g['fit_vz_offset'][i]]])
+        p, q = ro.offset_pq(g['fit_p'][i], g['fit_q'][i], xr)
+        p, q = ro.resize_pq(p, q, 2, tuple(g['obs_tau_indices'][i]), match)
+        p_list.append(p)
+        q_list.append(q)
+    scale = g['fit_coefficient_scale'][:7]
+    x, iters, _ = ro.resolve_window(p_list, q_list, scale, g['fit_R_inf'][:7] / scale, 0, True, [0, 1])
+    assert iters == int(g['win_ipm'][0])
+    x_drt = x[:, 2:] * scale[:, None]
+    assert rel_err(x_drt, g['win_x_resolved'][:, match[0]:match[1]]) < 1e-9
+    assert rel_err(x[:, 0] * scale, g['win_special_R_inf']) < 1e-9
+    assert rel_err(x[:, 1] * scale * g['fit_inductance_scale'][:7], g['win_special_inductance']) < 1e-9
