@@ -243,6 +243,61 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def builder_rooflines(eng, drt, flush, hbm_peak):
+    """Achieved HBM write bandwidth of the other matrix builders (algorithmic bytes of SURVEY.md section 8d over the
+    CUDA-event time of one launch on n_grids independent grids, L2 flushed): the chrono step-response matrix (C3 shape),
+    the dense chrono variance matrix, the penalty matrices, the DOP columns, the trapz-mode impedance matrices (FP64 /
+    transcendental bound: reported with its evaluation rate)."""
+    import torch
+    from hybdrt_b200 import engine as E, synth
+
+    def timed(fn, nbytes, reps=3):
+        fn()
+        fn()
+        ms = []
+        for k in range(reps):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        sec = float(np.mean(ms)) * 1e-3
+        return {'achieved': nbytes / sec / 1e9, 'unit': 'GB/s', 'frac': nbytes / sec / 1e9 / hbm_peak, 'ms': sec * 1e3,
+                'bytes_per_launch': nbytes}
+
+    res = {}
+    eps = drt.tau_epsilon
+    tab = drt.interpolate_lookups
+    t3, i3, _, _, _ = synth.make_hybrid_batch(1, seed=1)
+    tau = np.logspace(-7, 2, 94)
+    g = 512
+    times = eng.dev(np.repeat(t3[None], g, 0) * (1 + 1e-4 * np.arange(g)[:, None] / g))
+    taus = eng.dev(np.repeat(tau[None], g, 0))
+    st, sa = eng.dev(np.zeros((g, 1))), eng.dev(np.full((g, 1), 1e-2))
+    res['response_interp_kernel'] = dict(timed(lambda: eng.build_response(times, taus, st, sa, eps, E.MODE_INTERP, tab), 8.0 * g * len(t3) * len(tau)),
+                                         workload=f'{g} grids, {len(t3)} samples x {len(tau)} basis (C3 shape)')
+    g = 16
+    res['chrono_vmm_kernel'] = dict(timed(lambda: eng.build_chrono_vmm(times[:g], st[:g], 4.0), 8.0 * g * len(t3) ** 2),
+                                    workload=f'{g} grids, {len(t3)}^2 dense variance matrix')
+    g = 8192
+    grid = eng.dev(np.repeat(np.log(np.logspace(-7, 3, 101))[None], g, 0) * (1 + 1e-6 * np.arange(g)[:, None] / g))
+    res['penalty_kernel'] = dict(timed(lambda: eng.build_penalty(grid, eps, False), 24.0 * g * 101 ** 2),
+                                 workload=f'{g} grids, M0..M2 101 x 101 (general path, no Toeplitz fill)')
+    g = 8192
+    freq = eng.dev(np.repeat(synth.C2_FREQ[None], g, 0) * (1 + 1e-3 * np.arange(g)[:, None] / g))
+    nu = np.linspace(-1, 1, 51)
+    res['dop_z_kernel'] = dict(timed(lambda: eng.build_dop_z(freq, nu, 5.0), 16.0 * g * 70 * len(nu)),
+                               workload=f'{g} grids, 70 freqs x {len(nu)} phasance basis (complex erf per entry)')
+    g = 64
+    tz = timed(lambda: eng.build_impedance(freq[:g], eng.dev(np.repeat(np.logspace(-7, 3, 101)[None], g, 0)), eps, E.MODE_TRAPZ), 16.0 * g * 70 * 101)
+    tz['integrand_evaluations_per_s'] = 2.0 * g * 70 * 101 * 1000 / (tz['ms'] * 1e-3)
+    res['impedance_trapz_kernel'] = dict(tz, bound='fp64 + transcendental (1000-point quadrature per entry), not HBM',
+                                         workload=f'{g} grids, 70 x 101, A_re + A_im')
+    return res
+
+
 def other_configs(eng, fp64_peak, flush):
     """BASELINE configs C3 (hybrid) and C4 (DRT+DOP) at full size: the fit kernel re-launched on the inputs already
     resident in HBM (the launch the public API made), CUDA events, FP64 roofline fraction from the same flop model."""
@@ -584,6 +639,7 @@ def run_gpu(args):
                                        'bytes_per_launch': filt_bytes,
                                        'workload': f'{n_tr} raw traces x {len(rt)} samples -> {len(dec)} kept samples each '
                                                    f'(downsample_data, decimation_interval=8, factor 2)'},
+            'roofline_builders': builder_rooflines(eng, drt, flush, hbm_peak) if (world == 1 and not args.no_configs) else None,
             'cpu_baseline': cpu,
             'parity': parity,
             'configs': other_configs(eng, fp64_peak, flush) if (world == 1 and not args.no_configs) else None,

@@ -312,6 +312,80 @@ impedance_interp_kernel(const double* __restrict__ freq, const double* __restric
     }
 }
 
+// Step-response matrix, interp mode, production path (mat1d.py:16-122): the same persistent scheme as the impedance
+// builder.  ln((t - t_k) / tau_m) is formed as ln(t - t_k) - ln(tau_m) (logs once per row and step / per column, against
+// one division and one log per entry and step), the lookup is the (slope, intercept) table in shared memory.  A work
+// item is `rows_per_item` rows of one grid.  Needs a uniform lookup table and bounded arguments (else the generic
+// kernel below runs).
+__global__ void __launch_bounds__(kIThreads, 2)
+response_interp_fast_kernel(const double* __restrict__ times, const double* __restrict__ tau,
+                            const double* __restrict__ step_times, const double* __restrict__ step_sizes, int n_grids,
+                            int nt, int nb, int n_steps, const double* __restrict__ td_x, const double* __restrict__ td_v,
+                            int npts, double* __restrict__ rm, int rows_per_item, int tiles_per_grid, int* __restrict__ fallback) {
+    extern __shared__ __align__(16) double sm[];
+    double2* t_sc = reinterpret_cast<double2*>(sm);                  // [npts + 1], see interp_smem
+    double* s_ltau = reinterpret_cast<double*>(t_sc + npts + 1);     // [nb] ln tau
+    double* s_lt = s_ltau + nb;                                      // [rows_per_item][n_steps] ln(t - t_k), NaN where t <= t_k
+    double* s_sa = s_lt + (size_t)rows_per_item * n_steps;           // [n_steps]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < npts - 1; i += kIThreads) {
+        const double sl = (__ldg(td_v + i + 1) - __ldg(td_v + i)) / (__ldg(td_x + i + 1) - __ldg(td_x + i));
+        t_sc[i + 1] = make_double2(sl, fma(-sl, __ldg(td_x + i), __ldg(td_v + i)));
+    }
+    if (tid == 0) { t_sc[0] = make_double2(0.0, __ldg(td_v)); t_sc[npts] = make_double2(0.0, __ldg(td_v + npts - 1)); }
+    SmemTable tt;
+    tt.x = nullptr; tt.sc = t_sc; tt.x0 = __ldg(td_x); tt.xn = __ldg(td_x + npts - 1); tt.v0 = __ldg(td_v); tt.vn = __ldg(td_v + npts - 1);
+    tt.inv_dx = (double)(npts - 1) / (tt.xn - tt.x0);
+    tt.pos0 = -tt.x0 * tt.inv_dx - 0.5;
+    tt.uniform = true;
+    int bad = 0;
+    for (int i = tid; i < npts; i += kIThreads)
+        if (fabs((__ldg(td_x + i) - tt.x0) * tt.inv_dx - (double)i) > 1e-9) bad = 1;
+    const double half_xmax = 0.5 * (1073741824.0 - fabs(tt.pos0)) / tt.inv_dx;
+    const int groups = nb <= kIThreads ? kIThreads / nb : 1;
+    const int col0 = nb <= kIThreads ? tid % nb : tid;
+    const int rg = nb <= kIThreads ? tid / nb : 0;
+    const long long items = (long long)n_grids * tiles_per_grid;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const int g = (int)(item / tiles_per_grid);
+        const int r0 = (int)(item - (long long)g * tiles_per_grid) * rows_per_item;
+        const int rows = min(rows_per_item, nt - r0);
+        __syncthreads();                                              // the previous item is done with the staging vectors
+        for (int i = tid; i < nb; i += kIThreads) {
+            const double v = log(tau[(size_t)g * nb + i]);
+            s_ltau[i] = v;
+            if (!(fabs(v) < half_xmax)) bad = 1;
+        }
+        for (int i = tid; i < n_steps; i += kIThreads) s_sa[i] = step_sizes[(size_t)g * n_steps + i];
+        for (int i = tid; i < rows * n_steps; i += kIThreads) {
+            const int rr = i / n_steps, k = i - rr * n_steps;
+            const double dt = times[(size_t)g * nt + r0 + rr] - step_times[(size_t)g * n_steps + k];
+            const double v = dt > 0.0 ? log(dt) : nan("");
+            s_lt[i] = v;
+            if (dt > 0.0 && !(fabs(v) < half_xmax)) bad = 1;
+        }
+        if (__syncthreads_or(bad)) {                                  // odd table or unbounded arguments: the generic kernel redoes it all
+            if (tid == 0) *fallback = 1;
+            return;
+        }
+        if (rg < groups) {
+            for (int col = col0; col < nb; col += kIThreads) {
+                const double ltau = s_ltau[col];
+                double* __restrict__ po = rm + ((size_t)g * nt + r0 + rg) * nb + col;
+                const size_t step = (size_t)groups * nb;
+                for (int rr = rg; rr < rows; rr += groups, po += step) {
+                    double acc = 0.0;
+                    for (int k = 0; k < n_steps; ++k) {
+                        const double lt = s_lt[rr * n_steps + k];
+                        if (lt == lt) acc += __dmul_rn(interp_smem<true, false>(lt - ltau, tt, npts), s_sa[k]);
+                    }
+                    __stcs(po, acc);
+                }
+            }
+        }
+    }
+}
+
 // trapz mode: one warp per entry, both parts
 __global__ void impedance_trapz_kernel(const double* __restrict__ freq, const double* __restrict__ tau, int n_grids,
                                        int nf, int nb, double eps, int quad_points, double* __restrict__ a_re,
@@ -336,7 +410,8 @@ __global__ void response_interp_kernel(const double* __restrict__ times, const d
                                        const double* __restrict__ step_times, const double* __restrict__ step_sizes,
                                        int nt, int nb, int n_steps, const double* __restrict__ td_x,
                                        const double* __restrict__ td_v, int npts, double* __restrict__ rm,
-                                       int rows_per_cta) {
+                                       int rows_per_cta, const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;     // the fast kernel took the job
     extern __shared__ double sm[];
     double* s_tau = sm;
     double* s_t = sm + nb;
@@ -695,13 +770,35 @@ extern "C" int hdrt_build_response(int mode, const double* times, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == HDRT_MODE_INTERP) {
         if (!td_x || !td_v || grid_points < 2) { set_error("interp mode needs the response lookup"); return HDRT_ERR_ARG; }
+        const int* run_flag = nullptr;
+        {   // production path: persistent CTAs with the lookup table in shared memory (falls through if it declines)
+            int dev = 0, sms = 148;
+            HDRT_CUDA_CHECK(cudaGetDevice(&dev));
+            HDRT_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const int ctas = 2 * sms;
+            int rows_per_item = 128;
+            while (rows_per_item > 8 && (long long)n_grids * ((nt + rows_per_item - 1) / rows_per_item) < ctas) rows_per_item /= 2;
+            const int tiles = (nt + rows_per_item - 1) / rows_per_item;
+            const size_t fsmem = sizeof(double) * (2 * ((size_t)grid_points + 1) + nb + (size_t)rows_per_item * n_steps + n_steps);
+            static int* d_flag = nullptr;           // one-word device flag: the fast kernel sets it when it declines
+            if (fsmem <= 110 * 1024 && nb <= 4096) {
+                if (!d_flag) HDRT_CUDA_CHECK(cudaMalloc(&d_flag, sizeof(int)));
+                HDRT_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+                HDRT_CUDA_CHECK(cudaFuncSetAttribute(response_interp_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                const long long items = (long long)n_grids * tiles;
+                response_interp_fast_kernel<<<(int)(items < ctas ? items : ctas), kIThreads, fsmem, st>>>(
+                    times, tau, step_times, step_sizes, n_grids, nt, nb, n_steps, td_x, td_v, grid_points, rm, rows_per_item, tiles, d_flag);
+                HDRT_CUDA_CHECK(cudaGetLastError());
+                run_flag = d_flag;          // the generic kernel below runs only if the fast one declined (no host round trip)
+            }
+        }
         int rows_per_cta = 64;
         while (rows_per_cta > 8 && (long long)n_grids * ((nt + rows_per_cta - 1) / rows_per_cta) < 148 * 8) rows_per_cta /= 2;
         dim3 grid(n_grids, (nt + rows_per_cta - 1) / rows_per_cta);
         const size_t smem = sizeof(double) * (nb + rows_per_cta + 2 * n_steps);
         if (smem > 48 * 1024) { set_error("too many steps / basis points for the staging buffer"); return HDRT_ERR_UNSUPPORTED; }
         response_interp_kernel<<<grid, kMThreads, smem, st>>>(times, tau, step_times, step_sizes, nt, nb, n_steps, td_x,
-                                                              td_v, grid_points, rm, rows_per_cta);
+                                                              td_v, grid_points, rm, rows_per_cta, run_flag);
     } else if (mode == HDRT_MODE_TRAPZ) {
         const long long total = (long long)n_grids * nt * nb;
         response_trapz_kernel<<<grid_for(total * 32, kMThreads), kMThreads, 0, st>>>(times, tau, step_times, step_sizes,
