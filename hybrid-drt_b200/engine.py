@@ -150,7 +150,7 @@ class Engine:
         self._lookups = {}
         self._pinned = {}
         self.launches = 0           # kernels launched through this engine (bench.py reports it)
-        self.max_pinned_shapes = 8
+        self.max_pinned_shapes = 16
 
     def close(self):
         if getattr(self, 'handle', None):

@@ -69,6 +69,7 @@ class DRTMD:
     def clear_obs(self):
         self.obs_psi = np.zeros((0, len(self.psi_dim_names))) if self.psi_dim_names is not None else None
         self.obs_data, self.obs_group_id = [], []
+        self._blocks = []
         self.obs_data_badness = np.zeros(0)
         self.obs_ignore_flag = np.zeros(0, dtype=bool)
         self._n = 0
@@ -167,6 +168,7 @@ class DRTMD:
         f = np.asarray(eis_frequencies, dtype=float)
         nt = len(self.tau_supergrid)
         self.obs_psi = np.vstack([self.obs_psi, psi])
+        self._blocks.append((self._n, nb, f, z))        # bulk block: grouping and input stacking work on the arrays directly
         self.obs_data.extend((None, (f, z[b])) for b in range(nb))
         self.obs_group_id.extend([None] * nb)
         self.obs_data_badness = np.concatenate([self.obs_data_badness, np.zeros(nb)])
@@ -208,13 +210,37 @@ class DRTMD:
     def _group(self, obs_index):
         """Observations by measurement grid.  Arrays shared by identity (bulk adds) are hashed once."""
         groups, by_id = {}, {}
+        obs_index = np.asarray(obs_index, dtype=int)
+        if self._blocks and len(obs_index) > 64:
+            # members of bulk blocks (add_observations): one key per block, no per-observation Python work
+            starts = np.array([b[0] for b in self._blocks])
+            ends = starts + np.array([b[1] for b in self._blocks])
+            blk = np.searchsorted(starts, obs_index, side='right') - 1
+            inside = (blk >= 0) & (obs_index < ends[np.maximum(blk, 0)])
+            for bi in np.unique(blk[inside]):
+                f = self._blocks[bi][2]
+                key = self._grid_key((None, None, None), (f, None))
+                groups.setdefault(key, []).extend(obs_index[inside & (blk == bi)].tolist())
+            obs_index = obs_index[~inside]
         for idx in obs_index:
+            idx = int(idx)
             chrono, eis = self.get_obs_data(idx)
             ident = (id(chrono[0]), id(chrono[1]), id(eis[0]))
             if ident not in by_id:
                 by_id[ident] = self._grid_key(chrono, eis)
             groups.setdefault(by_id[ident], []).append(idx)
         return groups
+
+    def _block_z(self, local):
+        """z [len(local), Nf] straight from the bulk block all of `local` belongs to (None if they do not share one)."""
+        if not self._blocks or len(local) == 0:
+            return None
+        for start, nb, _, z in self._blocks:
+            if local[0] >= start and local[0] < start + nb:
+                if local.min() >= start and local.max() < start + nb:
+                    return np.asarray(z)[local - start]
+                return None
+        return None
 
     def fit_observation(self, obs_index, ignore_errors=False):
         self.fit_observations([obs_index], ignore_errors=ignore_errors, _quiet=True)
@@ -247,8 +273,10 @@ class DRTMD:
         local = members[mine]
         z = v = None
         if eis0[0] is not None:
-            z = np.stack([np.asarray(self.obs_data[i][1][1]) for i in local]) if len(local) else \
-                np.zeros((0, len(eis0[0])), dtype=complex)
+            z = self._block_z(local)
+            if z is None:
+                z = np.stack([np.asarray(self.obs_data[i][1][1]) for i in local]) if len(local) else \
+                    np.zeros((0, len(eis0[0])), dtype=complex)
         if chrono0[0] is not None:
             v = np.stack([np.asarray(self.obs_data[i][0][2], dtype=float) for i in local]) if len(local) else \
                 np.zeros((0, len(chrono0[0])))
@@ -278,7 +306,7 @@ class DRTMD:
                                  f'{len(self.pfrt_factors)} entries')
             fp = res.extract_parameters(step_x)                 # format_1d_params, drtmd.py:1145-1158
         else:
-            fp = res.fit_parameters()
+            fp = res.extract_parameters(res.host(['x'])['x'])      # the map keeps coefficients, not per-point sigmas: no weights copy
         host = res.host(['status', 'n_outer'])
         left = nearest_index(self.tau_supergrid, drt.basis_tau[0])
         right = nearest_index(self.tau_supergrid, drt.basis_tau[-1]) + 1

@@ -198,11 +198,23 @@ class BatchFit:
         if self._host is None:
             self._host = {}
         want = list(self.raw.keys()) if keys is None else keys
-        missing = [k for k in want if k not in self._host and k in self.raw]
+        missing = [k for k in want if k not in self._host and k in self.raw and isinstance(self.raw[k], torch.Tensor)]
         if missing:
-            torch.cuda.current_stream(self.raw[missing[0]].device).synchronize()
+            # through page-locked staging tensors: a pageable .cpu() of the big per-spectrum arrays runs at ~2 GB/s
+            # (the staging buffers are the engine's cached ones -- page-locking memory costs about as much as the copy --
+            # so the arrays handed out are copies of them, not views)
+            eng = self.plan['model'].engine
+            stream = torch.cuda.current_stream(self.raw[missing[0]].device)
             for k in missing:
-                self._host[k] = self.raw[k].cpu().numpy()
+                t = self.raw[k]
+                if t.numel() * t.element_size() >= (1 << 20):
+                    buf = eng.pinned(*t.shape, dtype=t.dtype)
+                    buf.copy_(t, non_blocking=True)
+                    stream.synchronize()
+                    self._host[k] = buf.numpy().copy()
+                else:
+                    stream.synchronize()
+                    self._host[k] = t.cpu().numpy()
         return self._host
 
     @property
@@ -281,11 +293,13 @@ class BatchFit:
     # ---- post-fit diagnostics of the mapping path (drtmd.py:256-279); need diag_tau at fit time
     def _uniform_weights(self):
         """weights='uniform': the mean estimated weight of each domain (drt1d.py:4433-4447)."""
-        ew = self.host(['est_weights'])['est_weights']
-        nc = self.plan['n_chrono']
-        wc = ew[:, :nc].mean(axis=1) if nc else np.zeros(len(ew))
-        we = ew[:, nc:].mean(axis=1) if ew.shape[1] > nc else np.zeros(len(ew))
-        return wc, we
+        if getattr(self, '_uw', None) is None:       # evaluate_rss and evaluate_llh both ask for it
+            ew = self.host(['est_weights'])['est_weights']
+            nc = self.plan['n_chrono']
+            wc = ew[:, :nc].mean(axis=1) if nc else np.zeros(len(ew))
+            we = ew[:, nc:].mean(axis=1) if ew.shape[1] > nc else np.zeros(len(ew))
+            self._uw = (wc, we)
+        return self._uw
 
     def evaluate_rss(self, normalize=True):
         """DRT.evaluate_rss(weights='uniform') (drt1d.py:4433-4459, qphb.evaluate_rss :1347-1352)."""
