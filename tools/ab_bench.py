@@ -9,8 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hybdrt_b200 import engine as E, synth  # noqa: E402
 from hybdrt_b200.models import DRT  # noqa: E402
-B = 10000
-freq, z = synth.make_eis_batch(B, seed=0)
+CONFIG = os.environ.get('AB_CONFIG', 'c2')          # c2 (default) or c4 (DRT + DOP, n = 153)
+B = 10000 if CONFIG == 'c2' else 2960
+freq, z = synth.make_eis_batch(B, seed=0) if CONFIG == 'c2' else synth.make_dop_batch(B, seed=2)
 libs = sys.argv[1:]
 res = {}
 for rep in range(2):
@@ -18,7 +19,7 @@ for rep in range(2):
         E._lib = None
         E._engines.clear()
         E.LIB_PATH = os.path.join(ROOT, 'hybrid-drt_b200', '_lib', name)
-        drt = DRT()
+        drt = DRT() if CONFIG == 'c2' else DRT(fit_dop=True)
         r0 = drt.fit_eis_batch(freq, z)
         plan = r0.plan
         zs = z / r0.scales['coefficient_scale'][:, None]
@@ -27,7 +28,8 @@ for rep in range(2):
         hyp = drt._c_hypers(plan['opts'])
         out = {}
         def step():
-            eng.qphb_fit_batch(plan['rm'], rv, plan['pen'], plan['h'], plan['l1'], plan['n_special'], vmm_eis=plan['vmm_eis'], hypers=hyp, out=out, pen_hint=plan.get('pen_hint'))
+            eng.qphb_fit_batch(plan['rm'], rv, plan['pen'], plan['h'], plan['l1'], plan['n_special'], vmm_eis=plan['vmm_eis'], hypers=hyp, out=out, pen_hint=plan.get('pen_hint'),
+                               dop_range=(drt.dop_indices if CONFIG != 'c2' else None))
         step(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

@@ -47,3 +47,25 @@ for rep in range(2):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 print(f'one launch, {len(wins)} windows: {dt:.2f} s ({len(wins) / dt:.1f} windows/s incl. host assembly)')
+# kernel alone (CUDA events around the launch inside _resolve_windows)
+eng = md.drt1d.engine
+orig = eng.resolve_qp_batch
+times_ms = []
+
+
+def timed(*a, **k):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = orig(*a, **k)
+    e1.record()
+    torch.cuda.synchronize()
+    times_ms.append(e0.elapsed_time(e1))
+    return out
+
+
+eng.resolve_qp_batch = timed
+md._resolve_windows(wins, False, 1, 1)
+md._resolve_windows(wins, False, 1, 1)
+it = md.last_resolve['iters']
+print(f'resolve_qp_kernel alone: {times_ms[-1]:.1f} ms for {len(wins)} windows ({len(wins) / times_ms[-1] * 1e3:.0f} windows/s, '
+      f'{np.mean(it):.1f} interior-point iterations per window, {times_ms[-1] / np.mean(it):.2f} ms per iteration of a wave)')
