@@ -468,29 +468,29 @@ __global__ void response_trapz_kernel(const double* __restrict__ times, const do
 // ---- derivative penalty matrices (mat1d.py:125-209, basis.py:382-395) ----------------------------
 __global__ void penalty_kernel(const double* __restrict__ grid, int n_grids, int nb, double eps, int toeplitz,
                                double* __restrict__ m) {
-    const long long per = (long long)nb * nb;
-    const long long total = (long long)n_grids * 3 * per;
+    // one thread per (grid, i, j): the three orders share the Gaussian factor; 32-bit index arithmetic (the round-1 form
+    // spent most of its instructions in 64-bit divisions and evaluated the exponential once per order)
+    const unsigned per = (unsigned)nb * (unsigned)nb;
     const double c = sqrt(3.141592653589793 / 2.0);
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(e % nb);
-        const int i = (int)((e / nb) % nb);
-        const int k = (int)((e / per) % 3);
-        const int g = (int)(e / (3 * per));
+    const double c0 = c * (1.0 / eps), c1 = -c * eps, c2 = c * (eps * eps * eps);
+    for (int g = blockIdx.y; g < n_grids; g += gridDim.y) {
         const double* x = grid + (size_t)g * nb;
-        double a;
-        if (toeplitz) {
-            const int d = i > j ? i - j : j - i;
-            a = eps * (x[0] - x[d]);
-        } else {
-            a = eps * (x[j] - x[i]);
+        double* out = m + (size_t)g * 3 * per;
+        for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
+            const unsigned i = e / (unsigned)nb, j = e - i * (unsigned)nb;
+            double a;
+            if (toeplitz) {
+                const unsigned d = i > j ? i - j : j - i;
+                a = eps * (x[0] - x[d]);
+            } else {
+                a = eps * (x[j] - x[i]);
+            }
+            const double a2 = a * a;
+            const double ex = exp(-(a2 / 2.0));
+            __stcs(out + e, c0 * ex);
+            __stcs(out + per + e, c1 * (-1.0 + a2) * ex);
+            __stcs(out + 2 * (size_t)per + e, c2 * (3.0 - 6.0 * a2 + a2 * a2) * ex);
         }
-        const double a2 = a * a;
-        const double ex = exp(-(a2 / 2.0));
-        double v;
-        if (k == 0) v = c * (1.0 / eps) * ex;
-        else if (k == 1) v = -c * eps * (-1.0 + a2) * ex;
-        else v = c * (eps * eps * eps) * (3.0 - 6.0 * a2 + a2 * a2) * ex;
-        m[e] = v;
     }
 }
 
@@ -527,7 +527,7 @@ __global__ void eis_vmm_kernel(const double* __restrict__ freq, int n_grids, int
 constexpr int kVRows = 32;   // rows per CTA, four per warp
 
 __global__ void chrono_vmm_kernel(const double* __restrict__ times, const double* __restrict__ step_times, int nt,
-                                  int n_steps, double vmm_eps, int uniform, double* __restrict__ vmm) {
+                                  int n_steps, double vmm_eps, int uniform, double* __restrict__ vmm, int staged) {
     extern __shared__ __align__(16) double sm[];
     double* s_tt = sm;                                       // [nt] transformed times
     double* s_off = sm + nt;                                 // [n_steps] segment offsets
@@ -582,6 +582,19 @@ __global__ void chrono_vmm_kernel(const double* __restrict__ times, const double
         const double tr = s_tt[r];
         const int sr = s_seg[r];
         double sum = 0.0;
+        if (staged) {
+            // the row is evaluated once (one exponential per entry) into this warp's staging row, then normalised on
+            // its way out; without the staging space (long traces) it is evaluated twice
+            double* s_row = reinterpret_cast<double*>(s_seg + nt + (nt & 1)) + (size_t)warp * nt;
+            for (int j = lane; j < nt; j += 32) {
+                const double v = (s_seg[j] == sr) ? rbf(tr - s_tt[j], vmm_eps) : 0.0;
+                s_row[j] = v;
+                sum += v;
+            }
+            sum = warp_sum(sum);
+            for (int j = lane; j < nt; j += 32) __stcs(out + (size_t)r * nt + j, s_row[j] / sum);
+            continue;
+        }
         for (int j = lane; j < nt; j += 32) sum += (s_seg[j] == sr) ? rbf(tr - s_tt[j], vmm_eps) : 0.0;
         sum = warp_sum(sum);
         for (int j = lane; j < nt; j += 32)
@@ -816,8 +829,9 @@ extern "C" int hdrt_build_penalty(const double* grid, int n_grids, int nb, doubl
                                   void* stream) {
     if (n_grids == 0) return HDRT_OK;
     if (!grid || !m || n_grids < 0 || nb <= 0) { set_error("hdrt_build_penalty: invalid argument"); return HDRT_ERR_ARG; }
-    const long long total = (long long)n_grids * 3 * nb * nb;
-    penalty_kernel<<<grid_for(total, kMThreads), kMThreads, 0, (cudaStream_t)stream>>>(grid, n_grids, nb, eps, toeplitz, m);
+    const unsigned per_blocks = ((unsigned)nb * (unsigned)nb + kMThreads - 1) / kMThreads;
+    dim3 pgrid(per_blocks < 64 ? per_blocks : 64, n_grids < 32768 ? n_grids : 32768);
+    penalty_kernel<<<pgrid, kMThreads, 0, (cudaStream_t)stream>>>(grid, n_grids, nb, eps, toeplitz, m);
     HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }
@@ -840,11 +854,17 @@ extern "C" int hdrt_build_chrono_vmm(const double* times, const double* step_tim
         return HDRT_ERR_ARG;
     }
     if (n_grids == 0) return HDRT_OK;
-    const size_t smem = sizeof(double) * ((size_t)nt + n_steps) + sizeof(int) * (size_t)nt;
+    size_t smem = sizeof(double) * ((size_t)nt + n_steps) + sizeof(int) * (size_t)nt;
     if (smem > 200 * 1024) { set_error("hdrt_build_chrono_vmm: %d samples do not fit the staging buffer", nt); return HDRT_ERR_UNSUPPORTED; }
+    const size_t staged_smem = sizeof(double) * ((size_t)nt + n_steps) + sizeof(int) * ((size_t)nt + (nt & 1)) +
+                               sizeof(double) * (size_t)nt * (kMThreads / 32);
+    // measured: staging the row costs the occupancy more than the second exponential costs the pipes (1.21 vs 1.50 TB/s
+    // at nt = 2000); it pays only while several CTAs still fit on an SM
+    const int staged = (!uniform && staged_smem <= 48 * 1024) ? 1 : 0;
+    if (staged) smem = staged_smem;
     HDRT_CUDA_CHECK(cudaFuncSetAttribute(chrono_vmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(n_grids, (nt + kVRows - 1) / kVRows);
-    chrono_vmm_kernel<<<grid, kMThreads, smem, (cudaStream_t)stream>>>(times, step_times, nt, n_steps, vmm_eps, uniform, vmm);
+    chrono_vmm_kernel<<<grid, kMThreads, smem, (cudaStream_t)stream>>>(times, step_times, nt, n_steps, vmm_eps, uniform, vmm, staged);
     HDRT_CUDA_CHECK(cudaGetLastError());
     return HDRT_OK;
 }

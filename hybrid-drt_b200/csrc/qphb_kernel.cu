@@ -105,9 +105,9 @@ struct Cfg {
 };
 
 using CfgS = Cfg<13, 2, 3>;  // n <= 104:  4 warps, 28 register tiles per warp, three CTAs per SM
-using CfgL = Cfg<20, 4, 1>;  // n <= 160: 16 warps, 15 register tiles per warp, one CTA per SM
+using CfgL = Cfg<20, 3, 1>;  // n <= 160: 3 x 3 warps, 28 register tiles per warp, one CTA per SM (4 x 4 warps: 128 registers, spills, -12 %)
 using CfgSX = Cfg<13, 2, 3, true>;   // the same with the optional paths compiled in
-using CfgLX = Cfg<20, 4, 1, true>;
+using CfgLX = Cfg<20, 3, 1, true>;
 
 __host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>

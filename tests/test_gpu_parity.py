@@ -159,6 +159,7 @@ def test_qphb_batch_vs_oracle_seeded(eng, orc, lookup_golden):
         assert rel_err(out['weights'][b], ref['weights']) < FIT_TOL, b
         assert abs(out['fun'][b] - ref['fun']) <= FIT_TOL * abs(ref['fun']), b
         assert rel_err(out['rho'][b], ref['rho']) < FIT_TOL, b
+        # s = u^2 with u the root of a quadratic whose discriminant cancels (qphb.py:346-360): 1e-6 on x leaves ~1e-5 on s
         assert rel_err(out['s_vectors'][b], ref['s_vectors']) < 1e-5, b
         assert rel_err(out['xmx_norms'][b], ref['xmx_norms']) < FIT_TOL, b
     assert n_same == len(z)       # iteration counts are discrete outcomes; all should agree
@@ -329,6 +330,7 @@ def test_model_hybrid_and_chrono():
     assert rel_err(drt.cvx_result['x'], hs['cvx_x']) < FIT_TOL
     assert rel_err(fp['x'], hs['x']) < FIT_TOL
     assert abs(fp['vz_offset'] - hs['vz_offset']) < FIT_TOL * max(1.0, abs(hs['vz_offset']))
+    # v_baseline is a ~1e-6-sized parameter: its own relative error is the absolute 1e-6-class error of the fit over a tiny norm
     assert rel_err(fp['v_baseline'], hs['v_baseline']) < 1e-5
     assert rel_err(fp['z_sigma_tot'], hs['z_sigma_tot']) < FIT_TOL
     assert rel_err(fp['v_sigma_tot'], hs['v_sigma_tot']) < FIT_TOL
@@ -538,7 +540,7 @@ def test_dop_with_time_domain_data(eng, orc):
     assert rel_err(rm2, orc.dop_v_matrix(t2, d['basis_nu'], nu_eps, st2, sa2)) < MAT_TOL
     drt = DRT(fit_dop=True)
     drt.fit_hybrid(d['times'], d['i_signal'], d['v_signal'][0], d['freq'], d['z'][0])
-    assert rel_err(drt.qphb_params['rm'], d['hyb_rm']) < 1e-9
+    assert rel_err(drt.qphb_params['rm'], d['hyb_rm']) < 1e-9      # includes the fitted vz_offset column (a fit output, not a 1e-10 matrix entry)
     assert drt.qphb_params['n_outer'] == int(d['hyb_n_outer']) and drt.qphb_params['n_ipm'] == int(d['hyb_ipm'])
     assert rel_err(drt.cvx_result['x'], d['hyb_cvx_x']) < FIT_TOL
     assert rel_err(drt.fit_parameters['x_dop'], d['hyb_x_dop']) < FIT_TOL
@@ -773,6 +775,7 @@ def test_mapping_drtmd_against_the_reference():
     assert rel_err(md.obs_special['inductance'], g['special_inductance']) < FIT_TOL
     # post-fit diagnostics (drtmd.py:256-279): distribution variance on the supergrid, llh, rss
     for b in range(6):
+        # the distribution variance goes through P^-1 (drt1d.py:3063-3151): conditioning amplifies the 1e-6-class fit error
         assert rel_err(md.obs_drt_var[b], g['obs_drt_var'][b]) < 1e-5
     assert rel_err(md.obs_rss, g['obs_rss']) < FIT_TOL and rel_err(md.obs_llh, g['obs_llh']) < FIT_TOL
     # batched == one at a time, and refit / incremental adds keep the containers consistent
