@@ -42,6 +42,20 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Eight per-lane partial sums -> eight warp totals in nine shuffles: lane l returns the total of v[l / 4].
+__device__ __forceinline__ double warp_reduce8(const double (&v)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    double k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = (b4 ? v[4 + i] : v[i]) + shfl_xor_d(b4 ? v[i] : v[4 + i], 16);
+    const double m0 = (b3 ? k[2] : k[0]) + shfl_xor_d(b3 ? k[0] : k[2], 8);
+    const double m1 = (b3 ? k[3] : k[1]) + shfl_xor_d(b3 ? k[1] : k[3], 8);
+    double t = (b2 ? m1 : m0) + shfl_xor_d(b2 ? m0 : m1, 4);
+    t += shfl_xor_d(t, 2);
+    t += shfl_xor_d(t, 1);
+    return t;
+}
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_xor_d(v, o));

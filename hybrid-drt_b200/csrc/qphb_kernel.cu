@@ -1354,6 +1354,61 @@ __device__ __forceinline__ double vmm_diag_at(const Ctx& c, int r) {
     return c.vmm_eis[(size_t)(r - c.nc) * ne + (r - c.nc)];
 }
 
+// Squared residuals of all rows into r2[]; with VZ the vz_offset column of a hybrid fit is rewritten from the same pass
+// (drt1d.py:972-979: the prediction without the vz_offset and v_baseline columns, sign by domain, times vz_strength).
+// The residual itself uses the column as it stood when the pass started.
+template <class C, bool VZ>
+__device__ __forceinline__ void residual_rows(const Ctx& c, const double (&xw)[(C::NV + 31) / 32], const double (&xv)[(C::NV + 31) / 32],
+                                              double x_vz) {
+    constexpr int CU = (C::NV + 31) / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = c.N, n = c.n;
+    double* r2 = C::rowr2(N);
+#pragma unroll 1
+    for (int rb = 8 * warp; rb < N; rb += 8 * C::kWarps) {
+        double v[8][CU];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double* __restrict__ src = c.rm + (size_t)min(rb + u, N - 1) * n;
+#pragma unroll
+            for (int w = 0; w < CU; ++w) v[u][w] = src[min(lane + 32 * w, n - 1)];
+        }
+        // the lanes with lane % 4 == 0 finish row rb + lane / 4
+        const int r = min(rb + (lane >> 2), N - 1);
+        const double rvr = C::EXT ? c.rv[r] * c.rv_scale : c.rv[r];
+        double vzr = 0.0, vzs = 0.0, vz0r = 0.0;
+        if (c.vz >= 0) vzr = c.vzcol[r];
+        if (VZ) {
+            vzs = c.vz_strength[r];
+            if (C::EXT && c.vz0 != nullptr) vz0r = c.vz0[r];
+        }
+        double acc[8], accv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc[u] = 0.0;
+            accv[u] = 0.0;
+#pragma unroll
+            for (int w = 0; w < CU; ++w) {
+                acc[u] = fma(v[u][w], xw[w], acc[u]);         // xw is zero beyond n and at column vz
+                if (VZ) accv[u] = fma(v[u][w], xv[w], accv[u]);
+            }
+        }
+        const double tot = warp_reduce8(acc, lane);
+        double totv = 0.0;
+        if (VZ) totv = warp_reduce8(accv, lane);
+        if ((lane & 3) == 0 && rb + (lane >> 2) < N) {
+            const double resid = fma(vzr, x_vz, tot) - rvr;
+            r2[r] = resid * resid;
+            if (VZ) {
+                // a continuation predicts with the vz_offset column it started from (drt1d.py:1296-1302 copies
+                // the matrix once, with that column in place); the plain fit copies it while it is still zero
+                const double pred = fma(vz0r, x_vz, totv);
+                c.vzcol[r] = ((r < c.nc) ? pred : -pred) * vzs;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Error-structure weights (qphb.estimate_weights, qphb.py:1545-1594) + vz_offset column rewrite
 // ------------------------------------------------------------------------------------------------
@@ -1364,58 +1419,31 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
     const int N = c.N, n = c.n, nc = c.nc;
     const double* xs = C::vec(C::XS);
     PROF_DECL;
-    // residuals: one warp per row, four rows per pass.  All loads of a pass (L2 hits, several hundred cycles
-    // each) are issued before the first use: row / column indices are clamped instead of branched around.
-    constexpr int RU = C::RU, CU = (C::NV + 31) / 32;
-    double xw[CU];     // this lane's coefficients (DOP ones with the column rescale of solve_rp folded in)
+    // residuals: a warp takes eight consecutive rows per pass.  All loads of a pass (L2 hits, several hundred cycles
+    // each) are issued before the first use -- row / column indices are clamped instead of branched around -- and the
+    // eight (sixteen, with the vz_offset prediction) row sums cross the warp in one transposed reduction.
+    constexpr int CU = (C::NV + 31) / 32;
+    double xw[CU];     // this lane's coefficients (DOP ones with the column rescale of solve_rp folded in); not column vz
+    double xv[CU];     // ... and without the v_baseline columns: the prediction that sets the vz_offset column
 #pragma unroll
     for (int w = 0; w < CU; ++w) {
         const int col = lane + 32 * w;
-        xw[w] = (col < n) ? xs[col] : 0.0;
+        xw[w] = (col < n && col != c.vz) ? xs[col] : 0.0;
         if (C::EXT && col >= c.dop_a && col < c.dop_b) xw[w] *= c.dop_cs;
+        xv[w] = (col < c.vb_a || col >= c.vb_b) ? xw[w] : 0.0;
     }
-    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
-        double v[RU][CU];
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const double* __restrict__ src = c.rm + (size_t)min(rb + u * C::kWarps, N - 1) * n;
-#pragma unroll
-            for (int w = 0; w < CU; ++w) v[u][w] = src[min(lane + 32 * w, n - 1)];
-        }
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const int r = min(rb + u * C::kWarps, N - 1);
-            double acc = 0.0, accv = 0.0;
-#pragma unroll
-            for (int w = 0; w < CU; ++w) {
-                const int col = lane + 32 * w;
-                if (col < n) {
-                    const double t = ((col == c.vz) ? c.vzcol[r] : v[u][w]) * xw[w];
-                    acc += t;
-                    if (col != c.vz && (col < c.vb_a || col >= c.vb_b)) accv += t;
-                }
-            }
-            acc = warp_sum(acc);
-            if (update_vz) accv = warp_sum(accv);
-            if (lane == 0 && rb + u * C::kWarps < N) {
-                const double resid = acc - (C::EXT ? c.rv[r] * c.rv_scale : c.rv[r]);
-                C::rowr2(c.N)[r] = resid * resid;
-                if (update_vz) {
-                    // a continuation predicts with the vz_offset column it started from (drt1d.py:1296-1302 copies
-                    // the matrix once, with that column in place); the plain fit copies it while it is still zero
-                    if (C::EXT && c.vz0 != nullptr) accv += c.vz0[r] * xs[c.vz];
-                    const double sep = (r < nc) ? accv : -accv;
-                    c.vzcol[r] = sep * c.vz_strength[r];
-                }
-            }
-        }
-    }
+    const double x_vz = (c.vz >= 0) ? xs[c.vz] : 0.0;
+    if (update_vz) residual_rows<C, true>(c, xw, xv, x_vz);
+    else residual_rows<C, false>(c, xw, xv, x_vz);
     __syncthreads();
     PROF_ADD(11);
+    constexpr int RU = C::RU;
     const bool uniform_chrono = nc > 0 && c.vmm_chrono == nullptr;
     const bool outl = C::EXT && c.outlier_p >= 0.0;
     base = C::EXT && base;
     const double* uin = C::rowr2(c.N);
+    // with the 'uniform' chrono error structure the chrono rows of vmm are never touched: their estimate is the mean
+    const int row0 = uniform_chrono ? nc : 0;
     if (outl) {
         // qphb.solve_outlier_t (qphb.py:1497-1519): s_bar = vmm r^2, t = 1 - P(outlier | r); the averaging matrix
         // then becomes T^1/2 vmm T^1/2 + (I - T) (qphb.outlier_tvt :1522-1538), applied below without forming it
@@ -1427,25 +1455,26 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
             block_reduce<C, 1, 0u>(t1, c);
             mean1 = t1[0] / (double)nc;
         }
-        for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+        auto outlier_row = [&](int r, double s_bar) {
+            const double r2 = uin[r];
+            if (base) { const double d = vmm_diag_at(c, r); s_bar = (s_bar - d * r2) / (1.0 - d); }
+            const double sd = sqrt(s_bar), ar = sqrt(r2);
+            const double k2pi = 2.5066282746310002;   // sqrt(2 pi)
+            const double pdf_in = 1.0 / (sd * k2pi) * exp(-0.5 * r2 / (sd * sd));
+            const double pdf_out = 1.0 / (ar * k2pi) * exp(-0.5 * r2 / (ar * ar));
+            double t = 1.0 - p * pdf_out / ((1.0 - p) * pdf_in + p * pdf_out);
+            if (sd > ar) t = 1.0;
+            c.t_out[r] = t;
+            C::rowu(c.N)[r] = sqrt(t) * r2;
+        };
+        for (int r = tid; r < row0; r += C::kThreads) outlier_row(r, mean1);
+        for (int rb = row0 + warp; rb < N; rb += RU * C::kWarps) {
             double sh[RU];
             vmm_rows<C>(c, uin, rb, sh);
 #pragma unroll
             for (int u = 0; u < RU; ++u) {
                 const int r = rb + u * C::kWarps;
-                if (lane == 0 && r < N) {
-                    const double r2 = uin[r];
-                    double s_bar = (r < nc && uniform_chrono) ? mean1 : sh[u];
-                    if (base) { const double d = vmm_diag_at(c, r); s_bar = (s_bar - d * r2) / (1.0 - d); }
-                    const double sd = sqrt(s_bar), ar = sqrt(r2);
-                    const double k2pi = 2.5066282746310002;   // sqrt(2 pi)
-                    const double pdf_in = 1.0 / (sd * k2pi) * exp(-0.5 * r2 / (sd * sd));
-                    const double pdf_out = 1.0 / (ar * k2pi) * exp(-0.5 * r2 / (ar * ar));
-                    double t = 1.0 - p * pdf_out / ((1.0 - p) * pdf_in + p * pdf_out);
-                    if (sd > ar) t = 1.0;
-                    c.t_out[r] = t;
-                    C::rowu(c.N)[r] = sqrt(t) * r2;
-                }
+                if (lane == 0 && r < N) outlier_row(r, sh[u]);
             }
         }
         __syncthreads();
@@ -1459,29 +1488,29 @@ __device__ __noinline__ void weights_phase(Ctx& cref, const double* est, double 
         chrono_mean = t1[0] / (double)nc;
     }
     // variance estimate s_hat = vmm_eff r2 (block diagonal: chrono rows x chrono columns, EIS rows x EIS columns)
-    for (int rb = warp; rb < N; rb += RU * C::kWarps) {
+    auto weight_row = [&](int r, double s_hat) {
+        if (base) { const double d = vmm_diag_at(c, r); s_hat = (s_hat - d * uin[r]) / (1.0 - d); }
+        if (outl) {
+            const double t = c.t_out[r];
+            s_hat = sqrt(t) * s_hat + (1.0 - t) * C::rowr2(c.N)[r];
+        }
+        if (s_hat < var_floor) s_hat = var_floor;
+        double w = 1.0 / sqrt(s_hat);
+        if (est != nullptr) {
+            const double e = est[r];
+            const double frac = w / (w + e);
+            w = frac * w + (1.0 - frac) * e;
+        }
+        C::roww()[r] = fmax(w, 1e-10);
+    };
+    for (int r = tid; r < row0; r += C::kThreads) weight_row(r, chrono_mean);
+    for (int rb = row0 + warp; rb < N; rb += RU * C::kWarps) {
         double sh[RU];
         vmm_rows<C>(c, uin, rb, sh);
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
             const int r = rb + u * C::kWarps;
-            double s_hat = sh[u];
-            if (r < nc && uniform_chrono) s_hat = chrono_mean;
-            if (lane == 0 && r < N) {
-                if (base) { const double d = vmm_diag_at(c, r); s_hat = (s_hat - d * uin[r]) / (1.0 - d); }
-                if (outl) {
-                    const double t = c.t_out[r];
-                    s_hat = sqrt(t) * s_hat + (1.0 - t) * C::rowr2(c.N)[r];
-                }
-                if (s_hat < var_floor) s_hat = var_floor;
-                double w = 1.0 / sqrt(s_hat);
-                if (est != nullptr) {
-                    const double e = est[r];
-                    const double frac = w / (w + e);
-                    w = frac * w + (1.0 - frac) * e;
-                }
-                C::roww()[r] = fmax(w, 1e-10);
-            }
+            if (lane == 0 && r < N) weight_row(r, sh[u]);
         }
     }
     __syncthreads();

@@ -1,7 +1,7 @@
 """Development aid: per-phase clock64 breakdown of the QPHB kernel (warp 0 of block 0).
 
 Builds a -DHDRT_PROFILE copy of the library next to the product one, runs a C2 batch and prints cycles per fit.
-usage (GPU box): python tools/phase_profile.py [batch]
+usage (GPU box): python tools/phase_profile.py [c2|c3|c4] [batch]
 """
 import ctypes as C
 import os
@@ -26,15 +26,27 @@ E.LIB_PATH = out
 from hybdrt_b200.models import DRT  # noqa: E402
 
 batch = int([a for a in sys.argv[1:] if a.isdigit()][0]) if any(a.isdigit() for a in sys.argv[1:]) else 444
-freq, z = synth.make_eis_batch(batch, seed=0)
-drt = DRT()
+which = ([a for a in sys.argv[1:] if a in ('c2', 'c3', 'c4')] or ['c2'])[0]
+if which == 'c2':
+    freq, z = synth.make_eis_batch(batch, seed=0)
+    drt = DRT()
+    fit = lambda: drt.fit_eis_batch(freq, z)
+elif which == 'c3':
+    t_, i_, v_, f_, z_ = synth.make_hybrid_batch(batch, seed=1)
+    drt = DRT()
+    fit = lambda: drt.fit_hybrid_batch(t_, i_, v_, f_, z_)
+else:
+    f_, z_ = synth.make_dop_batch(batch, seed=2)
+    drt = DRT(fit_dop=True)
+    fit = lambda: drt.fit_eis_batch(f_, z_)
 lib = E.load_library()
 lib.hdrt_debug_profile.argtypes = [C.c_void_p, C.c_int]
-drt.fit_eis_batch(freq, z)
+fit()
 torch.cuda.synchronize()
 lib.hdrt_debug_profile(None, 1)
-res = drt.fit_eis_batch(freq, z)
+res = fit()
 torch.cuda.synchronize()
+print('config', which, 'batch', batch, 'mean outer', float(res.host(['n_outer'])['n_outer'].mean()), 'mean ipm', float(res.host(['n_ipm'])['n_ipm'].mean()))
 buf = (C.c_ulonglong * 32)()
 lib.hdrt_debug_profile(buf, 0)
 v = np.array(list(buf), dtype=np.float64)
