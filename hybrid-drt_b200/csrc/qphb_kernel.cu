@@ -108,6 +108,10 @@ using CfgS = Cfg<13, 2, 3>;  // n <= 104:  4 warps, 28 register tiles per warp, 
 using CfgL = Cfg<20, 3, 1>;  // n <= 160: 3 x 3 warps, 28 register tiles per warp, one CTA per SM (4 x 4 warps: 128 registers, spills, -12 %)
 using CfgSX = Cfg<13, 2, 3, true>;   // the same with the optional paths compiled in
 using CfgLX = Cfg<20, 3, 1, true>;
+// Long problems (hybrid fits: thousands of chrono rows) leave room for two CTAs per SM at most: the same kernel with the
+// register budget of two (255 instead of 168: the Gram accumulators and fragments stay out of local memory)
+using CfgS2 = Cfg<13, 2, 2>;
+using CfgS2X = Cfg<13, 2, 2, true>;
 
 __host__ __device__ inline int rows_pad(int N) { return (N + 7) & ~7; }
 template <class C>
@@ -2147,7 +2151,11 @@ extern "C" int hdrt_qphb_fit_batch(hdrt_handle* h, const hdrt_qphb_problem* prob
         return HDRT_ERR_UNSUPPORTED;
     }
     if (warp_path_eligible(p, ext)) return launch_qphb_warp(h, p, st);
-    if (small_cfg(p.n_cols)) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
+    if (small_cfg(p.n_cols)) {
+        const bool three = 3 * ((size_t)smem + 64 + h->smem_reserved_per_cta) <= h->smem_per_sm;   // three CTAs per SM fit
+        if (three) return ext ? launch_qphb<CfgSX>(h, p, (size_t)smem, st) : launch_qphb<CfgS>(h, p, (size_t)smem, st);
+        return ext ? launch_qphb<CfgS2X>(h, p, (size_t)smem, st) : launch_qphb<CfgS2>(h, p, (size_t)smem, st);
+    }
     return ext ? launch_qphb<CfgLX>(h, p, (size_t)smem, st) : launch_qphb<CfgL>(h, p, (size_t)smem, st);
 }
 
