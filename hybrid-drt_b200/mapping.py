@@ -345,21 +345,31 @@ class DRTMD:
         if bad.any() and not ignore_errors:
             raise ValueError(f'Error encountered at obs_index {int(members[np.argmax(bad)])}: '
                              'Rank(A) < p or Rank([P; A; G]) < n')
-        good = members[~bad]
+        # the usual case -- every fit of the group fine, the group a run of consecutive observations (a whole map is one
+        # group) -- scatters with slices: block copies instead of index arrays over the full map on every rank
+        m0, nm = int(members[0]), len(members)
+        run = int(members[-1]) - m0 + 1 == nm and bool(np.all(np.diff(members) == 1))
+        clean = not bad.any()
+        sel = slice(None) if clean else ~bad
+        good = (slice(m0, m0 + nm) if run else members) if clean else members[~bad]
+        allm = slice(m0, m0 + nm) if run else members
         self.obs_x[good] = 0.0
-        self.obs_x[good, ..., left:right] = out['x'][~bad]
+        self.obs_x[good, ..., left:right] = out['x'][sel]
         for key in sp_keys:       # a vector parameter of size one (v_baseline with a single step) is stored as a scalar per observation
-            val = out['sp_' + key][~bad]
+            val = out['sp_' + key][sel]
             self.obs_special[key][good] = val.reshape((len(val), *self.special_param_shape(key)))
-        dv = out['drt_var'][~bad]                               # of the initial fit; one row per factor (drtmd.py:270)
+        dv = out['drt_var'][sel]                                # of the initial fit; one row per factor (drtmd.py:270)
         self.obs_drt_var[good] = dv[:, None, :] if self.fit_type == 'pfrt' else dv
-        self.obs_llh[good] = out['llh'][~bad]
-        self.obs_rss[good] = out['rss'][~bad]
+        self.obs_llh[good] = out['llh'][sel]
+        self.obs_rss[good] = out['rss'][sel]
         self.obs_fit_status[good] = True
-        self.obs_outer_iterations[members] = out['n_outer']
-        self.obs_status[members] = out['status']
-        for i in members:
-            self.obs_tau_indices[i] = (left, right)
+        self.obs_outer_iterations[allm] = out['n_outer']
+        self.obs_status[allm] = out['status']
+        if run:
+            self.obs_tau_indices[m0:m0 + nm] = [(left, right)] * nm
+        else:
+            for i in members:
+                self.obs_tau_indices[i] = (left, right)
         for i in members[bad]:
             self.obs_fit_status[i] = False
             self.obs_ignore_flag[i] = True

@@ -40,34 +40,63 @@ def gather_results(local, n_items, interleave=False, dst=None):
     Returns a dict of numpy arrays of leading size ``n_items`` on every rank (``dst=None``, all-gather) or on
     rank ``dst`` only (others get None).  Shards may have different sizes: they are padded to the largest one
     for the collective and trimmed afterwards.
+
+    One collective per dtype: the arrays of a dtype travel as the columns of one packed matrix; the rows are put back
+    into item order on the device (one index_select) and every result leaves it as one contiguous device -> host copy.
     """
     rank, ws = world()
     if ws == 1:
         return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in local.items()}
-    backend = dist.get_backend()
-    counts = [len(shard_indices(n_items, ws, r, interleave)) for r in range(ws)]
+    nccl = dist.get_backend() == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if nccl else torch.device('cpu')
+    idx = [shard_indices(n_items, ws, r, interleave) for r in range(ws)]
+    counts = [len(i) for i in idx]
     cmax = max(counts)
-    out = {}
+    # row of item i in the stacked (ws * cmax) layout of the collective
+    in_order = (not interleave) and all(c == cmax for c in counts)
+    pos = None
+    if not in_order:
+        pos_np = np.empty(n_items, dtype=np.int64)
+        for r in range(ws):
+            pos_np[idx[r]] = r * cmax + np.arange(counts[r])
+        pos = torch.from_numpy(pos_np).to(dev)
+    tensors, groups = {}, {}
     for name in sorted(local):
         v = local[name]
-        t = v if isinstance(v, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(v))
-        if backend == 'nccl' and not t.is_cuda:
-            t = t.cuda()
-        if backend != 'nccl' and t.is_cuda:
-            t = t.cpu()
-        pad = torch.zeros((cmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        if dst is None:
-            bufs = [torch.empty_like(pad) for _ in range(ws)]
-            dist.all_gather(bufs, pad)
+        t = v.detach() if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+        t = t.to(dev)
+        if t.shape[0] != counts[rank]:
+            raise ValueError(f'{name}: {t.shape[0]} rows for a shard of {counts[rank]}')
+        tensors[name] = t
+        groups.setdefault(t.dtype, []).append(name)
+    receives = dst is None or rank == dst
+    out = {name: None for name in tensors}
+    for dtype, names in groups.items():
+        cols = [tensors[nm].reshape(counts[rank], int(np.prod(tensors[nm].shape[1:], dtype=np.int64))) for nm in names]
+        widths = [c.shape[1] for c in cols]
+        k = sum(widths)
+        if len(cols) == 1 and counts[rank] == cmax:
+            pad = cols[0].contiguous()
         else:
-            bufs = [torch.empty_like(pad) for _ in range(ws)] if rank == dst else None
-            dist.gather(pad, bufs, dst=dst)
-            if rank != dst:
-                out[name] = None
-                continue
-        full = np.empty((n_items,) + tuple(t.shape[1:]), dtype=pad.cpu().numpy().dtype)
-        for r in range(ws):
-            full[shard_indices(n_items, ws, r, interleave)] = bufs[r][:counts[r]].cpu().numpy()
-        out[name] = full
+            pad = torch.zeros((cmax, k), dtype=dtype, device=dev)
+            off = 0
+            for c, w in zip(cols, widths):
+                pad[:counts[rank], off:off + w] = c
+                off += w
+        big = torch.empty((ws * cmax, k), dtype=dtype, device=dev) if receives else None
+        if dst is None:
+            if nccl:
+                dist.all_gather_into_tensor(big, pad)
+            else:
+                dist.all_gather(list(big.view(ws, cmax, k).unbind(0)), pad)
+        else:
+            dist.gather(pad, list(big.view(ws, cmax, k).unbind(0)) if receives else None, dst=dst)
+        if not receives:
+            continue
+        ordered = big[:n_items] if in_order else big.index_select(0, pos)
+        off = 0
+        for nm, w in zip(names, widths):
+            part = ordered if len(names) == 1 else ordered[:, off:off + w].contiguous()
+            out[nm] = part.cpu().numpy().reshape((n_items,) + tuple(tensors[nm].shape[1:]))
+            off += w
     return out
