@@ -463,7 +463,7 @@ def run_gpu(args):
         r = drt.fit_eis_batch(freq, z)
         fp = r.fit_parameters()                             # D2H of x and weights + unscaling on the host
         if world > 1:                                       # the path's only collective: results to rank 0 (NCCL)
-            sharding.gather_results({'x': r.raw['x'], 'weights': r.raw['weights']}, world * B, dst=0)
+            sharding.gather_results({'x': r.raw['x'], 'weights': r.raw['weights']}, world * B, dst=0, copy=False)
         return r, fp
 
     for _ in range(args.warmup):

@@ -331,7 +331,7 @@ class DRTMD:
                 if key in res.scales:
                     self.obs_scales.setdefault(key, np.zeros(self._n))[members] = np.asarray(res.scales[key])[:nloc]
         if ws > 1:
-            out = _sharding.gather_results(out, len(members), interleave=True)
+            out = _sharding.gather_results(out, len(members), interleave=True, copy=False)   # scattered into obs_* right below
         # ---- scatter into the observation arrays (drtmd.py:256-287)
         if self.obs_special is None:
             self.obs_special = {}

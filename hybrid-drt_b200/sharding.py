@@ -33,7 +33,20 @@ def shard_indices(n_items, world_size, rank, interleave=False):
     return np.arange(start, start + base + (1 if rank < extra else 0))
 
 
-def gather_results(local, n_items, interleave=False, dst=None):
+_PINNED = {}          # (name, shape, dtype) -> page-locked staging tensor of the device -> host copies (a handful of them)
+
+
+def _staging(name, shape, dtype):
+    key = (name, tuple(shape), dtype)        # per result name: two results of one gather never share a buffer
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) >= 32:
+            _PINNED.pop(next(iter(_PINNED)))
+        buf = _PINNED[key] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    return buf
+
+
+def gather_results(local, n_items, interleave=False, dst=None, copy=True):
     """Reassemble per-rank result arrays into full-batch arrays.
 
     ``local``: dict name -> array / tensor whose first axis is this rank's shard (in shard_indices order).
@@ -42,7 +55,9 @@ def gather_results(local, n_items, interleave=False, dst=None):
     for the collective and trimmed afterwards.
 
     One collective per dtype: the arrays of a dtype travel as the columns of one packed matrix; the rows are put back
-    into item order on the device (one index_select) and every result leaves it as one contiguous device -> host copy.
+    into item order on the device (one index_select) and every result leaves it as one contiguous device -> host copy
+    through a cached page-locked buffer.  ``copy=False`` returns views of those buffers: valid until the next gather of
+    the same shapes -- for callers that consume the arrays at once (the map scatter); the default copies them out.
     """
     rank, ws = world()
     if ws == 1:
@@ -97,6 +112,12 @@ def gather_results(local, n_items, interleave=False, dst=None):
         off = 0
         for nm, w in zip(names, widths):
             part = ordered if len(names) == 1 else ordered[:, off:off + w].contiguous()
-            out[nm] = part.cpu().numpy().reshape((n_items,) + tuple(tensors[nm].shape[1:]))
+            if part.is_cuda:
+                host = _staging(nm, part.shape, part.dtype)
+                host.copy_(part)
+                arr = host.numpy().copy() if copy else host.numpy()
+            else:
+                arr = part.numpy()
+            out[nm] = arr.reshape((n_items,) + tuple(tensors[nm].shape[1:]))
             off += w
     return out
