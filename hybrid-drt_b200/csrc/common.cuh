@@ -56,6 +56,10 @@ __device__ __forceinline__ double warp_reduce8(const double (&v)[8], int lane) {
     return t;
 }
 
+// max(t, v) for a running maximum t that is never NaN; a NaN v is skipped, as fmax would.  One compare and two selects
+// where fmax on doubles is eight instructions on this target.
+__device__ __forceinline__ double dmax_run(double t, double v) { return (v > t) ? v : t; }
+
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_xor_d(v, o));
