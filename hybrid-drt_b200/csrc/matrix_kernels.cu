@@ -132,7 +132,8 @@ __global__ void impedance_interp_global_kernel(const double* __restrict__ freq, 
 // shared-memory loads -- no log, no division: the kernel is bound by the HBM writes.  ln(omega tau) is formed as
 // ln(omega) + ln(tau); the reference itself evaluates entries either way (full evaluation, or first row / column
 // + Toeplitz fill, mat1d.py:341-372), the two differ at the 1e-16 level.
-// A work item is `rows_per_item` rows of one grid; stores are 16-byte, streaming (the output is not re-read).
+// A work item is `rows_per_item` rows of one grid; stores are 8-byte, streaming (the output is not re-read): consecutive
+// threads write consecutive columns, a warp instruction covers 256 contiguous bytes.
 struct SmemTable {
     const double* x;      // knots
     const double2* sc;    // per interval: slope, intercept (v_j - slope x_j): the interpolant is fma(slope, x, intercept)
